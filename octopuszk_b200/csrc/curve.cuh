@@ -1,0 +1,208 @@
+// BN254a group arithmetic for G1 (over Fq) and G2 (over Fq2 = Fq[u]/(u^2+1)), y^2 = x^3 + b, a = 0.
+//
+// The reference works in Jacobian coordinates with add-2007-bl / dbl-2009-l (BNG1.java:38-97,133-161,
+// BNG2.java:43-126; CUDA copies at algebra_msm_VariableBaseMSM.cu:278-623).  Parity is equality of group
+// elements (BNG1.equals compares projectively, BNG1.java:191-224), so the device code is free to use cheaper
+// representations: affine inputs (after a batched inversion), XYZZ accumulators (x = X/ZZ, y = Y/ZZZ,
+// ZZ^3 = ZZZ^2; mixed add 8M+2S instead of 11M+5S), and Jacobian only on the wire.
+#pragma once
+#include "fp256.cuh"
+
+namespace ozk {
+
+// ---- Fq2 (algebra/fields/Fp2.java:44-118 with non-residue p-1, BN254aFq2Parameters.java:38) ---------------
+struct Fq2 {
+    Fq c0, c1;
+    OZK_HD static Fq2 zero() { return {Fq::zero(), Fq::zero()}; }
+    OZK_HD static Fq2 one() { return {Fq::one(), Fq::zero()}; }
+    OZK_HD bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+    OZK_HD bool operator==(const Fq2& b) const { return c0 == b.c0 && c1 == b.c1; }
+    OZK_HD bool operator!=(const Fq2& b) const { return !(*this == b); }
+    OZK_HD static Fq2 add(const Fq2& a, const Fq2& b) { return {Fq::add(a.c0, b.c0), Fq::add(a.c1, b.c1)}; }
+    OZK_HD static Fq2 sub(const Fq2& a, const Fq2& b) { return {Fq::sub(a.c0, b.c0), Fq::sub(a.c1, b.c1)}; }
+    OZK_HD static Fq2 dbl(const Fq2& a) { return {Fq::dbl(a.c0), Fq::dbl(a.c1)}; }
+    OZK_HD static Fq2 neg(const Fq2& a) { return {Fq::neg(a.c0), Fq::neg(a.c1)}; }
+    // Karatsuba, u^2 = -1: (a0 b0 - a1 b1) + ((a0+a1)(b0+b1) - a0 b0 - a1 b1) u
+    OZK_HD static Fq2 mul(const Fq2& a, const Fq2& b) {
+        Fq t0 = Fq::mul(a.c0, b.c0);
+        Fq t1 = Fq::mul(a.c1, b.c1);
+        Fq t2 = Fq::mul(Fq::add(a.c0, a.c1), Fq::add(b.c0, b.c1));
+        return {Fq::sub(t0, t1), Fq::sub(Fq::sub(t2, t0), t1)};
+    }
+    // complex squaring: (a0+a1)(a0-a1) + 2 a0 a1 u
+    OZK_HD static Fq2 sqr(const Fq2& a) {
+        Fq t = Fq::mul(a.c0, a.c1);
+        Fq s = Fq::mul(Fq::add(a.c0, a.c1), Fq::sub(a.c0, a.c1));
+        return {s, Fq::dbl(t)};
+    }
+    // Fp2.inverse (Fp2.java:109-118): conj(a) / (a0^2 + a1^2)
+    OZK_HD static Fq2 inv(const Fq2& a) {
+        Fq n = Fq::add(Fq::sqr(a.c0), Fq::sqr(a.c1));
+        Fq ni = Fq::inv(n);
+        return {Fq::mul(a.c0, ni), Fq::neg(Fq::mul(a.c1, ni))};
+    }
+    OZK_HD static Fq2 to_mont(const Fq2& a) { return {Fq::to_mont(a.c0), Fq::to_mont(a.c1)}; }
+    OZK_HD static Fq2 from_mont(const Fq2& a) { return {Fq::from_mont(a.c0), Fq::from_mont(a.c1)}; }
+    OZK_HD bool is_canonical() const { return c0.is_canonical() && c1.is_canonical(); }
+};
+
+// ---- point representations --------------------------------------------------------------------------------
+// Affine: infinity is encoded as (0, 0), which is on neither curve (b != 0).
+template <class F>
+struct Affine {
+    F x, y;
+    OZK_HD bool is_inf() const { return x.is_zero() && y.is_zero(); }
+    OZK_HD static Affine inf() { return {F::zero(), F::zero()}; }
+};
+
+// Jacobian (the reference's wire representation): x = X/Z^2, y = Y/Z^3; infinity iff Z == 0 (BNG1.java:103-105).
+template <class F>
+struct Jacobian {
+    F x, y, z;
+    OZK_HD bool is_inf() const { return z.is_zero(); }
+    OZK_HD static Jacobian inf() { return {F::zero(), F::one(), F::zero()}; }   // (0,1,0), BN254aG1Parameters.java:52-55
+};
+
+// XYZZ accumulator: infinity iff ZZ == 0.
+template <class F>
+struct XYZZ {
+    F x, y, zz, zzz;
+    OZK_HD bool is_inf() const { return zz.is_zero(); }
+    OZK_HD static XYZZ inf() { return {F::zero(), F::zero(), F::zero(), F::zero()}; }
+    OZK_HD static XYZZ from_affine(const Affine<F>& p) {
+        if (p.is_inf()) return inf();
+        return {p.x, p.y, F::one(), F::one()};
+    }
+};
+
+// 2 * (affine) -> XYZZ  (EFD mdbl-2008-s-1, a = 0).  p must not be infinity; y != 0 on a prime-order curve.
+template <class F>
+OZK_HD XYZZ<F> xyzz_dbl_affine(const Affine<F>& p) {
+    F U = F::dbl(p.y);
+    F V = F::sqr(U);
+    F W = F::mul(U, V);
+    F S = F::mul(p.x, V);
+    F xx = F::sqr(p.x);
+    F M = F::add(F::dbl(xx), xx);
+    XYZZ<F> r;
+    r.x = F::sub(F::sqr(M), F::dbl(S));
+    r.y = F::sub(F::mul(M, F::sub(S, r.x)), F::mul(W, p.y));
+    r.zz = V;
+    r.zzz = W;
+    return r;
+}
+
+// 2 * XYZZ (EFD dbl-2008-s-1, a = 0)
+template <class F>
+OZK_HD XYZZ<F> xyzz_dbl(const XYZZ<F>& p) {
+    if (p.is_inf()) return p;
+    F U = F::dbl(p.y);
+    F V = F::sqr(U);
+    F W = F::mul(U, V);
+    F S = F::mul(p.x, V);
+    F xx = F::sqr(p.x);
+    F M = F::add(F::dbl(xx), xx);
+    XYZZ<F> r;
+    r.x = F::sub(F::sqr(M), F::dbl(S));
+    r.y = F::sub(F::mul(M, F::sub(S, r.x)), F::mul(W, p.y));
+    r.zz = F::mul(V, p.zz);
+    r.zzz = F::mul(W, p.zzz);
+    return r;
+}
+
+// acc += (affine) q   (EFD madd-2008-s, 8M + 2S) with the special cases the reference handles explicitly in
+// BNG1.add (BNG1.java:42-81): O + q, acc + O, acc == q (double), acc == -q (infinity).
+template <class F>
+OZK_HD void xyzz_madd(XYZZ<F>& acc, const Affine<F>& q) {
+    if (q.is_inf()) return;
+    if (acc.is_inf()) {
+        acc = {q.x, q.y, F::one(), F::one()};
+        return;
+    }
+    F U2 = F::mul(q.x, acc.zz);
+    F S2 = F::mul(q.y, acc.zzz);
+    F Pp = F::sub(U2, acc.x);
+    F Rr = F::sub(S2, acc.y);
+    if (Pp.is_zero()) {
+        if (Rr.is_zero()) acc = xyzz_dbl_affine(q);
+        else acc = XYZZ<F>::inf();
+        return;
+    }
+    F PP = F::sqr(Pp);
+    F PPP = F::mul(Pp, PP);
+    F Q = F::mul(acc.x, PP);
+    F X3 = F::sub(F::sub(F::sqr(Rr), PPP), F::dbl(Q));
+    F Y3 = F::sub(F::mul(Rr, F::sub(Q, X3)), F::mul(acc.y, PPP));
+    acc.x = X3;
+    acc.y = Y3;
+    acc.zz = F::mul(acc.zz, PP);
+    acc.zzz = F::mul(acc.zzz, PPP);
+}
+
+// acc += q (both XYZZ)  (EFD add-2008-s, 12M + 2S) with the same special cases.
+template <class F>
+OZK_HD void xyzz_add(XYZZ<F>& acc, const XYZZ<F>& q) {
+    if (q.is_inf()) return;
+    if (acc.is_inf()) {
+        acc = q;
+        return;
+    }
+    F U1 = F::mul(acc.x, q.zz);
+    F U2 = F::mul(q.x, acc.zz);
+    F S1 = F::mul(acc.y, q.zzz);
+    F S2 = F::mul(q.y, acc.zzz);
+    F Pp = F::sub(U2, U1);
+    F Rr = F::sub(S2, S1);
+    if (Pp.is_zero()) {
+        if (Rr.is_zero()) acc = xyzz_dbl(acc);
+        else acc = XYZZ<F>::inf();
+        return;
+    }
+    F PP = F::sqr(Pp);
+    F PPP = F::mul(Pp, PP);
+    F Q = F::mul(U1, PP);
+    F X3 = F::sub(F::sub(F::sqr(Rr), PPP), F::dbl(Q));
+    F Y3 = F::sub(F::mul(Rr, F::sub(Q, X3)), F::mul(S1, PPP));
+    acc.x = X3;
+    acc.y = Y3;
+    acc.zz = F::mul(F::mul(acc.zz, q.zz), PP);
+    acc.zzz = F::mul(F::mul(acc.zzz, q.zzz), PPP);
+}
+
+template <class F>
+OZK_HD Affine<F> affine_neg(const Affine<F>& p) {
+    return {p.x, F::neg(p.y)};
+}
+
+// XYZZ -> Jacobian without an inversion: choose Z = ZZ*ZZZ (= z^5), then X_j = x Z^2 = X ZZ ZZZ^2 and
+// Y_j = y Z^3 = Y ZZ^3 ZZZ^2.  Any representative is acceptable on the wire (projective equality).
+template <class F>
+OZK_HD Jacobian<F> xyzz_to_jacobian(const XYZZ<F>& p) {
+    if (p.is_inf()) return Jacobian<F>::inf();
+    F zzz2 = F::sqr(p.zzz);
+    F t = F::mul(p.zz, zzz2);          // ZZ ZZZ^2
+    Jacobian<F> r;
+    r.x = F::mul(p.x, t);
+    r.y = F::mul(F::mul(p.y, t), F::sqr(p.zz));
+    r.z = F::mul(p.zz, p.zzz);
+    return r;
+}
+
+// XYZZ -> affine with one field inversion.
+template <class F>
+OZK_HD Affine<F> xyzz_to_affine(const XYZZ<F>& p) {
+    if (p.is_inf()) return Affine<F>::inf();
+    F i = F::inv(F::mul(p.zz, p.zzz));      // 1/(ZZ ZZZ)
+    F izz = F::mul(i, p.zzz);
+    F izzz = F::mul(i, p.zz);
+    return {F::mul(p.x, izz), F::mul(p.y, izzz)};
+}
+
+using G1Affine = Affine<Fq>;
+using G2Affine = Affine<Fq2>;
+using G1XYZZ = XYZZ<Fq>;
+using G2XYZZ = XYZZ<Fq2>;
+using G1Jac = Jacobian<Fq>;
+using G2Jac = Jacobian<Fq2>;
+
+}  // namespace ozk
