@@ -1,0 +1,92 @@
+// Internal (non-ABI) definitions shared by the .cu translation units of liboctozk.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/octozk.h"
+
+namespace ozk {
+
+void set_error(const char* fmt, ...);
+
+#define OZK_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            ::ozk::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return OZK_ERR_CUDA;                                                                    \
+        }                                                                                           \
+    } while (0)
+
+#define OZK_TRY(call)              \
+    do {                           \
+        int rc__ = (call);         \
+        if (rc__ != OZK_OK) return rc__; \
+    } while (0)
+
+#define OZK_ARG(cond, msg)                 \
+    do {                                   \
+        if (!(cond)) {                     \
+            ::ozk::set_error("%s", msg);   \
+            return OZK_ERR_ARG;            \
+        }                                  \
+    } while (0)
+
+// A grow-only device buffer.  Growing synchronises the stream first (the old block may still be in use).
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int reserve(size_t need, cudaStream_t s) {
+        if (need <= bytes) return OZK_OK;
+        if (p) {
+            OZK_CUDA(cudaStreamSynchronize(s));
+            OZK_CUDA(cudaFree(p));
+            p = nullptr;
+            bytes = 0;
+        }
+        size_t want = need + need / 8;
+        OZK_CUDA(cudaMalloc(&p, want));
+        bytes = want;
+        return OZK_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
+
+struct NttPlan;
+struct FixedTable;
+
+}  // namespace ozk
+
+// The context: one per (thread, device) user.  Re-entrancy contract: a context must not be
+// used from two threads at once; separate contexts are independent (own stream, own scratch, own caches).
+struct ozk_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // scratch
+    ozk::DevBuf io_a, io_b, io_c, io_out;     // staging for the host-pointer entry points
+    ozk::DevBuf work;                          // NTT ping-pong buffer
+    ozk::DevBuf msm[12];                       // MSM pipeline buffers (see msm.cu)
+    ozk::DevBuf fb[4];                         // fixed-base buffers
+    void* pinned = nullptr;                    // small pinned host block for flags / results
+    std::map<std::string, ozk::NttPlan*> ntt_plans;
+    std::map<std::string, ozk::FixedTable*> fixed_tables;
+};
+
+namespace ozk {
+// activates ctx->device for the calling thread
+int ctx_enter(ozk_ctx* ctx);
+}  // namespace ozk

@@ -5,13 +5,14 @@
 // thread per element and explicit mad.lo.cc/madc.hi.cc chains.  Values are kept fully reduced in [0, m) so that
 // "canonical out"  only needs a from-Montgomery multiply.
 #pragma once
+#include "chains.cuh"
 #include "consts.cuh"
 #include "ptx_arith.cuh"
 
 namespace ozk {
 
 template <class P>
-struct Fp {
+struct alignas(16) Fp {
     uint32_t v[8];
 
     // ---- constants ---------------------------------------------------------------------------------------
@@ -50,45 +51,41 @@ struct Fp {
     OZK_HD bool operator!=(const Fp& b) const { return !(*this == b); }
 
     // ---- add / sub (inputs and outputs in [0, m)) ---------------------------------------------------------
-    OZK_HD static Fp add(const Fp& a, const Fp& b) {
-        using namespace ptx;
-        uint32_t s[8], d[8];
-        s[0] = add_cc(a.v[0], b.v[0]);
+    OZK_HD static void load_mod(uint32_t (&m)[8]) {
 #pragma unroll
-        for (int i = 1; i < 7; i++) s[i] = addc_cc(a.v[i], b.v[i]);
-        s[7] = addc(a.v[7], b.v[7]);                 // a + b < 2m < 2^255: no carry out
-        d[0] = sub_cc(s[0], P::mod(0));
-#pragma unroll
-        for (int i = 1; i < 8; i++) d[i] = subc_cc(s[i], P::mod(i));
-        uint32_t borrow = subc(0u, 0u);              // 0xffffffff when s < m
+        for (int i = 0; i < 8; i++) m[i] = P::mod(i);
+    }
+    // r = s >= m ? s - m : s
+    OZK_HD static Fp reduce_once(const uint32_t (&s)[8]) {
+        uint32_t m[8], d[8], bw;
+        load_mod(m);
+        chain::sub8(d, bw, s, m);
         Fp r;
 #pragma unroll
-        for (int i = 0; i < 8; i++) r.v[i] = borrow ? s[i] : d[i];
+        for (int i = 0; i < 8; i++) r.v[i] = bw ? s[i] : d[i];
         return r;
     }
+    OZK_HD static Fp add(const Fp& a, const Fp& b) {
+        uint32_t s[8];
+        chain::add8(s, a.v, b.v);                    // a + b < 2m < 2^255: no carry out
+        return reduce_once(s);
+    }
     OZK_HD static Fp sub(const Fp& a, const Fp& b) {
-        using namespace ptx;
-        uint32_t d[8];
-        d[0] = sub_cc(a.v[0], b.v[0]);
+        uint32_t d[8], mm[8], bw;
+        chain::sub8(d, bw, a.v, b.v);
 #pragma unroll
-        for (int i = 1; i < 8; i++) d[i] = subc_cc(a.v[i], b.v[i]);
-        uint32_t mask = subc(0u, 0u);                // all ones when a < b
+        for (int i = 0; i < 8; i++) mm[i] = P::mod(i) & bw;   // add the modulus back when a < b
         Fp r;
-        r.v[0] = add_cc(d[0], P::mod(0) & mask);
-#pragma unroll
-        for (int i = 1; i < 7; i++) r.v[i] = addc_cc(d[i], P::mod(i) & mask);
-        r.v[7] = addc(d[7], P::mod(7) & mask);
+        chain::add8(r.v, d, mm);
         return r;
     }
     OZK_HD static Fp dbl(const Fp& a) { return add(a, a); }
     OZK_HD static Fp neg(const Fp& a) {
         if (a.is_zero()) return a;
-        using namespace ptx;
+        uint32_t m[8], bw;
+        load_mod(m);
         Fp r;
-        r.v[0] = sub_cc(P::mod(0), a.v[0]);
-#pragma unroll
-        for (int i = 1; i < 7; i++) r.v[i] = subc_cc(P::mod(i), a.v[i]);
-        r.v[7] = subc(P::mod(7), a.v[7]);
+        chain::sub8(r.v, bw, m, a.v);
         return r;
     }
 
@@ -96,88 +93,45 @@ struct Fp {
     // Operand scanning with the reduction interleaved.  The running sum T is held as two 8-limb accumulators,
     // `e` aligned at limb 0 and `o` aligned at limb 1 (T = e + o * 2^32): products a[j]*b_i with even j land in
     // `e`, with odd j in `o`, so every 64-bit product is added by one lo/hi pair on a single carry chain
-    // (= one IMAD.WIDE.X each).  After a round T is divisible by 2^32; dropping the zero limb makes the old `o`
+    // (= one IMAD.WIDE.U32.X each).  After a round T is divisible by 2^32; dropping the zero limb makes the old `o`
     // the new limb-0 accumulator, so the two arrays swap roles every round.  T < 2m throughout, which is why the
-    // `o` chains can never carry out and the `e` chains carry into o[7].
+    // `o` chains can never carry out and the `e` chains carry into o[7].  (chains.cuh holds the two blocks.)
     // Cost: 8 rounds x (16 wide multiply-adds + 1 low multiply) = 136 integer-pipe multiplies.
-    struct Acc {
-        uint32_t e[8], o[8];
-    };
-    template <bool FIRST>
-    OZK_HD static void round(uint32_t* e, uint32_t* o, const uint32_t* a, uint32_t bi) {
-        using namespace ptx;
-        // On entry (FIRST == false): `o` is last round's limb-0 accumulator (its limb 0 is zero, limb 1 still has to
-        // be folded into e[0]) and `e` is last round's limb-1 accumulator, i.e. already this round's limb-0 one.
-        if (FIRST) {
-#pragma unroll
-            for (int j = 0; j < 8; j += 2) {
-                e[j] = mul_lo(a[j], bi);
-                e[j + 1] = mul_hi(a[j], bi);
-                o[j] = mul_lo(a[j + 1], bi);
-                o[j + 1] = mul_hi(a[j + 1], bi);
-            }
-        } else {
-            e[0] = add_cc(e[0], o[1]);
-            // new limb-1 accumulator = (old limb-0 accumulator >> 64) + odd products, carry from the fold above
-#pragma unroll
-            for (int j = 0; j < 6; j += 2) {
-                o[j] = madc_lo_cc(a[j + 1], bi, o[j + 2]);
-                o[j + 1] = madc_hi_cc(a[j + 1], bi, o[j + 3]);
-            }
-            o[6] = madc_lo_cc(a[7], bi, 0u);
-            o[7] = madc_hi(a[7], bi, 0u);
-            e[0] = mad_lo_cc(a[0], bi, e[0]);
-            e[1] = madc_hi_cc(a[0], bi, e[1]);
-#pragma unroll
-            for (int j = 2; j < 8; j += 2) {
-                e[j] = madc_lo_cc(a[j], bi, e[j]);
-                e[j + 1] = madc_hi_cc(a[j], bi, e[j + 1]);
-            }
-            o[7] = addc(o[7], 0u);
-        }
-        uint32_t m = mul_lo(e[0], P::NP0);
-        o[0] = mad_lo_cc(P::mod(1), m, o[0]);
-        o[1] = madc_hi_cc(P::mod(1), m, o[1]);
-#pragma unroll
-        for (int j = 2; j < 8; j += 2) {
-            o[j] = madc_lo_cc(P::mod(j + 1), m, o[j]);
-            o[j + 1] = madc_hi_cc(P::mod(j + 1), m, o[j + 1]);
-        }
-        e[0] = mad_lo_cc(P::mod(0), m, e[0]);
-        e[1] = madc_hi_cc(P::mod(0), m, e[1]);
-#pragma unroll
-        for (int j = 2; j < 8; j += 2) {
-            e[j] = madc_lo_cc(P::mod(j), m, e[j]);
-            e[j + 1] = madc_hi_cc(P::mod(j), m, e[j + 1]);
-        }
-        o[7] = addc(o[7], 0u);
-    }
-
     OZK_HD static Fp mul(const Fp& a, const Fp& b) {
-        using namespace ptx;
-        uint32_t x[8], y[8];
-        round<true>(x, y, a.v, b.v[0]);
-        round<false>(y, x, a.v, b.v[1]);
-        round<false>(x, y, a.v, b.v[2]);
-        round<false>(y, x, a.v, b.v[3]);
-        round<false>(x, y, a.v, b.v[4]);
-        round<false>(y, x, a.v, b.v[5]);
-        round<false>(x, y, a.v, b.v[6]);
-        round<false>(y, x, a.v, b.v[7]);
-        // after the last round: y was the limb-0 accumulator (y[0] == 0), x the limb-1 one.  T / 2^32 = x + (y >> 32).
-        uint32_t s[8], d[8];
-        s[0] = add_cc(x[0], y[1]);
+        uint32_t x[8], y[8], m[8];
+        load_mod(m);
+        // round 0: plain products, nothing to accumulate yet (x: limb-0 accumulator, y: limb-1 accumulator)
 #pragma unroll
-        for (int i = 1; i < 7; i++) s[i] = addc_cc(x[i], y[i + 1]);
-        s[7] = addc(x[7], 0u);
-        d[0] = sub_cc(s[0], P::mod(0));
+        for (int j = 0; j < 8; j += 2) {
+            uint64_t pe = (uint64_t)a.v[j] * b.v[0];
+            uint64_t po = (uint64_t)a.v[j + 1] * b.v[0];
+            x[j] = (uint32_t)pe;
+            x[j + 1] = (uint32_t)(pe >> 32);
+            y[j] = (uint32_t)po;
+            y[j + 1] = (uint32_t)(po >> 32);
+        }
+        chain::mont_round_mp(x, y, m, P::NP0);
+        chain::mont_round_ab(y, x, a.v, b.v[1]);
+        chain::mont_round_mp(y, x, m, P::NP0);
+        chain::mont_round_ab(x, y, a.v, b.v[2]);
+        chain::mont_round_mp(x, y, m, P::NP0);
+        chain::mont_round_ab(y, x, a.v, b.v[3]);
+        chain::mont_round_mp(y, x, m, P::NP0);
+        chain::mont_round_ab(x, y, a.v, b.v[4]);
+        chain::mont_round_mp(x, y, m, P::NP0);
+        chain::mont_round_ab(y, x, a.v, b.v[5]);
+        chain::mont_round_mp(y, x, m, P::NP0);
+        chain::mont_round_ab(x, y, a.v, b.v[6]);
+        chain::mont_round_mp(x, y, m, P::NP0);
+        chain::mont_round_ab(y, x, a.v, b.v[7]);
+        chain::mont_round_mp(y, x, m, P::NP0);
+        // y was the limb-0 accumulator of the last round (y[0] == 0), x the limb-1 one: T / 2^32 = x + (y >> 32) < 2m
+        uint32_t sh[8], s[8];
 #pragma unroll
-        for (int i = 1; i < 8; i++) d[i] = subc_cc(s[i], P::mod(i));
-        uint32_t borrow = subc(0u, 0u);
-        Fp r;
-#pragma unroll
-        for (int i = 0; i < 8; i++) r.v[i] = borrow ? s[i] : d[i];
-        return r;
+        for (int i = 0; i < 7; i++) sh[i] = y[i + 1];
+        sh[7] = 0;
+        chain::add8(s, x, sh);
+        return reduce_once(s);
     }
     OZK_HD static Fp sqr(const Fp& a) { return mul(a, a); }
 
@@ -190,11 +144,10 @@ struct Fp {
     }
     // true when the raw 256-bit value is < modulus
     OZK_HD bool is_canonical() const {
-        using namespace ptx;
-        (void)sub_cc(v[0], P::mod(0));
-#pragma unroll
-        for (int i = 1; i < 8; i++) (void)subc_cc(v[i], P::mod(i));
-        return subc(0u, 0u) != 0;
+        uint32_t m[8], d[8], bw;
+        load_mod(m);
+        chain::sub8(d, bw, v, m);
+        return bw != 0;
     }
 
     // ---- exponentiation / inversion (Fermat; Fp.inverse is BigInteger.modInverse, algebra/fields/Fp.java:88-90) --

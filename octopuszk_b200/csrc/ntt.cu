@@ -1,0 +1,590 @@
+// Radix-2 NTT over BN254a Fr as a multi-pass ("four-step" generalised to k passes) transform.
+//
+// Replaces FFTAuxiliary.serialRadix2FFT (src/main/java/algebra/fft/FFTAuxiliary.java:100-123: bit-reverse swap, then
+// log n stages each touching the whole array) and the reference's dormant CUDA version (algebra_fft_FFTAuxiliary.cu:
+// one launch per stage, every thread recomputing its twiddle with two modular exponentiations, :96-140).
+//
+// Factor n = n_1 n_2 ... n_k with n_j <= 512.  Writing the input index as i = (i_1, ..., i_k) with i_1 slowest and the
+// output index as k = k_1 + n_1 k_2 + n_1 n_2 k_3 + ..., pass j replaces digit i_j by k_j with an n_j-point transform
+// held entirely in shared memory, and (for j < k) multiplies by the inter-pass twiddle
+// omega_n^{(n / (n_j inner)) * (remaining index) * k_j}.  Every pass reads and writes whole 128-byte lines:
+//   - passes 1..k-1 walk the transform dimension with stride `inner` and take 4+ adjacent columns per CTA;
+//   - the last pass reads contiguous rows and writes the transposed (natural-order) result, taking 4+ rows that are
+//     adjacent in the OUTPUT per CTA.
+// So there is no bit-reversal pass and the data crosses HBM 2k times (k = 3 for 2^19..2^27).
+//
+// Data stays in canonical (non-Montgomery) form end to end: every multiplication is data x twiddle, and the twiddles
+// are stored as w*2^256 mod r, so mont_mul(x, w~) = x*w needs no conversions at the boundary.
+//
+// Inside a CTA the n_j-point transform is decimation-in-frequency, radix-8 per thread in registers (three butterfly
+// stages per shared-memory round trip); outputs are picked up in bit-reversed position by the store phase.
+#include <cstring>
+
+#include "common.h"
+#include "fp256.cuh"
+
+namespace ozk {
+
+static constexpr int kMaxLogT = 9;          // largest in-CTA transform: 512 points
+static constexpr int kTileLog = 11;         // 2048 elements (64 KB) per CTA tile
+static constexpr int kMaxPasses = 4;
+
+struct NttPlan {
+    int log_n = 0;
+    int npass = 0;
+    int logt[kMaxPasses] = {0, 0, 0, 0};
+    int H = 0;                    // two-level split of the inter-pass twiddle exponent
+    Fr* wsub[kMaxPasses] = {};    // per pass: omega_{n_j}^t, t < n_j/2 (Montgomery form)
+    Fr* tlo = nullptr;            // omega_n^e, e < 2^H
+    Fr* thi = nullptr;            // omega_n^(e 2^H), e < 2^(log_n - H)
+    void* block = nullptr;
+};
+
+// ---- small helpers -----------------------------------------------------------------------------------------
+__device__ __forceinline__ Fr load_fr(const uint4* p) {
+    uint4 a = p[0], b = p[1];
+    Fr r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void store_fr(uint4* p, const Fr& r) {
+    p[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    p[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+
+__device__ Fr fr_pow(Fr base, uint32_t e) {
+    Fr r = Fr::one();
+    while (e) {
+        if (e & 1) r = Fr::mul(r, base);
+        base = Fr::sqr(base);
+        e >>= 1;
+    }
+    return r;
+}
+
+// ---- twiddle tables ------------------------------------------------------------------------------------------
+// table[i] = omega^(i * step) in Montgomery form; `omega_canon` is the canonical 32-byte value from the caller.
+__global__ void ntt_gen_table(Fr* table, uint32_t count, uint32_t step, Fr omega_canon) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    Fr w = Fr::to_mont(omega_canon);
+    table[i] = fr_pow(w, i * step);
+}
+
+// flag[0] = 1 when omega is canonical and omega^(n/2) == -1 (i.e. omega is a primitive n-th root of unity)
+__global__ void ntt_check_omega(uint32_t* flag, Fr omega_canon, uint32_t half_n) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    bool ok = omega_canon.is_canonical();
+    if (ok) {
+        Fr w = Fr::to_mont(omega_canon);
+        Fr h = half_n ? fr_pow(w, half_n) : w;           // n == 1: omega must be 1
+        Fr target = half_n ? Fr::neg(Fr::one()) : Fr::one();
+        ok = (h == target);
+    }
+    flag[0] = ok ? 1u : 0u;
+}
+
+// ---- the pass kernel -----------------------------------------------------------------------------------------
+struct PassArgs {
+    const uint4* in;
+    uint4* out;
+    const Fr* wsub;
+    const Fr* tlo;
+    const Fr* thi;
+    uint32_t H;
+    uint32_t log_n;
+    uint32_t log_inner;    // non-last passes: stride of the transform dimension
+    uint32_t log_outer;    // number of independent transforms per column = n / (T * inner)
+    uint32_t log_c;        // columns (non-last) or rows (last) per tile
+    uint32_t log_n1;       // last pass: radix of pass 1 (rows adjacent in the output differ in k_1)
+    uint32_t nmid;         // last pass: number of middle passes (2..k-1) and their radices
+    uint32_t logmid0, logmid1;
+    uint32_t log_t;        // this pass's transform size
+};
+
+template <bool LAST>
+struct Layout {
+    // shared-memory slot (in 16-byte units, per plane) of element t of column c
+    __device__ __forceinline__ static uint32_t slot(uint32_t t, uint32_t c, uint32_t log_t, uint32_t log_c) {
+        if (LAST) {
+            uint32_t pitch = (1u << log_t) + (1u << (log_t > 3 ? log_t - 3 : 0)) + 1;   // +1 slot per 8, odd pitch
+            return c * pitch + t + (t >> 3);
+        } else {
+            return (t << log_c) + c;
+        }
+    }
+    __device__ __forceinline__ static uint32_t plane_slots(uint32_t log_t, uint32_t log_c) {
+        if (LAST) {
+            uint32_t pitch = (1u << log_t) + (1u << (log_t > 3 ? log_t - 3 : 0)) + 1;
+            return (pitch << log_c) + 4;
+        } else {
+            return (1u << (log_t + log_c)) + 4;    // +64 B so the two planes start in different bank groups
+        }
+    }
+};
+
+static size_t pass_smem_bytes(bool last, int log_t, int log_c) {
+    uint32_t slots;
+    if (last) {
+        uint32_t pitch = (1u << log_t) + (1u << (log_t > 3 ? log_t - 3 : 0)) + 1;
+        slots = (pitch << log_c) + 4;
+    } else {
+        slots = (1u << (log_t + log_c)) + 4;
+    }
+    size_t data = (size_t)slots * 16 * 2;
+    size_t tw = (size_t)(log_t ? (1u << (log_t - 1)) : 1) * 32;
+    return data + tw;
+}
+
+__device__ __forceinline__ Fr lds_fr(const uint4* lo, const uint4* hi, uint32_t s) {
+    uint4 a = lo[s], b = hi[s];
+    Fr r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void sts_fr(uint4* lo, uint4* hi, uint32_t s, const Fr& r) {
+    lo[s] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    hi[s] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+
+// Q decimation-in-frequency stages on 2^Q registers.  Element u sits at index base + u*m of the transform; stage a
+// pairs u with u + 2^(Q-1-a).  The twiddle of a pair depends only on (u mod half) and j = index mod m.
+// M_IS_ONE (the final step, m == 1): exponents with u_local == 0 are zero, those multiplications are skipped.
+template <int Q, bool M_IS_ONE>
+__device__ __forceinline__ void dif_step(Fr (&x)[1 << Q], const Fr* wtab, uint32_t j, uint32_t log_m, uint32_t log_t) {
+#pragma unroll
+    for (int a = 0; a < Q; a++) {
+        const int half = 1 << (Q - 1 - a);           // pair distance in units of m
+        const uint32_t sh = log_t - 1 - (log_m + (Q - 1 - a));   // exponent scale: T / (2 * half * m)
+#pragma unroll
+        for (int ul = 0; ul < half; ul++) {
+            const bool trivial = M_IS_ONE && ul == 0;
+            Fr w;
+            if (!trivial) w = wtab[(((uint32_t)ul << log_m) + j) << sh];
+#pragma unroll
+            for (int blk = 0; blk < (1 << Q); blk += 2 * half) {
+                Fr& p = x[blk + ul];
+                Fr& q = x[blk + ul + half];
+                Fr s = Fr::add(p, q);
+                Fr d = Fr::sub(p, q);
+                p = s;
+                q = trivial ? d : Fr::mul(d, w);
+            }
+        }
+    }
+}
+
+template <int Q, bool M_IS_ONE, bool LAST>
+__device__ __forceinline__ void run_step(uint4* lo, uint4* hi, const Fr* wtab, uint32_t log_m, uint32_t log_t, uint32_t log_c) {
+    const uint32_t groups_per_col = 1u << (log_t - Q);
+    const uint32_t ngroups = groups_per_col << log_c;
+    for (uint32_t gi = threadIdx.x; gi < ngroups; gi += blockDim.x) {
+        uint32_t g, c;
+        if (LAST) {
+            g = gi & (groups_per_col - 1);
+            c = gi >> (log_t - Q);
+        } else {
+            c = gi & ((1u << log_c) - 1);
+            g = gi >> log_c;
+        }
+        const uint32_t j = g & ((1u << log_m) - 1);
+        const uint32_t base = ((g >> log_m) << (log_m + Q)) + j;
+        Fr x[1 << Q];
+#pragma unroll
+        for (int u = 0; u < (1 << Q); u++) x[u] = lds_fr(lo, hi, Layout<LAST>::slot(base + ((uint32_t)u << log_m), c, log_t, log_c));
+        dif_step<Q, M_IS_ONE>(x, wtab, j, log_m, log_t);
+#pragma unroll
+        for (int u = 0; u < (1 << Q); u++) sts_fr(lo, hi, Layout<LAST>::slot(base + ((uint32_t)u << log_m), c, log_t, log_c), x[u]);
+    }
+}
+
+template <bool LAST>
+__global__ void __launch_bounds__(256, 2) ntt_pass_kernel(PassArgs a) {
+    extern __shared__ uint4 smem[];
+    const uint32_t LOGT = a.log_t;
+    const uint32_t T = 1u << LOGT;
+    const uint32_t log_c = a.log_c;
+    const uint32_t C = 1u << log_c;
+    uint4* lo = smem;
+    uint4* hi = smem + Layout<LAST>::plane_slots(LOGT, log_c);
+    Fr* wtab = reinterpret_cast<Fr*>(hi + Layout<LAST>::plane_slots(LOGT, log_c));
+
+    // ---- tile decode
+    size_t in_base, out_base;
+    uint32_t col0 = 0;     // first column index (non-last): the "remaining index" of the inter-pass twiddle
+    if (!LAST) {
+        const uint32_t tiles_per_o = 1u << (a.log_inner - log_c);
+        const uint32_t o = blockIdx.x >> (a.log_inner - log_c);
+        col0 = (blockIdx.x & (tiles_per_o - 1)) << log_c;
+        in_base = (((size_t)o << LOGT) << a.log_inner) + col0;
+        out_base = in_base;
+    } else {
+        // rows o = (k_1, rho) with k_1 slowest; a tile takes C consecutive k_1 for one rho
+        const uint32_t log_rho = a.log_outer - a.log_n1;
+        const uint32_t rho = blockIdx.x & ((1u << log_rho) - 1);
+        const uint32_t k10 = (blockIdx.x >> log_rho) << log_c;
+        in_base = (((size_t)k10 << log_rho) + rho) << LOGT;
+        // output index = k_1 + n_1 * (k_2 + n_2 * (k_3 ...)) + (n/T) * t ; rho = (k_2, k_3, ...) with k_2 slowest.
+        // Two middle passes at most (kMaxPasses == 4): rho = k_2 * n_3 + k_3  ->  k_2 + n_2 * k_3.
+        uint32_t rev = rho;
+        if (a.nmid == 2) {
+            const uint32_t k3 = rho & ((1u << a.logmid1) - 1);
+            const uint32_t k2 = rho >> a.logmid1;
+            rev = k2 + (k3 << a.logmid0);
+        }
+        out_base = (size_t)k10 + ((size_t)rev << a.log_n1);
+    }
+
+    // ---- twiddles of the in-CTA transform
+    for (uint32_t i = threadIdx.x; i < T; i += blockDim.x) {     // T/2 entries of two uint4 each
+        reinterpret_cast<uint4*>(wtab)[i] = reinterpret_cast<const uint4*>(a.wsub)[i];
+    }
+
+    // ---- load the tile (16 bytes per thread per step, fastest index = the contiguous one in global memory)
+    if (!LAST) {
+        const uint32_t per_row = C * 2;                     // uint4 per row of the tile
+        const uint32_t total = T * per_row;
+        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+            uint32_t t = i >> (log_c + 1), r = i & (per_row - 1);
+            uint32_t c = r >> 1, h = r & 1;
+            uint4 v = a.in[(in_base + ((size_t)t << a.log_inner) + c) * 2 + h];
+            (h ? hi : lo)[Layout<LAST>::slot(t, c, LOGT, log_c)] = v;
+        }
+    } else {
+        const uint32_t log_rho = a.log_outer - a.log_n1;
+        const uint32_t per_row = T * 2;
+        const uint32_t total = C * per_row;
+        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+            uint32_t c = i >> (LOGT + 1), r = i & (per_row - 1);
+            uint32_t t = r >> 1, h = r & 1;
+            uint4 v = a.in[(in_base + ((((size_t)c << log_rho)) << LOGT) + t) * 2 + h];
+            (h ? hi : lo)[Layout<LAST>::slot(t, c, LOGT, log_c)] = v;
+        }
+    }
+    __syncthreads();
+
+    // ---- DIF stages from half-size T/2 down to 1: (LOGT mod 3) single stages first, then radix-8 steps.
+    {
+        uint32_t log_m = LOGT;
+        uint32_t r0 = LOGT % 3;
+        if (LOGT < 3) r0 = LOGT;
+        while (r0 > 0) {
+            log_m -= 1;
+            r0 -= 1;
+            if (log_m == 0) run_step<1, true, LAST>(lo, hi, wtab, 0, LOGT, log_c);
+            else run_step<1, false, LAST>(lo, hi, wtab, log_m, LOGT, log_c);
+            __syncthreads();
+        }
+        while (log_m > 0) {
+            log_m -= 3;
+            if (log_m == 0) run_step<3, true, LAST>(lo, hi, wtab, 0, LOGT, log_c);
+            else run_step<3, false, LAST>(lo, hi, wtab, log_m, LOGT, log_c);
+            __syncthreads();
+        }
+    }
+
+    // ---- store: element k of the transform sits at bit-reversed position; lanes run along the contiguous output index
+    const uint32_t total = T << log_c;
+    for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+        const uint32_t c = i & (C - 1);
+        const uint32_t k = i >> log_c;
+        const uint32_t pos = LOGT ? (__brev(k) >> (32 - LOGT)) : 0;
+        Fr v = lds_fr(lo, hi, Layout<LAST>::slot(pos, c, LOGT, log_c));
+        if (!LAST) {
+            // inter-pass twiddle omega_n^(outer * column * k)
+            const uint32_t e = (((col0 + c) * k) << a.log_outer);
+            if (e != 0) {
+                Fr w = Fr::mul(a.tlo[e & ((1u << a.H) - 1)], a.thi[e >> a.H]);
+                v = Fr::mul(v, w);
+            }
+            store_fr(a.out + (out_base + ((size_t)k << a.log_inner) + c) * 2, v);
+        } else {
+            store_fr(a.out + (out_base + ((size_t)k << a.log_outer) + c) * 2, v);
+        }
+    }
+}
+
+// ---- elementwise helpers ---------------------------------------------------------------------------------------
+// out[i] = in[i] * scale * coset^i   (scale / coset given in Montgomery form; `has_coset` selects the power term)
+__global__ void __launch_bounds__(256) fr_scale_powers_kernel(const uint4* in, uint4* out, size_t n, Fr scale_canon, Fr coset_canon,
+                                                              int has_scale, int has_coset) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    if (i >= n) return;
+    Fr f = has_scale ? Fr::to_mont(scale_canon) : Fr::one(), step = Fr::one();
+    if (has_coset) {
+        // f = scale * coset^i, step = coset^stride
+        const Fr coset = Fr::to_mont(coset_canon);
+        Fr b = coset;
+        size_t e = i;
+        while (e) {
+            if (e & 1) f = Fr::mul(f, b);
+            b = Fr::sqr(b);
+            e >>= 1;
+        }
+        b = coset;
+        e = stride;
+        while (e) {
+            if (e & 1) step = Fr::mul(step, b);
+            b = Fr::sqr(b);
+            e >>= 1;
+        }
+    }
+    for (; i < n; i += stride) {
+        Fr v = load_fr(in + i * 2);
+        v = Fr::mul(v, f);
+        store_fr(out + i * 2, v);
+        if (has_coset) f = Fr::mul(f, step);
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+static void fr_from_bytes(Fr& f, const uint8_t* b) { memcpy(f.v, b, 32); }
+
+void ntt_free_plans(ozk_ctx* ctx) {
+    for (auto& kv : ctx->ntt_plans) {
+        if (kv.second->block) cudaFree(kv.second->block);
+        delete kv.second;
+    }
+    ctx->ntt_plans.clear();
+}
+
+static int ntt_get_plan(ozk_ctx* ctx, int log_n, const uint8_t omega[32], NttPlan** out) {
+    std::string key((const char*)omega, 32);
+    key.push_back((char)log_n);
+    auto it = ctx->ntt_plans.find(key);
+    if (it != ctx->ntt_plans.end()) {
+        *out = it->second;
+        return OZK_OK;
+    }
+    Fr om;
+    fr_from_bytes(om, omega);
+    // validate omega on the device
+    uint32_t* flag = (uint32_t*)ctx->pinned;
+    OZK_TRY(ctx->io_out.reserve(256, ctx->stream));
+    ntt_check_omega<<<1, 32, 0, ctx->stream>>>((uint32_t*)ctx->io_out.p, om, log_n ? (1u << (log_n - 1)) : 0u);
+    OZK_CUDA(cudaMemcpyAsync(flag, ctx->io_out.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    OZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (flag[0] != 1u) {
+        set_error("ozk_ntt_fr: omega is not a canonical primitive 2^%d-th root of unity in Fr", log_n);
+        return OZK_ERR_DOMAIN;
+    }
+    NttPlan* p = new NttPlan();
+    p->log_n = log_n;
+    p->npass = log_n <= kMaxLogT ? 1 : (log_n + kMaxLogT - 1) / kMaxLogT;
+    {
+        int rem = log_n;
+        for (int j = 0; j < p->npass; j++) {
+            int left = p->npass - j;
+            p->logt[j] = (rem + left - 1) / left;      // balanced, larger radices first
+            rem -= p->logt[j];
+        }
+    }
+    p->H = (log_n + 1) / 2;
+    size_t count = 0;
+    size_t off_w[kMaxPasses];
+    for (int j = 0; j < p->npass; j++) {
+        off_w[j] = count;
+        count += p->logt[j] ? (size_t)1 << (p->logt[j] - 1) : 1;
+    }
+    size_t off_lo = count;
+    count += (size_t)1 << p->H;
+    size_t off_hi = count;
+    count += (size_t)1 << (log_n - p->H);
+    OZK_CUDA(cudaMalloc(&p->block, count * sizeof(Fr)));
+    Fr* base = (Fr*)p->block;
+    for (int j = 0; j < p->npass; j++) {
+        p->wsub[j] = base + off_w[j];
+        uint32_t cnt = p->logt[j] ? 1u << (p->logt[j] - 1) : 1u;
+        ntt_gen_table<<<(cnt + 127) / 128, 128, 0, ctx->stream>>>(p->wsub[j], cnt, 1u << (log_n - p->logt[j]), om);
+    }
+    p->tlo = base + off_lo;
+    p->thi = base + off_hi;
+    {
+        uint32_t cnt = 1u << p->H;
+        ntt_gen_table<<<(cnt + 127) / 128, 128, 0, ctx->stream>>>(p->tlo, cnt, 1u, om);
+        cnt = 1u << (log_n - p->H);
+        ntt_gen_table<<<(cnt + 127) / 128, 128, 0, ctx->stream>>>(p->thi, cnt, 1u << p->H, om);
+    }
+    OZK_CUDA(cudaGetLastError());
+    ctx->ntt_plans[key] = p;
+    *out = p;
+    return OZK_OK;
+}
+
+template <bool LAST>
+static int launch_pass(ozk_ctx* ctx, int log_t, const PassArgs& a, uint32_t grid) {
+    size_t smem = pass_smem_bytes(LAST, log_t, a.log_c);
+    uint32_t threads = 1u << (log_t + a.log_c >= 3 ? log_t + a.log_c - 3 : 0);
+    if (threads < 32) threads = 32;
+    if (threads > 256) threads = 256;
+    static bool attr_done[64] = {};
+    if (!attr_done[ctx->device & 63]) {
+        OZK_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<LAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr_done[ctx->device & 63] = true;
+    }
+    ntt_pass_kernel<LAST><<<grid, threads, smem, ctx->stream>>>(a);
+    OZK_CUDA(cudaGetLastError());
+    return OZK_OK;
+}
+
+static int ntt_run(ozk_ctx* ctx, const void* d_in, void* d_out, int log_n, const uint8_t omega[32]) {
+    NttPlan* p;
+    OZK_TRY(ntt_get_plan(ctx, log_n, omega, &p));
+    const size_t bytes = ((size_t)32) << log_n;
+    void* work = nullptr;
+    if (p->npass > 1) {
+        OZK_TRY(ctx->work.reserve(bytes, ctx->stream));
+        work = ctx->work.p;
+    }
+    int log_inner = log_n;
+    for (int j = 0; j < p->npass; j++) {
+        const int lt = p->logt[j];
+        log_inner -= lt;
+        const bool last = (j == p->npass - 1);
+        PassArgs a;
+        memset(&a, 0, sizeof a);
+        a.in = (const uint4*)(j == 0 ? d_in : work);
+        a.out = (uint4*)(last ? d_out : work);
+        a.wsub = p->wsub[j];
+        a.tlo = p->tlo;
+        a.thi = p->thi;
+        a.H = p->H;
+        a.log_n = log_n;
+        a.log_inner = log_inner;
+        a.log_outer = log_n - lt - log_inner;
+        a.log_t = lt;
+        if (!last) {
+            int lc = kTileLog - lt;
+            if (lc > log_inner) lc = log_inner;
+            a.log_c = lc;
+            uint32_t grid = 1u << (log_n - lt - lc);
+            OZK_TRY(launch_pass<false>(ctx, lt, a, grid));
+        } else {
+            a.log_n1 = p->npass > 1 ? p->logt[0] : 0;
+            a.nmid = p->npass > 2 ? p->npass - 2 : 0;
+            a.logmid0 = a.nmid > 0 ? p->logt[1] : 0;
+            a.logmid1 = a.nmid > 1 ? p->logt[2] : 0;
+            int lc = kTileLog - lt;
+            if (lc > (int)a.log_n1) lc = a.log_n1;
+            a.log_c = lc;
+            uint32_t grid = 1u << (log_n - lt - lc);
+            OZK_TRY(launch_pass<true>(ctx, lt, a, grid));
+        }
+    }
+    return OZK_OK;
+}
+
+static int ilog2_exact(size_t n) {
+    if (n == 0 || (n & (n - 1))) return -1;
+    int l = 0;
+    while (((size_t)1 << l) < n) l++;
+    return l;
+}
+
+// byte-wise "value < r" on a 32-byte little-endian number (plain comparison; no field arithmetic on the host)
+static bool fr_bytes_canonical(const uint8_t* b) {
+    static const uint32_t mod[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+    uint32_t v[8];
+    memcpy(v, b, 32);
+    for (int i = 7; i >= 0; i--) {
+        if (v[i] < mod[i]) return true;
+        if (v[i] > mod[i]) return false;
+    }
+    return false;
+}
+
+static int scale_powers(ozk_ctx* ctx, const void* d_in, void* d_out, size_t n, const uint8_t* scale, const uint8_t* coset) {
+    Fr s, g;
+    memset(&s, 0, sizeof s);
+    memset(&g, 0, sizeof g);
+    // the constants go to the kernel in canonical form; it converts them to Montgomery form itself
+    if (scale) {
+        if (!fr_bytes_canonical(scale)) {
+            set_error("fr: scale factor is not reduced mod r");
+            return OZK_ERR_DOMAIN;
+        }
+        fr_from_bytes(s, scale);
+    }
+    if (coset) {
+        if (!fr_bytes_canonical(coset)) {
+            set_error("fr: coset generator is not reduced mod r");
+            return OZK_ERR_DOMAIN;
+        }
+        fr_from_bytes(g, coset);
+    }
+    size_t blocks = (n + 255) / 256;
+    size_t cap = (size_t)ctx->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    fr_scale_powers_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>((const uint4*)d_in, (uint4*)d_out, n, s, g, scale ? 1 : 0, coset ? 1 : 0);
+    OZK_CUDA(cudaGetLastError());
+    return OZK_OK;
+}
+
+}  // namespace ozk
+
+using namespace ozk;
+
+extern "C" {
+
+int ozk_ntt_fr_dev(ozk_ctx* ctx, const void* d_in, void* d_out, size_t n, const uint8_t omega[32]) {
+    OZK_TRY(ctx_enter(ctx));
+    OZK_ARG(d_in && d_out && omega, "ozk_ntt_fr_dev: null pointer");
+    int log_n = ilog2_exact(n);
+    OZK_ARG(log_n >= 0 && log_n <= 28, "ozk_ntt_fr_dev: n must be a power of two <= 2^28 (Fr has 2-adicity 28)");
+    return ntt_run(ctx, d_in, d_out, log_n, omega);
+}
+
+int ozk_ntt_fr_ex_dev(ozk_ctx* ctx, const void* d_in, void* d_out, size_t n, const uint8_t omega[32],
+                      const uint8_t* pre_coset, const uint8_t* post_scale, const uint8_t* post_coset) {
+    OZK_TRY(ctx_enter(ctx));
+    OZK_ARG(d_in && d_out && omega, "ozk_ntt_fr_ex_dev: null pointer");
+    int log_n = ilog2_exact(n);
+    OZK_ARG(log_n >= 0 && log_n <= 28, "ozk_ntt_fr_ex_dev: n must be a power of two <= 2^28");
+    const void* src = d_in;
+    if (pre_coset) {
+        OZK_TRY(scale_powers(ctx, d_in, d_out, n, nullptr, pre_coset));
+        src = d_out;
+    }
+    OZK_TRY(ntt_run(ctx, src, d_out, log_n, omega));
+    if (post_scale || post_coset) OZK_TRY(scale_powers(ctx, d_out, d_out, n, post_scale, post_coset));
+    return OZK_OK;
+}
+
+int ozk_ntt_fr(ozk_ctx* ctx, uint8_t* data, size_t n, const uint8_t omega[32]) {
+    OZK_TRY(ctx_enter(ctx));
+    OZK_ARG(data && omega, "ozk_ntt_fr: null pointer");
+    int log_n = ilog2_exact(n);
+    OZK_ARG(log_n >= 0 && log_n <= 28, "ozk_ntt_fr: n must be a power of two <= 2^28 (Fr has 2-adicity 28)");
+    const size_t bytes = n * 32;
+    OZK_TRY(ctx->io_a.reserve(bytes, ctx->stream));
+    OZK_CUDA(cudaMemcpyAsync(ctx->io_a.p, data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    OZK_TRY(ntt_run(ctx, ctx->io_a.p, ctx->io_a.p, log_n, omega));
+    OZK_CUDA(cudaMemcpyAsync(data, ctx->io_a.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    OZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return OZK_OK;
+}
+
+int ozk_fr_scale_dev(ozk_ctx* ctx, const void* d_a, void* d_out, size_t n, const uint8_t b[32]) {
+    OZK_TRY(ctx_enter(ctx));
+    OZK_ARG(d_a && d_out && b, "ozk_fr_scale_dev: null pointer");
+    if (n == 0) return OZK_OK;
+    return scale_powers(ctx, d_a, d_out, n, b, nullptr);
+}
+
+int ozk_fr_scale(ozk_ctx* ctx, const uint8_t* a, size_t n, const uint8_t b[32], uint8_t* out) {
+    OZK_TRY(ctx_enter(ctx));
+    OZK_ARG(b && (n == 0 || (a && out)), "ozk_fr_scale: null pointer");
+    if (n == 0) return OZK_OK;
+    const size_t bytes = n * 32;
+    OZK_TRY(ctx->io_a.reserve(bytes, ctx->stream));
+    OZK_CUDA(cudaMemcpyAsync(ctx->io_a.p, a, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    OZK_TRY(scale_powers(ctx, ctx->io_a.p, ctx->io_a.p, n, b, nullptr));
+    OZK_CUDA(cudaMemcpyAsync(out, ctx->io_a.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    OZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return OZK_OK;
+}
+
+}  // extern "C"

@@ -4,15 +4,16 @@
 // mad.lo.cc + madc.hi.cc on the same operands into one IMAD.WIDE.U32(.X), so a chain of 2k wrappers costs k
 // integer-pipe issues.  The wrappers are `asm volatile` so the order of the chain (and so the carry flag) is kept.
 //
-// Host code (plain g++ or the host pass of nvcc): the same wrappers emulate the instructions with a thread-local
-// carry flag.  That lets tests/host_arith_check.cc run the *identical* limb algorithms on the CPU, where no GPU
-// exists, and compare them with the Python oracle.  The host path is test scaffolding only: no product entry point
-// computes with it (the C ABI in capi.cu launches kernels and fails when there is no device).
+// Plain g++ (tests only, never nvcc): the same wrappers emulate the instructions with a thread-local carry flag.
+// That lets tests/host_arith_check.cc run the *identical* limb algorithms on the CPU, where no GPU exists, and
+// compare them with the Python oracle.  The emulation is compiled out of every product translation unit.
 #pragma once
 #include <cstdint>
 
 #if defined(__CUDACC__)
-#define OZK_HD __host__ __device__ __forceinline__
+// Product build (nvcc): the arithmetic exists as DEVICE code only -- liboctozk.so contains no host implementation of
+// any field or curve operation, so nothing can silently fall back to the CPU.
+#define OZK_HD __device__ __forceinline__
 #define OZK_D __device__ __forceinline__
 #else
 #define OZK_HD inline
@@ -22,7 +23,7 @@
 namespace ozk {
 namespace ptx {
 
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
 
 OZK_D uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 OZK_D uint32_t addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }

@@ -1,0 +1,222 @@
+"""ctypes binding of the C ABI in include/octozk.h.
+
+The library is built in-tree by octopuszk_b200/build.py.  There is no fallback of any kind: if liboctozk.so is
+missing, or no CUDA device is usable, loading / context creation raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB: Optional[ctypes.CDLL] = None
+
+OZK_OK = 0
+
+
+class OzkError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"octozk error {code}: {msg}")
+        self.code = code
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "lib", "liboctozk.so")
+
+
+_c_u8p = ctypes.c_char_p
+_vp = ctypes.c_void_p
+_sz = ctypes.c_size_t
+_int = ctypes.c_int
+
+# name -> (restype, argtypes); every symbol include/octozk.h declares
+SIGNATURES = {
+    "ozk_device_count": (_int, []),
+    "ozk_ctx_create": (_int, [_int, ctypes.POINTER(_vp)]),
+    "ozk_ctx_destroy": (None, [_vp]),
+    "ozk_ctx_set_stream": (_int, [_vp, _vp]),
+    "ozk_ctx_sync": (_int, [_vp]),
+    "ozk_last_error": (ctypes.c_char_p, []),
+    "ozk_version": (ctypes.c_char_p, []),
+    "ozk_fr_scale": (_int, [_vp, _vp, _sz, _c_u8p, _vp]),
+    "ozk_fr_scale_dev": (_int, [_vp, _vp, _vp, _sz, _c_u8p]),
+    "ozk_ntt_fr": (_int, [_vp, _vp, _sz, _c_u8p]),
+    "ozk_ntt_fr_dev": (_int, [_vp, _vp, _vp, _sz, _c_u8p]),
+    "ozk_ntt_fr_ex_dev": (_int, [_vp, _vp, _vp, _sz, _c_u8p, _c_u8p, _c_u8p, _c_u8p]),
+    "ozk_imad_peak": (_int, [_vp, ctypes.POINTER(ctypes.c_double)]),
+    "ozk_modmul_peak": (_int, [_vp, ctypes.POINTER(ctypes.c_double)]),
+    # MSM_BEGIN
+#    "ozk_msm_g1": (_int, [_vp, _vp, _vp, _sz, _vp]),
+#    "ozk_msm_g1_dev": (_int, [_vp, _vp, _vp, _sz, _vp]),
+#    "ozk_msm_g2": (_int, [_vp, _vp, _vp, _sz, _vp]),
+#    "ozk_msm_g2_dev": (_int, [_vp, _vp, _vp, _sz, _vp]),
+#    "ozk_msm_g1g2": (_int, [_vp, _vp, _vp, _vp, _sz, _vp]),
+#    "ozk_msm_g1g2_dev": (_int, [_vp, _vp, _vp, _vp, _sz, _vp]),
+#    "ozk_fixed_g1": (_int, [_vp, _c_u8p, _vp, _sz, _int, _int, _vp]),
+#    "ozk_fixed_g1_dev": (_int, [_vp, _c_u8p, _vp, _sz, _int, _int, _vp]),
+#    "ozk_fixed_g2": (_int, [_vp, _c_u8p, _vp, _sz, _int, _int, _vp]),
+#    "ozk_fixed_g2_dev": (_int, [_vp, _c_u8p, _vp, _sz, _int, _int, _vp]),
+#    "ozk_msm_last_stats": (_int, [_vp, ctypes.POINTER(ctypes.c_double), _int]),
+    # MSM_END
+}
+
+
+def load_library(path: Optional[str] = None) -> ctypes.CDLL:
+    global _LIB
+    if _LIB is not None and path is None:
+        return _LIB
+    p = path or library_path()
+    if not os.path.exists(p):
+        raise OzkError(-100, f"{p} not found: build it with `python -m octopuszk_b200.build` (no CPU fallback exists)")
+    lib = ctypes.CDLL(p)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)        # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _LIB = lib
+    return lib
+
+
+def _ptr(x):
+    """Address of a bytes-like / numpy / torch buffer, or a raw int device pointer."""
+    if x is None:
+        return 0
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    if hasattr(x, "ctypes"):
+        return x.ctypes.data
+    if isinstance(x, bytes):
+        return x                      # ctypes passes the buffer address and keeps the object alive for the call
+    if isinstance(x, bytearray):
+        return (ctypes.c_char * len(x)).from_buffer(x)
+    if isinstance(x, ctypes.Array):
+        return x
+    raise TypeError(type(x))
+
+
+class Context:
+    """One liboctozk context (own stream + scratch) on one device."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        self.lib = load_library()
+        h = ctypes.c_void_p()
+        self._h = None
+        self._check(self.lib.ozk_ctx_create(device, ctypes.byref(h)))
+        self._h = h
+        self.device = device
+        if stream is not None:
+            self.set_stream(stream)
+
+    def _check(self, rc: int):
+        if rc != OZK_OK:
+            raise OzkError(rc, self.lib.ozk_last_error().decode())
+
+    def close(self):
+        if self._h is not None:
+            self.lib.ozk_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self.lib.ozk_ctx_set_stream(self._h, ctypes.c_void_p(cuda_stream)))
+
+    def sync(self):
+        self._check(self.lib.ozk_ctx_sync(self._h))
+
+    # ---- diagnostics
+    def imad_peak(self) -> float:
+        v = ctypes.c_double()
+        self._check(self.lib.ozk_imad_peak(self._h, ctypes.byref(v)))
+        return v.value
+
+    def modmul_peak(self) -> float:
+        v = ctypes.c_double()
+        self._check(self.lib.ozk_modmul_peak(self._h, ctypes.byref(v)))
+        return v.value
+
+    # ---- Fr
+    def fr_scale(self, a: bytes, b: bytes) -> bytes:
+        n = len(a) // 32
+        out = ctypes.create_string_buffer(n * 32)
+        self._check(self.lib.ozk_fr_scale(self._h, a, n, b, out))
+        return out.raw
+
+    def fr_scale_dev(self, d_a, d_out, n: int, b: bytes):
+        self._check(self.lib.ozk_fr_scale_dev(self._h, _ptr(d_a), _ptr(d_out), n, b))
+
+    # ---- NTT
+    def ntt(self, data: bytes, omega: bytes) -> bytes:
+        n = len(data) // 32
+        buf = ctypes.create_string_buffer(bytes(data), n * 32)
+        self._check(self.lib.ozk_ntt_fr(self._h, buf, n, omega))
+        return buf.raw
+
+    def ntt_host_inplace(self, buf, n: int, omega: bytes):
+        self._check(self.lib.ozk_ntt_fr(self._h, _ptr(buf), n, omega))
+
+    def ntt_dev(self, d_in, d_out, n: int, omega: bytes):
+        self._check(self.lib.ozk_ntt_fr_dev(self._h, _ptr(d_in), _ptr(d_out), n, omega))
+
+    def ntt_ex_dev(self, d_in, d_out, n: int, omega: bytes, pre_coset=None, post_scale=None, post_coset=None):
+        self._check(self.lib.ozk_ntt_fr_ex_dev(self._h, _ptr(d_in), _ptr(d_out), n, omega, pre_coset, post_scale, post_coset))
+
+    # ---- variable-base MSM
+    def msm_g1(self, scalars, bases, n: int) -> bytes:
+        out = ctypes.create_string_buffer(96)
+        self._check(self.lib.ozk_msm_g1(self._h, _ptr(scalars), _ptr(bases), n, out))
+        return out.raw
+
+    def msm_g1_dev(self, d_scalars, d_bases, n: int) -> bytes:
+        out = ctypes.create_string_buffer(96)
+        self._check(self.lib.ozk_msm_g1_dev(self._h, _ptr(d_scalars), _ptr(d_bases), n, out))
+        return out.raw
+
+    def msm_g2(self, scalars, bases, n: int) -> bytes:
+        out = ctypes.create_string_buffer(192)
+        self._check(self.lib.ozk_msm_g2(self._h, _ptr(scalars), _ptr(bases), n, out))
+        return out.raw
+
+    def msm_g2_dev(self, d_scalars, d_bases, n: int) -> bytes:
+        out = ctypes.create_string_buffer(192)
+        self._check(self.lib.ozk_msm_g2_dev(self._h, _ptr(d_scalars), _ptr(d_bases), n, out))
+        return out.raw
+
+    def msm_g1g2(self, scalars, bases1, bases2, n: int) -> bytes:
+        out = ctypes.create_string_buffer(288)
+        self._check(self.lib.ozk_msm_g1g2(self._h, _ptr(scalars), _ptr(bases1), _ptr(bases2), n, out))
+        return out.raw
+
+    def msm_g1g2_dev(self, d_scalars, d_bases1, d_bases2, n: int) -> bytes:
+        out = ctypes.create_string_buffer(288)
+        self._check(self.lib.ozk_msm_g1g2_dev(self._h, _ptr(d_scalars), _ptr(d_bases1), _ptr(d_bases2), n, out))
+        return out.raw
+
+    def msm_last_stats(self):
+        arr = (ctypes.c_double * 16)()
+        k = self.lib.ozk_msm_last_stats(self._h, arr, 16)
+        return list(arr)[:max(k, 0)]
+
+    # ---- fixed-base batch MSM
+    def fixed_g1(self, base: bytes, scalars, n: int, outerc: int, window: int) -> bytes:
+        out = ctypes.create_string_buffer(n * 96)
+        self._check(self.lib.ozk_fixed_g1(self._h, base, _ptr(scalars), n, outerc, window, out))
+        return out.raw
+
+    def fixed_g1_dev(self, base: bytes, d_scalars, n: int, outerc: int, window: int, d_out):
+        self._check(self.lib.ozk_fixed_g1_dev(self._h, base, _ptr(d_scalars), n, outerc, window, _ptr(d_out)))
+
+    def fixed_g2(self, base: bytes, scalars, n: int, outerc: int, window: int) -> bytes:
+        out = ctypes.create_string_buffer(n * 192)
+        self._check(self.lib.ozk_fixed_g2(self._h, base, _ptr(scalars), n, outerc, window, out))
+        return out.raw
+
+    def fixed_g2_dev(self, base: bytes, d_scalars, n: int, outerc: int, window: int, d_out):
+        self._check(self.lib.ozk_fixed_g2_dev(self._h, base, _ptr(d_scalars), n, outerc, window, _ptr(d_out)))

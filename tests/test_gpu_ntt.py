@@ -1,0 +1,129 @@
+"""GPU parity: radix-2 NTT over Fr and the Fr vector scale, through the C ABI, against the oracle
+(FFTAuxiliary.serialRadix2FFT restated in oracle/dizk_oracle.py)."""
+import random
+
+import pytest
+
+from oracle import dizk_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from octopuszk_b200 import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def _pack(v):
+    return b"".join(O.le32(x) for x in v)
+
+
+def _unpack(b):
+    return [O.from_le(b[i:i + 32]) for i in range(0, len(b), 32)]
+
+
+def test_fr_scale_matches_oracle(ctx):
+    rng = random.Random(11)
+    a = [0, 1, O.R - 1, O.R - 2, (1 << 253)] + [rng.randrange(O.R) for _ in range(1000)]
+    for b in (0, 1, O.R - 1, rng.randrange(O.R)):
+        got = _unpack(ctx.fr_scale(_pack(a), O.le32(b)))
+        assert got == O.field_batch_msm(a, b)
+
+
+def test_fr_scale_rejects_unreduced(ctx):
+    from octopuszk_b200 import OzkError
+    with pytest.raises(OzkError):
+        ctx.fr_scale(_pack([1, 2]), O.le32(O.R))
+
+
+def test_ntt_reference_kat(ctx):
+    # SURVEY.md Appendix B / SerialFFTTest.java:168-190 carried to Fr
+    got = _unpack(ctx.ntt(_pack([2, 5, 3, 8]), O.le32(O.root_of_unity(4))))
+    assert got == [18, 21888242871839275209022642834368543560924422484752198131886912786320552141471,
+                   21888242871839275222246405745257275088548364400416034343698204186575808495609,
+                   13223762910888731527623941915663836211811291400255256354144]
+
+
+@pytest.mark.parametrize("log_n", list(range(0, 14)))
+def test_ntt_matches_oracle_all_small_sizes(ctx, log_n):
+    rng = random.Random(100 + log_n)
+    n = 1 << log_n
+    x = [rng.randrange(O.R) for _ in range(n)]
+    if n >= 4:
+        x[0], x[1], x[2] = 0, O.R - 1, 1
+    omega = O.root_of_unity(n)
+    exp = list(x)
+    O.serial_radix2_fft(exp, omega)
+    assert _unpack(ctx.ntt(_pack(x), O.le32(omega))) == exp
+    # inverse direction: omega^-1 (SerialFFT.radix2InverseFFT without the n^-1 scaling)
+    inv = pow(omega, -1, O.R)
+    exp2 = list(x)
+    O.serial_radix2_fft(exp2, inv)
+    assert _unpack(ctx.ntt(_pack(x), O.le32(inv))) == exp2
+
+
+@pytest.mark.parametrize("log_n", [16, 18, 19, 20, 22])
+def test_ntt_large_spot_check_and_roundtrip(ctx, log_n):
+    """Sizes the Python oracle cannot transform in seconds: compare sampled outputs with Horner evaluation of the
+    input at omega^k (the definition FFTAuxiliary.serialRadix2FFT satisfies), then invert and compare everything."""
+    import numpy as np
+    rng = random.Random(200 + log_n)
+    n = 1 << log_n
+    raw = np.frombuffer(rng.randbytes(n * 32), dtype=np.uint8).reshape(n, 32).copy()
+    raw[:, 31] &= 0x1F                      # < 2^253 < r : canonical
+    x_bytes = raw.tobytes()
+    omega = O.root_of_unity(n)
+    y_bytes = ctx.ntt(x_bytes, O.le32(omega))
+    ks = [0, 1, n - 1, n // 2] + [rng.randrange(n) for _ in range(2)]
+    if log_n <= 18:
+        x = _unpack(x_bytes)
+        for k in ks:
+            assert O.from_le(y_bytes[32 * k:32 * k + 32]) == O.naive_evaluate(x, pow(omega, k, O.R))
+    z_bytes = ctx.ntt(y_bytes, O.le32(pow(omega, -1, O.R)))
+    ninv = pow(n, -1, O.R)
+    back = ctx.fr_scale(z_bytes, O.le32(ninv))
+    assert back == x_bytes
+    # linearity / delta response, size independent: NTT(e_j)[k] = omega^(jk)
+    j = rng.randrange(n)
+    d = bytearray(n * 32)
+    d[32 * j:32 * j + 32] = O.le32(1)
+    yd = ctx.ntt(bytes(d), O.le32(omega))
+    for k in ks:
+        assert O.from_le(yd[32 * k:32 * k + 32]) == pow(omega, j * k, O.R)
+
+
+def test_ntt_rejects_bad_omega(ctx):
+    from octopuszk_b200 import OzkError
+    with pytest.raises(OzkError):
+        ctx.ntt(_pack([1, 2, 3, 4]), O.le32(O.root_of_unity(8)))     # primitive 8th root, not 4th
+    with pytest.raises(OzkError):
+        ctx.ntt(_pack([1, 2, 3]), O.le32(1))                          # not a power of two
+
+
+def test_ntt_ex_wrappers_match_serialfft(ctx):
+    """radix2InverseFFT / radix2CosetFFT / radix2CosetInverseFFT (SerialFFT.java:86-115) via the fused entry point."""
+    import torch
+    rng = random.Random(5)
+    n = 1 << 10
+    dom = O.SerialFFT(n)
+    x = [rng.randrange(O.R) for _ in range(n)]
+    g = O.FR_MULT_GEN
+    dev = torch.device("cuda:0")
+    d_in = torch.frombuffer(bytearray(_pack(x)), dtype=torch.uint8).to(dev)
+    d_out = torch.empty_like(d_in)
+    ninv = pow(n, -1, O.R)
+
+    def run(**kw):
+        ctx.ntt_ex_dev(d_in, d_out, n, **kw)
+        ctx.sync()
+        return _unpack(d_out.cpu().numpy().tobytes())
+
+    e = list(x); dom.radix2_inverse_fft(e)
+    assert run(omega=O.le32(pow(dom.omega, -1, O.R)), post_scale=O.le32(ninv)) == e
+    e = list(x); dom.radix2_coset_fft(e, g)
+    assert run(omega=O.le32(dom.omega), pre_coset=O.le32(g)) == e
+    e = list(x); dom.radix2_coset_inverse_fft(e, g)
+    assert run(omega=O.le32(pow(dom.omega, -1, O.R)), post_scale=O.le32(ninv), post_coset=O.le32(pow(g, -1, O.R))) == e
