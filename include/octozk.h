@@ -30,6 +30,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define OZK_API __attribute__((visibility("default")))
+#else
+#define OZK_API
+#endif
+
 #define OZK_OK 0
 #define OZK_ERR_ARG (-1)
 #define OZK_ERR_CUDA (-2)
@@ -42,43 +48,61 @@ typedef struct ozk_ctx ozk_ctx;
  * threads do not share state (the reference shares the default stream and device-synchronises after every launch,
  * algebra_msm_VariableBaseMSM.cu:1286-1413).  The reference's placement rule is device = taskID % deviceCount
  * (algebra_msm_VariableBaseMSM.cu:1248-1257). */
-int ozk_device_count(void);
-int ozk_ctx_create(int device, ozk_ctx** out);
-void ozk_ctx_destroy(ozk_ctx* ctx);
+OZK_API int ozk_device_count(void);
+OZK_API int ozk_ctx_create(int device, ozk_ctx** out);
+OZK_API void ozk_ctx_destroy(ozk_ctx* ctx);
 /* use an externally owned cudaStream_t (e.g. the caller's current stream) for all later work */
-int ozk_ctx_set_stream(ozk_ctx* ctx, void* cuda_stream);
-int ozk_ctx_sync(ozk_ctx* ctx);
-const char* ozk_last_error(void);
-const char* ozk_version(void);
+OZK_API int ozk_ctx_set_stream(ozk_ctx* ctx, void* cuda_stream);
+OZK_API int ozk_ctx_sync(ozk_ctx* ctx);
+OZK_API const char* ozk_last_error(void);
+OZK_API const char* ozk_version(void);
 
 /* ---- Fr vector x constant ------------------------------------------------------------------------------
  * out[i] = a[i] * b mod r.  Replaces field_MSM / Java_algebra_msm_FixedBaseMSM_fieldBatchMSMNativeHelper
  * (algebra_msm_FixedBaseMSM.cu:1241-1266, :1500-1558). */
-int ozk_fr_scale(ozk_ctx* ctx, const uint8_t* a, size_t n, const uint8_t b[32], uint8_t* out);
-int ozk_fr_scale_dev(ozk_ctx* ctx, const void* d_a, void* d_out, size_t n, const uint8_t b[32]);
+OZK_API int ozk_fr_scale(ozk_ctx* ctx, const uint8_t* a, size_t n, const uint8_t b[32], uint8_t* out);
+OZK_API int ozk_fr_scale_dev(ozk_ctx* ctx, const void* d_a, void* d_out, size_t n, const uint8_t b[32]);
 
 /* ---- radix-2 NTT over Fr ---------------------------------------------------------------------------------
  * out[k] = sum_j in[j] * omega^(j k), natural order in and out, n a power of two <= 2^28, omega a primitive n-th
  * root of unity.  Replaces FFTAuxiliary.serialRadix2FFT (src/main/java/algebra/fft/FFTAuxiliary.java:60-124) and the
  * dormant Java_algebra_fft_FFTAuxiliary_serialRadix2FFTNativeHelper / best_fft (algebra_fft_FFTAuxiliary.cu:167-260).
  * d_in == d_out is allowed. */
-int ozk_ntt_fr(ozk_ctx* ctx, uint8_t* data, size_t n, const uint8_t omega[32]);
-int ozk_ntt_fr_dev(ozk_ctx* ctx, const void* d_in, void* d_out, size_t n, const uint8_t omega[32]);
+OZK_API int ozk_ntt_fr(ozk_ctx* ctx, uint8_t* data, size_t n, const uint8_t omega[32]);
+OZK_API int ozk_ntt_fr_dev(ozk_ctx* ctx, const void* d_in, void* d_out, size_t n, const uint8_t omega[32]);
 /* Fused wrappers of src/main/java/algebra/fft/SerialFFT.java:75-115,157-162:
  *   in[i] *= pre_coset^i (if non-NULL), transform with omega, out[i] *= post_scale * post_coset^i (either may be NULL).
  *   radix2InverseFFT      : omega^-1, post_scale = n^-1
  *   radix2CosetFFT        : pre_coset = g
  *   radix2CosetInverseFFT : omega^-1, post_scale = n^-1, post_coset = g^-1
  *   divideByZOnCoset      : folds into post_scale */
-int ozk_ntt_fr_ex_dev(ozk_ctx* ctx, const void* d_in, void* d_out, size_t n, const uint8_t omega[32],
+OZK_API int ozk_ntt_fr_ex_dev(ozk_ctx* ctx, const void* d_in, void* d_out, size_t n, const uint8_t omega[32],
                       const uint8_t* pre_coset, const uint8_t* post_scale, const uint8_t* post_coset);
+
+/* ---- variable-base MSM --------------------------------------------------------------------------------------
+ * out = sum_i scalars[i] * bases[i].  Replaces VariableBaseMSM.serialMSM's native leg
+ * Java_algebra_msm_VariableBaseMSM_variableBaseSerialMSMNativeHelper (algebra_msm_VariableBaseMSM.cu:1614-1695,
+ * pippengerMSMG1 :1246-1428, pippengerMSMG2 :1433-1604) and, for the paired form, ...variableBaseDoubleMSMNativeHelper
+ * (:1712-1788), which runs G1 then G2 on the same scalars; here both share one scalar sort.
+ * scalars: n x 32 B (< r).  G1 bases: n x 96 B, G2 bases: n x 192 B (Jacobian, any Z; Z == 0 is infinity).
+ * out: one point in the same layout (G1 96 B, G2 192 B, paired: G1 || G2 = 288 B); infinity is (0,1,0).
+ * n == 0 gives infinity.  Unlike the Java caller's 2^23 / 2^22 / 2^21 chunking (VariableBaseMSM.java:211,268,494) any
+ * n < 2^31 that fits in device memory is accepted in one call. */
+OZK_API int ozk_msm_g1(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* bases, size_t n, uint8_t out[96]);
+OZK_API int ozk_msm_g1_dev(ozk_ctx* ctx, const void* d_scalars, const void* d_bases, size_t n, uint8_t out[96]);
+OZK_API int ozk_msm_g2(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* bases, size_t n, uint8_t out[192]);
+OZK_API int ozk_msm_g2_dev(ozk_ctx* ctx, const void* d_scalars, const void* d_bases, size_t n, uint8_t out[192]);
+OZK_API int ozk_msm_g1g2(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* bases1, const uint8_t* bases2, size_t n, uint8_t out[288]);
+OZK_API int ozk_msm_g1g2_dev(ozk_ctx* ctx, const void* d_scalars, const void* d_bases1, const void* d_bases2, size_t n, uint8_t out[288]);
+/* shape of the last MSM on this context: {window bits, windows, buckets per window, overflow tasks, overflow buckets} */
+OZK_API int ozk_msm_last_stats(ozk_ctx* ctx, double* out, int cap);
 
 /* ---- diagnostics ----------------------------------------------------------------------------------------- */
 /* Integer-pipe microbenchmark: independent 32x32+64 multiply-add chains on every SM; reports billions of
  * multiply-adds per second.  bench.py uses it as the measured integer roofline (MEASURED_PEAKS.json has none). */
-int ozk_imad_peak(ozk_ctx* ctx, double* gimad_per_s);
+OZK_API int ozk_imad_peak(ozk_ctx* ctx, double* gimad_per_s);
 /* Fr Montgomery multiplications per second with all operands in registers (upper bound for the field kernels). */
-int ozk_modmul_peak(ozk_ctx* ctx, double* gmodmul_per_s);
+OZK_API int ozk_modmul_peak(ozk_ctx* ctx, double* gmodmul_per_s);
 
 #ifdef __cplusplus
 }

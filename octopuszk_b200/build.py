@@ -24,8 +24,8 @@ NVCC_FLAGS = [
     "-I", os.path.join(ROOT, "include"),
 ]
 
-CU_SOURCES = ["capi.cu", "ntt.cu", "msm.cu", "fixed_base.cu"]
-HEADERS = ["common.h", "consts.cuh", "curve.cuh", "fp256.cuh", "ptx_arith.cuh", os.path.join(ROOT, "include", "octozk.h")]
+CU_SOURCES = ["capi.cu", "ntt.cu", "msm.cu", "msm_g1.cu", "msm_g2.cu", "fixed_base.cu"]
+HEADERS = ["common.h", "consts.cuh", "chains.cuh", "curve.cuh", "fp256.cuh", "ptx_arith.cuh", "msm_impl.cuh", os.path.join(ROOT, "include", "octozk.h")]
 
 
 def _newer(target: str, deps) -> bool:

@@ -81,6 +81,7 @@ struct ozk_ctx {
     ozk::DevBuf work;                          // NTT ping-pong buffer
     ozk::DevBuf msm[12];                       // MSM pipeline buffers (see msm.cu)
     ozk::DevBuf fb[4];                         // fixed-base buffers
+    double msm_stats[8] = {};                  // last MSM: window c, windows, buckets/window, overflow tasks, overflow buckets
     void* pinned = nullptr;                    // small pinned host block for flags / results
     std::map<std::string, ozk::NttPlan*> ntt_plans;
     std::map<std::string, ozk::FixedTable*> fixed_tables;

@@ -1,0 +1,373 @@
+// Variable-base MSM driver: scalar decomposition, counting sort of (window, bucket) pairs, and the C ABI.
+//
+// Replaces Java_algebra_msm_VariableBaseMSM_variableBaseSerialMSMNativeHelper / ...DoubleMSMNativeHelper and the host
+// loops pippengerMSMG1 / pippengerMSMG2 (algebra_msm_VariableBaseMSM.cu:1246-1788).  Differences that do not change
+// the result as a group element: signed digits (half the buckets), all windows processed at once, a counting sort of
+// 4-byte point indices instead of scattering whole 192-byte points per window (:758), no host round trips.
+#include <algorithm>
+#include <cstring>
+
+#include "common.h"
+#include "msm_impl.cuh"
+
+namespace ozk {
+
+// ---- scalar digits ---------------------------------------------------------------------------------------------
+// Signed c-bit recoding, least significant window first: d = bits + carry; if d > 2^(c-1): d -= 2^c, carry = 1.
+// So |d| <= 2^(c-1): bucket index |d| - 1 in [0, 2^(c-1)), sign separate.  Scalars are < r < 2^254, and
+// nwin = ceil(255 / c) leaves room for the last carry.
+__device__ __forceinline__ uint32_t scalar_bits(const uint32_t (&s)[8], uint32_t pos, uint32_t c) {
+    if (pos >= 256) return 0;
+    const uint32_t limb = pos >> 5, off = pos & 31;
+    uint64_t v = s[limb];
+    if (limb + 1 < 8) v |= (uint64_t)s[limb + 1] << 32;
+    return (uint32_t)(v >> off) & ((1u << c) - 1);
+}
+
+__device__ __forceinline__ bool scalar_lt_r(const uint32_t (&s)[8]) {
+    for (int i = 7; i >= 0; i--) {
+        const uint32_t m = FrParams::mod(i);
+        if (s[i] < m) return true;
+        if (s[i] > m) return false;
+    }
+    return false;
+}
+
+// MODE 0: histogram (count[w * nb + b] += 1).  MODE 1: scatter (sorted[w * n + cursor++] = i | sign << 31).
+template <int MODE>
+__global__ void __launch_bounds__(256) msm_digits(const uint4* __restrict__ scalars, size_t n, uint32_t c, uint32_t nwin,
+                                                  uint32_t* __restrict__ count_or_cursor, uint32_t* __restrict__ sorted,
+                                                  uint32_t* flag) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint4 a = scalars[2 * i], b = scalars[2 * i + 1];
+    uint32_t s[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    if (MODE == 0 && !scalar_lt_r(s)) atomicOr(flag, 2u);
+    const uint32_t half = 1u << (c - 1);
+    const uint32_t log_nb = c - 1;
+    uint32_t carry = 0;
+    for (uint32_t w = 0; w < nwin; w++) {
+        uint32_t d = scalar_bits(s, w * c, c) + carry;
+        uint32_t neg = 0;
+        carry = 0;
+        if (d > half) {
+            d = (1u << c) - d;
+            neg = 1;
+            carry = 1;
+        }
+        if (d == 0) continue;
+        const uint32_t slot = (w << log_nb) + (d - 1);
+        if (MODE == 0) {
+            atomicAdd(&count_or_cursor[slot], 1u);
+        } else {
+            const uint32_t pos = atomicAdd(&count_or_cursor[slot], 1u);
+            sorted[(size_t)w * n + pos] = (uint32_t)i | (neg << 31);
+        }
+    }
+}
+
+// One CTA per window: exclusive scan of the bucket counts -> window-local start offsets (also copied to `cursor`),
+// and the overflow work list for buckets with more than kSeg entries.
+__global__ void __launch_bounds__(1024) msm_scan(const uint32_t* __restrict__ count, uint32_t nb, uint32_t* __restrict__ start,
+                                                 uint32_t* __restrict__ cursor, OvfTask* __restrict__ ovf_tasks,
+                                                 uint32_t* __restrict__ ovf_task_count, OvfBucket* __restrict__ ovf_buckets,
+                                                 uint32_t* __restrict__ ovf_bucket_count, uint32_t ovf_task_cap, uint32_t ovf_bucket_cap) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry_s;
+    const uint32_t w = blockIdx.x;
+    const uint32_t* cnt = count + (size_t)w * nb;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nb; base += 1024) {
+        const uint32_t b = base + threadIdx.x;
+        const uint32_t v = b < nb ? cnt[b] : 0;
+        // block-wide exclusive scan of v
+        uint32_t x = v;
+        const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        for (int off = 1; off < 32; off <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, off);
+            if (lane >= off) x += y;
+        }
+        if (lane == 31) warp_sums[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t ws = warp_sums[lane];
+            for (int off = 1; off < 32; off <<= 1) {
+                uint32_t y = __shfl_up_sync(0xffffffffu, ws, off);
+                if (lane >= off) ws += y;
+            }
+            warp_sums[lane] = ws;
+        }
+        __syncthreads();
+        const uint32_t excl = carry_s + (wid ? warp_sums[wid - 1] : 0) + x - v;
+        if (b < nb) {
+            start[(size_t)w * nb + b] = excl;
+            cursor[(size_t)w * nb + b] = excl;
+            if (v > (uint32_t)kSeg) {
+                const uint32_t extra = (v - 1) / kSeg;
+                const uint32_t t0 = atomicAdd(ovf_task_count, extra);
+                const uint32_t k = atomicAdd(ovf_bucket_count, 1u);
+                if (k < ovf_bucket_cap && t0 + extra <= ovf_task_cap) {
+                    ovf_buckets[k] = {w * nb + b, t0, extra};
+                    for (uint32_t t = 0; t < extra; t++) ovf_tasks[t0 + t] = {w * nb + b, t + 1};
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = excl + v;
+        __syncthreads();
+    }
+}
+
+// ---- window choice ---------------------------------------------------------------------------------------------
+// Cost model: nwin(c) * (n mixed adds + 2 * 2^(c-1) full adds at ~1.5x the cost of a mixed add), and short runs waste
+// lanes (one thread per bucket), so prefer c with at least ~64 points per bucket when n allows.
+static uint32_t choose_window(size_t n) {
+    uint32_t best = 2;
+    double best_cost = 1e300;
+    for (uint32_t c = 2; c <= 16; c++) {
+        const double nwin = (255 + c - 1) / c;
+        const double nb = (double)(1u << (c - 1));
+        const double per_bucket = (double)n / nb;
+        const double imbalance = per_bucket >= 1 ? 1.0 + 2.5 / std::sqrt(per_bucket) : 4.0;
+        const double cost = nwin * ((double)n * imbalance + 3.0 * nb + 2000.0);
+        if (cost < best_cost) {
+            best_cost = cost;
+            best = c;
+        }
+    }
+    return best;
+}
+
+struct MsmShape {
+    uint32_t c, nwin, nb, log_nb;
+    uint32_t ovf_task_cap, ovf_bucket_cap;
+};
+
+static MsmShape msm_shape(size_t n) {
+    MsmShape s;
+    s.c = choose_window(n);
+    s.nwin = (255 + s.c - 1) / s.c;
+    s.log_nb = s.c - 1;
+    s.nb = 1u << s.log_nb;
+    size_t cap = ((size_t)s.nwin * n) / kSeg + 1;
+    s.ovf_task_cap = (uint32_t)std::min<size_t>(cap, 0x7fffffffu);
+    s.ovf_bucket_cap = s.ovf_task_cap;
+    return s;
+}
+
+// buffers in ctx->msm[]
+enum { B_AFF1 = 0, B_AFF2, B_COUNT, B_START, B_CURSOR, B_SORTED, B_BUCKETS, B_OVFTASK, B_OVFBUCKET, B_OVFPART, B_SCRATCH, B_MISC };
+
+// sort phase shared by G1 / G2 / paired calls: fills start/count/sorted and the overflow lists
+static int msm_sort(ozk_ctx* ctx, const void* d_scalars, size_t n, const MsmShape& sh) {
+    cudaStream_t st = ctx->stream;
+    const size_t nbt = (size_t)sh.nwin * sh.nb;
+    OZK_TRY(ctx->msm[B_COUNT].reserve(nbt * 4, st));
+    OZK_TRY(ctx->msm[B_START].reserve(nbt * 4, st));
+    OZK_TRY(ctx->msm[B_CURSOR].reserve(nbt * 4, st));
+    OZK_TRY(ctx->msm[B_SORTED].reserve((size_t)sh.nwin * n * 4, st));
+    OZK_TRY(ctx->msm[B_OVFTASK].reserve((size_t)sh.ovf_task_cap * sizeof(OvfTask), st));
+    OZK_TRY(ctx->msm[B_OVFBUCKET].reserve((size_t)sh.ovf_bucket_cap * sizeof(OvfBucket), st));
+    OZK_TRY(ctx->msm[B_MISC].reserve(256, st));
+    uint32_t* misc = (uint32_t*)ctx->msm[B_MISC].p;      // [0] flag, [1] ovf task count, [2] ovf bucket count
+    OZK_CUDA(cudaMemsetAsync(misc, 0, 64, st));
+    OZK_CUDA(cudaMemsetAsync(ctx->msm[B_COUNT].p, 0, nbt * 4, st));
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    msm_digits<0><<<grid, 256, 0, st>>>((const uint4*)d_scalars, n, sh.c, sh.nwin, (uint32_t*)ctx->msm[B_COUNT].p, nullptr, misc);
+    msm_scan<<<sh.nwin, 1024, 0, st>>>((const uint32_t*)ctx->msm[B_COUNT].p, sh.nb, (uint32_t*)ctx->msm[B_START].p,
+                                       (uint32_t*)ctx->msm[B_CURSOR].p, (OvfTask*)ctx->msm[B_OVFTASK].p, misc + 1,
+                                       (OvfBucket*)ctx->msm[B_OVFBUCKET].p, misc + 2, sh.ovf_task_cap, sh.ovf_bucket_cap);
+    msm_digits<1><<<grid, 256, 0, st>>>((const uint4*)d_scalars, n, sh.c, sh.nwin, (uint32_t*)ctx->msm[B_CURSOR].p,
+                                        (uint32_t*)ctx->msm[B_SORTED].p, misc);
+    OZK_CUDA(cudaGetLastError());
+    return OZK_OK;
+}
+
+// bucket phase for one group: convert bases, accumulate, reduce, final -> d_out (jac_bytes, canonical)
+static int msm_buckets(ozk_ctx* ctx, const MsmLaunch& L, const void* d_bases, size_t n, const MsmShape& sh, int aff_slot, void* d_out) {
+    cudaStream_t st = ctx->stream;
+    const size_t nbt = (size_t)sh.nwin * sh.nb;
+    uint32_t* misc = (uint32_t*)ctx->msm[B_MISC].p;
+    OZK_TRY(ctx->msm[aff_slot].reserve(n * L.affine_bytes, st));
+    OZK_TRY(ctx->msm[B_BUCKETS].reserve(nbt * L.xyzz_bytes, st));
+    OZK_TRY(ctx->msm[B_OVFPART].reserve((size_t)sh.ovf_task_cap * L.xyzz_bytes, st));
+    if (L.convert(st, d_bases, ctx->msm[aff_slot].p, n, misc, ctx->sm_count)) { set_error("msm: convert launch failed"); return OZK_ERR_CUDA; }
+    if (L.accumulate(st, ctx->msm[aff_slot].p, (const uint32_t*)ctx->msm[B_SORTED].p, (const uint32_t*)ctx->msm[B_START].p,
+                     (const uint32_t*)ctx->msm[B_COUNT].p, (const OvfTask*)ctx->msm[B_OVFTASK].p, misc + 1, (uint32_t)nbt, sh.log_nb, n,
+                     sh.ovf_task_cap, ctx->msm[B_BUCKETS].p, ctx->msm[B_OVFPART].p)) { set_error("msm: accumulate launch failed"); return OZK_ERR_CUDA; }
+    if (L.merge(st, (const OvfBucket*)ctx->msm[B_OVFBUCKET].p, misc + 2, std::min<uint32_t>(sh.ovf_bucket_cap, (uint32_t)nbt),
+                ctx->msm[B_OVFPART].p, ctx->msm[B_BUCKETS].p)) { set_error("msm: merge launch failed"); return OZK_ERR_CUDA; }
+
+    // hierarchical reduction.  scratch layout (in XYZZ elements per window): level arrays A_1.., acc arrays, sum temporaries
+    uint32_t m[8], nlev = 0;
+    m[0] = sh.nb;
+    while (m[nlev] > 1) {
+        m[nlev + 1] = (m[nlev] + kWsumS - 1) / kWsumS;
+        nlev++;
+    }
+    // total elements needed: for each level l: run (m[l+1]) + acc (m[l+1]) + acc-sum chain (m[l+1]/S + ... + 1)
+    size_t per_win = 4;
+    for (uint32_t l = 0; l < nlev; l++) {
+        per_win += 2 * (size_t)m[l + 1];
+        uint32_t k = m[l + 1];
+        while (k > 1) {
+            k = (k + kWsumS - 1) / kWsumS;
+            per_win += k;
+        }
+        per_win += 1;
+    }
+    OZK_TRY(ctx->msm[B_SCRATCH].reserve((per_win * sh.nwin + 512) * L.xyzz_bytes, st));
+    char* sp = (char*)ctx->msm[B_SCRATCH].p;
+    auto take = [&](size_t elems_per_win) {
+        void* p = sp;
+        sp += elems_per_win * sh.nwin * L.xyzz_bytes;
+        return p;
+    };
+    FinalArgs fa;
+    memset(&fa, 0, sizeof fa);
+    const void* level_in = ctx->msm[B_BUCKETS].p;
+    for (uint32_t l = 0; l < nlev; l++) {
+        void* run = take(m[l + 1]);
+        void* acc = take(m[l + 1]);
+        if (L.wsum(st, level_in, m[l], sh.nwin, run, acc)) { set_error("msm: wsum launch failed"); return OZK_ERR_CUDA; }
+        // sum acc over its m[l+1] groups
+        const void* cur = acc;
+        uint32_t k = m[l + 1];
+        while (k > 1) {
+            uint32_t k2 = (k + kWsumS - 1) / kWsumS;
+            void* nxt = take(k2);
+            if (L.sum(st, cur, k, sh.nwin, nxt)) { set_error("msm: sum launch failed"); return OZK_ERR_CUDA; }
+            cur = nxt;
+            k = k2;
+        }
+        fa.sum_acc[l] = (const uint4*)cur;
+        level_in = run;
+    }
+    fa.total = (const uint4*)level_in;     // one element per window: the plain sum of all buckets (nb == 1: the bucket itself)
+    fa.nlevels = nlev;
+    fa.nwin = sh.nwin;
+    fa.c = sh.c;
+    void* window_vals = take(1);
+    if (L.final(st, fa, window_vals, d_out)) { set_error("msm: final launch failed"); return OZK_ERR_CUDA; }
+    OZK_CUDA(cudaGetLastError());
+    return OZK_OK;
+}
+
+static int msm_finish(ozk_ctx* ctx, const void* d_res, size_t bytes, uint8_t* out) {
+    // result + flag come back in one small pinned block
+    uint8_t* pin = (uint8_t*)ctx->pinned;
+    OZK_CUDA(cudaMemcpyAsync(pin, d_res, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    OZK_CUDA(cudaMemcpyAsync(pin + 1024, ctx->msm[B_MISC].p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    OZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    const uint32_t* misc = (const uint32_t*)(pin + 1024);
+    ctx->msm_stats[3] = misc[1];
+    ctx->msm_stats[4] = misc[2];
+    if (misc[0] & 1u) { set_error("msm: a base coordinate is not reduced mod p"); return OZK_ERR_DOMAIN; }
+    if (misc[0] & 2u) { set_error("msm: a scalar is not reduced mod r"); return OZK_ERR_DOMAIN; }
+    memcpy(out, pin, bytes);
+    return OZK_OK;
+}
+
+// n == 0: the empty sum
+static void write_inf(uint8_t* out, size_t coord_bytes) {
+    memset(out, 0, 3 * coord_bytes);
+    out[coord_bytes] = 1;      // (0, 1, 0)
+}
+
+static int msm_run(ozk_ctx* ctx, const void* d_scalars, const void* d_b1, const void* d_b2, size_t n, uint8_t* out) {
+    OZK_ARG(n > 0 && n < ((size_t)1 << 31), "msm: between 1 and 2^31 - 1 points per call");
+    const MsmShape sh = msm_shape(n);
+    ctx->msm_stats[0] = sh.c;
+    ctx->msm_stats[1] = sh.nwin;
+    ctx->msm_stats[2] = sh.nb;
+    OZK_TRY(msm_sort(ctx, d_scalars, n, sh));
+    OZK_TRY(ctx->io_out.reserve(512, ctx->stream));
+    char* d_res = (char*)ctx->io_out.p;
+    size_t bytes = 0;
+    if (d_b1) {
+        OZK_TRY(msm_buckets(ctx, kMsmG1, d_b1, n, sh, B_AFF1, d_res));
+        bytes += 96;
+    }
+    if (d_b2) {
+        OZK_TRY(msm_buckets(ctx, kMsmG2, d_b2, n, sh, B_AFF2, d_res + bytes));
+        bytes += 192;
+    }
+    return msm_finish(ctx, d_res, bytes, out);
+}
+
+static int msm_run_host(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* b1, const uint8_t* b2, size_t n, uint8_t* out) {
+    {
+        OZK_TRY(ctx->io_a.reserve(n * 32, ctx->stream));
+        OZK_CUDA(cudaMemcpyAsync(ctx->io_a.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+        if (b1) {
+            OZK_TRY(ctx->io_b.reserve(n * 96, ctx->stream));
+            OZK_CUDA(cudaMemcpyAsync(ctx->io_b.p, b1, n * 96, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        if (b2) {
+            OZK_TRY(ctx->io_c.reserve(n * 192, ctx->stream));
+            OZK_CUDA(cudaMemcpyAsync(ctx->io_c.p, b2, n * 192, cudaMemcpyHostToDevice, ctx->stream));
+        }
+    }
+    return msm_run(ctx, ctx->io_a.p, b1 ? ctx->io_b.p : nullptr, b2 ? ctx->io_c.p : nullptr, n, out);
+}
+
+}  // namespace ozk
+
+using namespace ozk;
+
+extern "C" {
+
+int ozk_msm_g1_dev(ozk_ctx* ctx, const void* d_scalars, const void* d_bases, size_t n, uint8_t out[96]) {
+    OZK_TRY(ctx_enter(ctx));
+    OZK_ARG(out && (n == 0 || (d_scalars && d_bases)), "ozk_msm_g1_dev: null pointer");
+    if (n == 0) { write_inf(out, 32); return OZK_OK; }
+    return msm_run(ctx, d_scalars, d_bases, nullptr, n, out);
+}
+int ozk_msm_g2_dev(ozk_ctx* ctx, const void* d_scalars, const void* d_bases, size_t n, uint8_t out[192]) {
+    OZK_TRY(ctx_enter(ctx));
+    OZK_ARG(out && (n == 0 || (d_scalars && d_bases)), "ozk_msm_g2_dev: null pointer");
+    if (n == 0) { write_inf(out, 64); return OZK_OK; }
+    return msm_run(ctx, d_scalars, nullptr, d_bases, n, out);
+}
+int ozk_msm_g1g2_dev(ozk_ctx* ctx, const void* d_scalars, const void* d_bases1, const void* d_bases2, size_t n, uint8_t out[288]) {
+    OZK_TRY(ctx_enter(ctx));
+    OZK_ARG(out && (n == 0 || (d_scalars && d_bases1 && d_bases2)), "ozk_msm_g1g2_dev: null pointer");
+    if (n == 0) {
+        write_inf(out, 32);
+        write_inf(out + 96, 64);
+        return OZK_OK;
+    }
+    return msm_run(ctx, d_scalars, d_bases1, d_bases2, n, out);
+}
+int ozk_msm_g1(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* bases, size_t n, uint8_t out[96]) {
+    OZK_TRY(ctx_enter(ctx));
+    OZK_ARG(out && (n == 0 || (scalars && bases)), "ozk_msm_g1: null pointer");
+    if (n == 0) { write_inf(out, 32); return OZK_OK; }
+    return msm_run_host(ctx, scalars, bases, nullptr, n, out);
+}
+int ozk_msm_g2(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* bases, size_t n, uint8_t out[192]) {
+    OZK_TRY(ctx_enter(ctx));
+    OZK_ARG(out && (n == 0 || (scalars && bases)), "ozk_msm_g2: null pointer");
+    if (n == 0) { write_inf(out, 64); return OZK_OK; }
+    return msm_run_host(ctx, scalars, nullptr, bases, n, out);
+}
+int ozk_msm_g1g2(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* bases1, const uint8_t* bases2, size_t n, uint8_t out[288]) {
+    OZK_TRY(ctx_enter(ctx));
+    OZK_ARG(out && (n == 0 || (scalars && bases1 && bases2)), "ozk_msm_g1g2: null pointer");
+    if (n == 0) {
+        write_inf(out, 32);
+        write_inf(out + 96, 64);
+        return OZK_OK;
+    }
+    return msm_run_host(ctx, scalars, bases1, bases2, n, out);
+}
+
+int ozk_msm_last_stats(ozk_ctx* ctx, double* out, int cap) {
+    if (!ctx || !out) return 0;
+    int k = cap < 5 ? cap : 5;
+    for (int i = 0; i < k; i++) out[i] = ctx->msm_stats[i];
+    return k;
+}
+
+}  // extern "C"

@@ -1,0 +1,412 @@
+// Curve-generic kernels of the variable-base MSM (instantiated for G1 in msm_g1.cu and G2 in msm_g2.cu).
+//
+// Pipeline (msm.cu drives it; replaces pippengerMSMG1/G2, algebra_msm_VariableBaseMSM.cu:1246-1604, which loops over
+// windows on the host with ~6c+6 synchronous launches per window and one warp per big integer):
+//   convert  : Jacobian canonical bases -> affine Montgomery (batched inversion, Z == 1 fast path)
+//   digits   : signed c-bit digits of every scalar, histogram of (window, bucket)            [msm.cu]
+//   scan     : per-window exclusive scan -> bucket start offsets, overflow task list         [msm.cu]
+//   scatter  : counting-sort the point indices of every window by bucket                     [msm.cu]
+//   accumulate : one thread per (window, bucket) adds its run of points into an XYZZ accumulator (mixed add 8M+2S);
+//                runs longer than SEG are split into extra tasks and merged by a warp-cooperative reduction
+//   reduce   : sum_b (b+1) * B_b per window by a 32-ary hierarchy of running sums (all windows in parallel)
+//   final    : Horner over the windows, conversion to the canonical Jacobian wire format
+#pragma once
+#include "curve.cuh"
+
+namespace ozk {
+
+static constexpr int kSeg = 1024;        // longest run of points a single accumulate task handles
+static constexpr int kWsumS = 32;        // group size of the hierarchical bucket reduction (log2 = 5)
+static constexpr int kWsumLogS = 5;
+static constexpr int kConvBatch = 16;    // points per thread in the batched base normalisation
+
+struct OvfTask {
+    uint32_t bucket;   // w * nb + b
+    uint32_t seg;      // segment index >= 1 inside the bucket's run
+};
+struct OvfBucket {
+    uint32_t bucket;
+    uint32_t first_task;
+    uint32_t ntasks;
+};
+
+// ---- canonical <-> field element I/O --------------------------------------------------------------------------
+__device__ __forceinline__ Fq ld_fq(const uint4* p) {
+    uint4 a = p[0], b = p[1];
+    Fq r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void st_fq(uint4* p, const Fq& r) {
+    p[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    p[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+template <class F> struct FieldIO;
+template <> struct FieldIO<Fq> {
+    static constexpr int kU4 = 2;      // uint4 per element
+    __device__ __forceinline__ static Fq load(const uint4* p) { return ld_fq(p); }
+    __device__ __forceinline__ static void store(uint4* p, const Fq& v) { st_fq(p, v); }
+};
+template <> struct FieldIO<Fq2> {
+    static constexpr int kU4 = 4;
+    __device__ __forceinline__ static Fq2 load(const uint4* p) { return {ld_fq(p), ld_fq(p + 2)}; }
+    __device__ __forceinline__ static void store(uint4* p, const Fq2& v) { st_fq(p, v.c0); st_fq(p + 2, v.c1); }
+};
+
+template <class F>
+__device__ __forceinline__ Affine<F> load_affine(const uint4* base, size_t idx) {
+    const uint4* p = base + idx * (2 * FieldIO<F>::kU4);
+    return {FieldIO<F>::load(p), FieldIO<F>::load(p + FieldIO<F>::kU4)};
+}
+template <class F>
+__device__ __forceinline__ void store_affine(uint4* base, size_t idx, const Affine<F>& a) {
+    uint4* p = base + idx * (2 * FieldIO<F>::kU4);
+    FieldIO<F>::store(p, a.x);
+    FieldIO<F>::store(p + FieldIO<F>::kU4, a.y);
+}
+template <class F>
+__device__ __forceinline__ XYZZ<F> load_xyzz(const uint4* base, size_t idx) {
+    const uint4* p = base + idx * (4 * FieldIO<F>::kU4);
+    return {FieldIO<F>::load(p), FieldIO<F>::load(p + FieldIO<F>::kU4), FieldIO<F>::load(p + 2 * FieldIO<F>::kU4),
+            FieldIO<F>::load(p + 3 * FieldIO<F>::kU4)};
+}
+template <class F>
+__device__ __forceinline__ void store_xyzz(uint4* base, size_t idx, const XYZZ<F>& a) {
+    uint4* p = base + idx * (4 * FieldIO<F>::kU4);
+    FieldIO<F>::store(p, a.x);
+    FieldIO<F>::store(p + FieldIO<F>::kU4, a.y);
+    FieldIO<F>::store(p + 2 * FieldIO<F>::kU4, a.zz);
+    FieldIO<F>::store(p + 3 * FieldIO<F>::kU4, a.zzz);
+}
+
+// Out-of-line copies of the rarely taken / cold-path group operations: one compiled body per field instead of one per
+// call site (the carry-chain code is large; see DESIGN.md "build time").
+template <class F> __device__ __noinline__ void xyzz_add_ni(XYZZ<F>& acc, const XYZZ<F>& q) { xyzz_add(acc, q); }
+template <class F> __device__ __noinline__ void xyzz_dbl_ni(XYZZ<F>& p) { p = xyzz_dbl(p); }
+template <class F> __device__ __noinline__ void xyzz_dbl_affine_ni(XYZZ<F>& acc, const Affine<F>& q) { acc = xyzz_dbl_affine(q); }
+template <class F> __device__ __noinline__ F field_inv_ni(const F& a) { return F::inv(a); }
+
+// mixed add for the hot loop: the common path is inline, the doubling special case is a call
+template <class F>
+__device__ __forceinline__ void xyzz_madd_hot(XYZZ<F>& acc, const Affine<F>& q) {
+    if (q.is_inf()) return;
+    if (acc.is_inf()) {
+        acc = {q.x, q.y, F::one(), F::one()};
+        return;
+    }
+    F U2 = F::mul(q.x, acc.zz);
+    F S2 = F::mul(q.y, acc.zzz);
+    F Pp = F::sub(U2, acc.x);
+    F Rr = F::sub(S2, acc.y);
+    if (Pp.is_zero()) {
+        if (Rr.is_zero()) xyzz_dbl_affine_ni(acc, q);
+        else acc = XYZZ<F>::inf();
+        return;
+    }
+    F PP = F::sqr(Pp);
+    F PPP = F::mul(Pp, PP);
+    F Q = F::mul(acc.x, PP);
+    F X3 = F::sub(F::sub(F::sqr(Rr), PPP), F::dbl(Q));
+    acc.y = F::sub(F::mul(Rr, F::sub(Q, X3)), F::mul(acc.y, PPP));
+    acc.x = X3;
+    acc.zz = F::mul(acc.zz, PP);
+    acc.zzz = F::mul(acc.zzz, PPP);
+}
+
+__device__ __forceinline__ Fq canon_one(Fq*) {
+    Fq r = Fq::zero();
+    r.v[0] = 1;
+    return r;
+}
+__device__ __forceinline__ Fq2 canon_one(Fq2*) { return {canon_one((Fq*)nullptr), Fq::zero()}; }
+
+// ---- convert: Jacobian canonical -> affine Montgomery ------------------------------------------------------------
+// in : n x [X|Y|Z] canonical little-endian (the reference wire format, VariableBaseMSM.java:224-227 / :279-285)
+// out: n x [x|y] Montgomery, (0,0) for infinity.  flag |= 1 when a coordinate is not reduced.
+template <class F>
+__global__ void __launch_bounds__(128) msm_convert_bases(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n, uint32_t* flag) {
+    constexpr int U = FieldIO<F>::kU4;
+    const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    F prefix[kConvBatch];
+    F zm[kConvBatch];
+    bool all_unit = true;
+    bool bad = false;
+    const F one_canon = canon_one((F*)nullptr);
+    // forward: running product of the Z's (Z == 0 counts as 1)
+#pragma unroll 1
+    for (int k = 0; k < kConvBatch; k++) {
+        size_t i = tid + (size_t)k * nthreads;
+        F z = F::one();
+        if (i < n) {
+            F zc = FieldIO<F>::load(in + i * (3 * U) + 2 * U);
+            bad |= !zc.is_canonical();
+            if (!zc.is_zero()) {
+                if (zc != one_canon) {
+                    all_unit = false;
+                    z = F::to_mont(zc);
+                }
+            }
+        }
+        zm[k] = z;
+        prefix[k] = k ? F::mul(prefix[k - 1], z) : z;
+    }
+    F inv = F::one();
+    if (!all_unit) inv = field_inv_ni(prefix[kConvBatch - 1]);
+#pragma unroll 1
+    for (int k = kConvBatch - 1; k >= 0; k--) {
+        size_t i = tid + (size_t)k * nthreads;
+        F zi = F::one();
+        if (!all_unit) {
+            zi = k ? F::mul(inv, prefix[k - 1]) : inv;
+            inv = F::mul(inv, zm[k]);
+        }
+        if (i >= n) continue;
+        const uint4* p = in + i * (3 * U);
+        F xc = FieldIO<F>::load(p), yc = FieldIO<F>::load(p + U), zc = FieldIO<F>::load(p + 2 * U);
+        bad |= !xc.is_canonical() || !yc.is_canonical();
+        Affine<F> a;
+        if (zc.is_zero()) {
+            a = Affine<F>::inf();
+        } else {
+            a.x = F::to_mont(xc);
+            a.y = F::to_mont(yc);
+            if (!all_unit) {
+                F zi2 = F::sqr(zi);
+                a.x = F::mul(a.x, zi2);
+                a.y = F::mul(a.y, F::mul(zi2, zi));
+            }
+        }
+        store_affine<F>(out, i, a);
+    }
+    if (bad) atomicOr(flag, 1u);
+}
+
+// ---- accumulate ---------------------------------------------------------------------------------------------------
+// task t < nbuckets_total : bucket t, entries [0, min(cnt, SEG)) of its run           -> buckets[t]
+// task t >= nbuckets_total: overflow task (bucket, seg), entries [seg*SEG, ...)        -> ovf_partial[t - nbuckets_total]
+// sorted[w * n + pos] = point index | sign << 31 ; start/count are per (window, bucket), start is window-local.
+template <class F>
+__global__ void __launch_bounds__(128) msm_accumulate(const uint4* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                                                      const uint32_t* __restrict__ start, const uint32_t* __restrict__ count,
+                                                      const OvfTask* __restrict__ ovf_tasks, const uint32_t* __restrict__ ovf_count,
+                                                      uint32_t nbuckets_total, uint32_t log_nb, size_t n,
+                                                      uint4* __restrict__ buckets, uint4* __restrict__ ovf_partial) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t bucket, seg;
+    if (t < nbuckets_total) {
+        bucket = t;
+        seg = 0;
+    } else {
+        const uint32_t k = t - nbuckets_total;
+        if (k >= *ovf_count) return;
+        bucket = ovf_tasks[k].bucket;
+        seg = ovf_tasks[k].seg;
+    }
+    const uint32_t cnt = count[bucket];
+    const uint32_t w = bucket >> log_nb;
+    uint32_t lo = seg * kSeg;
+    uint32_t hi = min(cnt, lo + kSeg);
+    const uint32_t* run = sorted + (size_t)w * n + start[bucket];
+    XYZZ<F> acc = XYZZ<F>::inf();
+    if (lo < hi) {
+        uint32_t e = run[lo];
+        Affine<F> p = load_affine<F>(bases, e & 0x7fffffffu);
+        for (uint32_t j = lo; j < hi; j++) {
+            // prefetch the next point while this one is being added
+            uint32_t e_next = 0;
+            Affine<F> p_next = p;
+            if (j + 1 < hi) {
+                e_next = run[j + 1];
+                p_next = load_affine<F>(bases, e_next & 0x7fffffffu);
+            }
+            if (e >> 31) p.y = F::neg(p.y);
+            xyzz_madd_hot(acc, p);
+            e = e_next;
+            p = p_next;
+        }
+    }
+    if (t < nbuckets_total) store_xyzz<F>(buckets, bucket, acc);
+    else store_xyzz<F>(ovf_partial, t - nbuckets_total, acc);
+}
+
+// one warp per overflow bucket: buckets[b] += sum of its overflow partials
+template <class F>
+__global__ void __launch_bounds__(128) msm_merge_overflow(const OvfBucket* __restrict__ ovf_buckets, const uint32_t* __restrict__ ovf_bucket_count,
+                                                          const uint4* __restrict__ ovf_partial, uint4* __restrict__ buckets) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (warp >= *ovf_bucket_count) return;
+    const OvfBucket ob = ovf_buckets[warp];
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t k = lane; k < ob.ntasks; k += 32) {
+        XYZZ<F> q = load_xyzz<F>(ovf_partial, ob.first_task + k);
+        xyzz_add_ni(acc, q);
+    }
+    // butterfly reduction across the warp
+    constexpr int W = sizeof(XYZZ<F>) / 4;
+#pragma unroll 1
+    for (int off = 16; off >= 1; off >>= 1) {
+        XYZZ<F> other;
+        uint32_t* src = reinterpret_cast<uint32_t*>(&acc);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&other);
+#pragma unroll
+        for (int i = 0; i < W; i++) dst[i] = __shfl_xor_sync(0xffffffffu, src[i], off);
+        xyzz_add_ni(acc, other);
+    }
+    if (lane == 0) {
+        XYZZ<F> b = load_xyzz<F>(buckets, ob.bucket);
+        xyzz_add_ni(b, acc);
+        store_xyzz<F>(buckets, ob.bucket, b);
+    }
+}
+
+// ---- hierarchical bucket reduction ---------------------------------------------------------------------------------
+// For every window and every group g of S consecutive inputs: run[g] = sum_j in[gS+j], acc[g] = sum_j j * in[gS+j].
+template <class F>
+__global__ void __launch_bounds__(128) msm_wsum_level(const uint4* __restrict__ in, uint32_t m_in, uint32_t nwin,
+                                                      uint4* __restrict__ run_out, uint4* __restrict__ acc_out) {
+    const uint32_t groups = (m_in + kWsumS - 1) / kWsumS;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= groups * nwin) return;
+    const uint32_t w = t / groups, g = t % groups;
+    const size_t base = (size_t)w * m_in + (size_t)g * kWsumS;
+    const uint32_t len = min((uint32_t)kWsumS, m_in - g * kWsumS);
+    XYZZ<F> run = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
+    for (int j = (int)len - 1; j >= 1; j--) {
+        XYZZ<F> q = load_xyzz<F>(in, base + j);
+        xyzz_add_ni(run, q);
+        xyzz_add_ni(acc, run);
+    }
+    {
+        XYZZ<F> q = load_xyzz<F>(in, base);
+        xyzz_add_ni(run, q);
+    }
+    store_xyzz<F>(run_out, (size_t)w * groups + g, run);
+    store_xyzz<F>(acc_out, (size_t)w * groups + g, acc);
+}
+
+// out[w][g] = sum of the g-th group of S inputs of window w
+template <class F>
+__global__ void __launch_bounds__(128) msm_sum_level(const uint4* __restrict__ in, uint32_t m_in, uint32_t nwin, uint4* __restrict__ out) {
+    const uint32_t groups = (m_in + kWsumS - 1) / kWsumS;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= groups * nwin) return;
+    const uint32_t w = t / groups, g = t % groups;
+    const size_t base = (size_t)w * m_in + (size_t)g * kWsumS;
+    const uint32_t len = min((uint32_t)kWsumS, m_in - g * kWsumS);
+    XYZZ<F> s = XYZZ<F>::inf();
+    for (uint32_t j = 0; j < len; j++) {
+        XYZZ<F> q = load_xyzz<F>(in, base + j);
+        xyzz_add_ni(s, q);
+    }
+    store_xyzz<F>(out, (size_t)w * groups + g, s);
+}
+
+// ---- final ------------------------------------------------------------------------------------------------------------
+// sum_acc[l][w] (l < nlevels): sum over groups of acc at level l; total[w]: plain sum of all buckets of window w.
+// Window value W_w = total[w] + sum_l S^l * sum_acc[l][w]; result = sum_w 2^(c w) W_w.  Written as canonical Jacobian
+// (X|Y|Z, 32 bytes each per base-field element), (0,1,0) for infinity (what the reference emits,
+// algebra_msm_VariableBaseMSM.cu:1274-1276).
+struct FinalArgs {
+    const uint4* sum_acc[8];
+    const uint4* total;
+    uint32_t nlevels;
+    uint32_t nwin;
+    uint32_t c;
+};
+
+template <class F>
+__global__ void msm_final(FinalArgs a, uint4* __restrict__ window_vals, uint4* __restrict__ out) {
+    constexpr int U = FieldIO<F>::kU4;
+    const uint32_t w = threadIdx.x;
+    if (w < a.nwin) {
+        XYZZ<F> T = XYZZ<F>::inf();
+        for (int l = (int)a.nlevels - 1; l >= 0; l--) {
+            for (int d = 0; d < kWsumLogS; d++) xyzz_dbl_ni(T);
+            XYZZ<F> q = load_xyzz<F>(a.sum_acc[l], w);
+            xyzz_add_ni(T, q);
+        }
+        XYZZ<F> tot = load_xyzz<F>(a.total, w);
+        xyzz_add_ni(T, tot);
+        store_xyzz<F>(window_vals, w, T);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        XYZZ<F> res = XYZZ<F>::inf();
+        for (int ww = (int)a.nwin - 1; ww >= 0; ww--) {
+            for (uint32_t d = 0; d < a.c; d++) xyzz_dbl_ni(res);
+            XYZZ<F> q = load_xyzz<F>(window_vals, ww);
+            xyzz_add_ni(res, q);
+        }
+        Jacobian<F> j = xyzz_to_jacobian(res);
+        FieldIO<F>::store(out, F::from_mont(j.x));
+        FieldIO<F>::store(out + U, F::from_mont(j.y));
+        FieldIO<F>::store(out + 2 * U, F::from_mont(j.z));
+    }
+}
+
+// ---- host-side launch wrappers (declared here, defined per field in msm_g1.cu / msm_g2.cu) --------------------------
+struct MsmLaunch {
+    int (*convert)(cudaStream_t, const void* in, void* out, size_t n, uint32_t* flag, int sm_count);
+    int (*accumulate)(cudaStream_t, const void* bases, const uint32_t* sorted, const uint32_t* start, const uint32_t* count,
+                      const OvfTask* tasks, const uint32_t* ovf_count, uint32_t nbuckets_total, uint32_t log_nb, size_t n,
+                      uint32_t ovf_cap, void* buckets, void* ovf_partial);
+    int (*merge)(cudaStream_t, const OvfBucket* ob, const uint32_t* ob_count, uint32_t ob_cap, const void* ovf_partial, void* buckets);
+    int (*wsum)(cudaStream_t, const void* in, uint32_t m_in, uint32_t nwin, void* run_out, void* acc_out);
+    int (*sum)(cudaStream_t, const void* in, uint32_t m_in, uint32_t nwin, void* out);
+    int (*final)(cudaStream_t, const FinalArgs& a, void* window_vals, void* out);
+    size_t affine_bytes;     // per point
+    size_t jac_bytes;        // per point, wire format
+    size_t xyzz_bytes;
+};
+
+extern const MsmLaunch kMsmG1;
+extern const MsmLaunch kMsmG2;
+
+#define OZK_DEFINE_MSM_LAUNCH(F, NAME)                                                                                         \
+    static int NAME##_convert(cudaStream_t s, const void* in, void* out, size_t n, uint32_t* flag, int sm_count) {             \
+        size_t threads_needed = (n + kConvBatch - 1) / kConvBatch;                                                             \
+        unsigned grid = (unsigned)((threads_needed + 127) / 128);                                                              \
+        if (grid == 0) grid = 1;                                                                                               \
+        (void)sm_count;                                                                                                        \
+        msm_convert_bases<F><<<grid, 128, 0, s>>>((const uint4*)in, (uint4*)out, n, flag);                                     \
+        return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                                     \
+    }                                                                                                                          \
+    static int NAME##_accumulate(cudaStream_t s, const void* bases, const uint32_t* sorted, const uint32_t* start,             \
+                                 const uint32_t* count, const OvfTask* tasks, const uint32_t* ovf_count, uint32_t nbt,         \
+                                 uint32_t log_nb, size_t n, uint32_t ovf_cap, void* buckets, void* ovf_partial) {              \
+        size_t total = (size_t)nbt + ovf_cap;                                                                                  \
+        unsigned grid = (unsigned)((total + 127) / 128);                                                                       \
+        msm_accumulate<F><<<grid, 128, 0, s>>>((const uint4*)bases, sorted, start, count, tasks, ovf_count, nbt, log_nb, n,    \
+                                               (uint4*)buckets, (uint4*)ovf_partial);                                          \
+        return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                                     \
+    }                                                                                                                          \
+    static int NAME##_merge(cudaStream_t s, const OvfBucket* ob, const uint32_t* ob_count, uint32_t ob_cap,                    \
+                            const void* ovf_partial, void* buckets) {                                                          \
+        if (ob_cap == 0) return 0;                                                                                             \
+        unsigned grid = (unsigned)(((size_t)ob_cap * 32 + 127) / 128);                                                         \
+        msm_merge_overflow<F><<<grid, 128, 0, s>>>(ob, ob_count, (const uint4*)ovf_partial, (uint4*)buckets);                  \
+        return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                                     \
+    }                                                                                                                          \
+    static int NAME##_wsum(cudaStream_t s, const void* in, uint32_t m_in, uint32_t nwin, void* run_out, void* acc_out) {       \
+        uint32_t groups = (m_in + kWsumS - 1) / kWsumS;                                                                        \
+        unsigned grid = (groups * nwin + 127) / 128;                                                                           \
+        msm_wsum_level<F><<<grid, 128, 0, s>>>((const uint4*)in, m_in, nwin, (uint4*)run_out, (uint4*)acc_out);                \
+        return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                                     \
+    }                                                                                                                          \
+    static int NAME##_sum(cudaStream_t s, const void* in, uint32_t m_in, uint32_t nwin, void* out) {                           \
+        uint32_t groups = (m_in + kWsumS - 1) / kWsumS;                                                                        \
+        unsigned grid = (groups * nwin + 127) / 128;                                                                           \
+        msm_sum_level<F><<<grid, 128, 0, s>>>((const uint4*)in, m_in, nwin, (uint4*)out);                                      \
+        return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                                     \
+    }                                                                                                                          \
+    static int NAME##_final(cudaStream_t s, const FinalArgs& a, void* window_vals, void* out) {                                \
+        msm_final<F><<<1, 256, 0, s>>>(a, (uint4*)window_vals, (uint4*)out);                                                   \
+        return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                                     \
+    }                                                                                                                          \
+    const MsmLaunch NAME = {NAME##_convert, NAME##_accumulate, NAME##_merge, NAME##_wsum, NAME##_sum, NAME##_final,            \
+                            sizeof(Affine<F>), sizeof(Jacobian<F>), sizeof(XYZZ<F>)};
+
+}  // namespace ozk

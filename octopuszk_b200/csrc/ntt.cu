@@ -431,6 +431,11 @@ static int launch_pass(ozk_ctx* ctx, int log_t, const PassArgs& a, uint32_t grid
 }
 
 static int ntt_run(ozk_ctx* ctx, const void* d_in, void* d_out, int log_n, const uint8_t omega[32]) {
+    if (log_n == 0) {
+        // n == 1: FFTAuxiliary.serialRadix2FFT returns at once whatever omega is (FFTAuxiliary.java:64-66)
+        if (d_in != d_out) OZK_CUDA(cudaMemcpyAsync(d_out, d_in, 32, cudaMemcpyDeviceToDevice, ctx->stream));
+        return OZK_OK;
+    }
     NttPlan* p;
     OZK_TRY(ntt_get_plan(ctx, log_n, omega, &p));
     const size_t bytes = ((size_t)32) << log_n;

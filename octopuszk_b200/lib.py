@@ -46,17 +46,17 @@ SIGNATURES = {
     "ozk_imad_peak": (_int, [_vp, ctypes.POINTER(ctypes.c_double)]),
     "ozk_modmul_peak": (_int, [_vp, ctypes.POINTER(ctypes.c_double)]),
     # MSM_BEGIN
-#    "ozk_msm_g1": (_int, [_vp, _vp, _vp, _sz, _vp]),
-#    "ozk_msm_g1_dev": (_int, [_vp, _vp, _vp, _sz, _vp]),
-#    "ozk_msm_g2": (_int, [_vp, _vp, _vp, _sz, _vp]),
-#    "ozk_msm_g2_dev": (_int, [_vp, _vp, _vp, _sz, _vp]),
-#    "ozk_msm_g1g2": (_int, [_vp, _vp, _vp, _vp, _sz, _vp]),
-#    "ozk_msm_g1g2_dev": (_int, [_vp, _vp, _vp, _vp, _sz, _vp]),
+    "ozk_msm_g1": (_int, [_vp, _vp, _vp, _sz, _vp]),
+    "ozk_msm_g1_dev": (_int, [_vp, _vp, _vp, _sz, _vp]),
+    "ozk_msm_g2": (_int, [_vp, _vp, _vp, _sz, _vp]),
+    "ozk_msm_g2_dev": (_int, [_vp, _vp, _vp, _sz, _vp]),
+    "ozk_msm_g1g2": (_int, [_vp, _vp, _vp, _vp, _sz, _vp]),
+    "ozk_msm_g1g2_dev": (_int, [_vp, _vp, _vp, _vp, _sz, _vp]),
 #    "ozk_fixed_g1": (_int, [_vp, _c_u8p, _vp, _sz, _int, _int, _vp]),
 #    "ozk_fixed_g1_dev": (_int, [_vp, _c_u8p, _vp, _sz, _int, _int, _vp]),
 #    "ozk_fixed_g2": (_int, [_vp, _c_u8p, _vp, _sz, _int, _int, _vp]),
 #    "ozk_fixed_g2_dev": (_int, [_vp, _c_u8p, _vp, _sz, _int, _int, _vp]),
-#    "ozk_msm_last_stats": (_int, [_vp, ctypes.POINTER(ctypes.c_double), _int]),
+    "ozk_msm_last_stats": (_int, [_vp, ctypes.POINTER(ctypes.c_double), _int]),
     # MSM_END
 }
 

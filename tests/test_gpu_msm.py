@@ -1,0 +1,153 @@
+"""GPU parity: variable-base MSM (G1, G2, paired) through the C ABI against the oracle's restatement of
+VariableBaseMSM.pippengerMSM / serialMSM / doubleMSM.  Equality is equality of group elements (BNG1.equals)."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import dizk_oracle as O
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from octopuszk_b200 import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def _run(ctx, group, scalars, bases):
+    n = len(scalars)
+    sb = O.pack_scalars(scalars)
+    if group is O.G1:
+        out = ctx.msm_g1(sb, O.pack_g1(bases), n)
+        assert len(out) == 96
+    else:
+        out = ctx.msm_g2(sb, O.pack_g2(bases), n)
+        assert len(out) == 192
+    pt = util.unpack_point(group, out)
+    # returned coordinates are fully reduced (Java stores them without mod, BN254aG1.java:55-59)
+    flat = pt if group is O.G1 else [c for f in pt for c in f]
+    assert all(0 <= v < O.P for v in flat)
+    return pt
+
+
+def test_reference_kat_75G(ctx):
+    # SerialVariableBaseMSMTest.java:31-77 carried to G1
+    bases = [O.G1.mul(O.G1.generator, k) for k in (5, 2, 7, 3)]
+    got = O.G1.to_affine(_run(ctx, O.G1, [3, 11, 2, 8], bases))
+    assert got[:2] == (14670023805213312856584033961079180710026959676164645964476657106778352781859,
+                       211633134735504671946091929992244044834074118928621612299531666035417451988)
+    # duplicates: 4 x (3 * 5G) = 60 G (DistributedVariableBaseMSMTest.java:92-124)
+    got = _run(ctx, O.G1, [3] * 4, [bases[0]] * 4)
+    assert O.G1.equals(got, O.G1.mul(O.G1.generator, 60))
+
+
+@pytest.mark.parametrize("gname", ["G1", "G2"])
+@pytest.mark.parametrize("n", [1, 2, 3, 17, 100, 1023])
+def test_small_random_vs_oracle(ctx, gname, n):
+    G = O.G1 if gname == "G1" else O.G2
+    if G is O.G2 and n > 100:
+        n = 257
+    rng = random.Random(1000 + n)
+    ks, pool = util.known_dlog_points(G, min(n, 12), seed=n, random_z=True)
+    bases = [pool[rng.randrange(len(pool))] for _ in range(n)]
+    scalars = [rng.randrange(O.R) for _ in range(n)]
+    # edge cases the reference meets in Groth16 inputs: infinity bases, zero / one / r-1 scalars,
+    # a point and its negation, the same point many times
+    if n >= 17:
+        bases[0] = G.zero()
+        bases[1] = (pool[0][0], pool[0][1], G.F.zero)            # Z == 0 with junk X, Y
+        scalars[2] = 0
+        scalars[3] = 1
+        scalars[4] = O.R - 1
+        bases[5] = pool[1]
+        bases[6] = G.negate(pool[1])
+        scalars[5] = scalars[6] = rng.randrange(O.R)
+        bases[7] = bases[8] = bases[9] = pool[2]
+        scalars[7] = scalars[8] = scalars[9] = 12345
+        bases[10] = G.to_affine(pool[3])                          # Z == 1
+    exp = O.pippenger_msm(G, scalars, bases)
+    assert G.equals(_run(ctx, G, scalars, bases), exp)
+    assert G.equals(exp, O.naive_msm(G, scalars, bases))
+
+
+def test_all_zero_scalars_and_empty(ctx):
+    ks, pool = util.known_dlog_points(O.G1, 4, seed=3)
+    assert O.G1.is_zero(_run(ctx, O.G1, [0, 0, 0, 0], pool))
+    out = ctx.msm_g1(b"", b"", 0)
+    assert O.G1.is_zero(O.unpack_g1(out)[0])
+    out = ctx.msm_g2(b"", b"", 0)
+    assert O.G2.is_zero(O.unpack_g2(out)[0])
+
+
+def test_rejects_unreduced_inputs(ctx):
+    from octopuszk_b200 import OzkError
+    ks, pool = util.known_dlog_points(O.G1, 2, seed=4)
+    with pytest.raises(OzkError):
+        ctx.msm_g1(O.le32(O.R) + O.le32(1), O.pack_g1(pool), 2)
+    bad = [(O.P, pool[0][1], pool[0][2]), pool[1]]
+    with pytest.raises(OzkError):
+        ctx.msm_g1(O.le32(1) + O.le32(1), b"".join(O.le32(v) for p in bad for v in p), 2)
+
+
+def test_paired_matches_separate(ctx):
+    # VariableBaseMSM.doubleMSM: one scalar vector on G1 and G2 bases (VariableBaseMSM.java:480-606)
+    rng = random.Random(77)
+    n = 300
+    k1, p1 = util.known_dlog_points(O.G1, 8, seed=5)
+    k2, p2 = util.known_dlog_points(O.G2, 8, seed=6)
+    b1 = [p1[i % 8] for i in range(n)]
+    b2 = [p2[i % 8] for i in range(n)]
+    scalars = [rng.randrange(O.R) for _ in range(n)]
+    out = ctx.msm_g1g2(O.pack_scalars(scalars), O.pack_g1(b1), O.pack_g2(b2), n)
+    assert len(out) == 288
+    e1, e2 = O.double_msm(scalars, b1, b2)
+    assert O.G1.equals(O.unpack_g1(out[:96])[0], e1)
+    assert O.G2.equals(O.unpack_g2(out[96:])[0], e2)
+
+
+@pytest.mark.parametrize("gname,log_n", [("G1", 14), ("G1", 16), ("G1", 18), ("G1", 20), ("G2", 14), ("G2", 16)])
+def test_large_known_dlog(ctx, gname, log_n):
+    """Sizes the oracle cannot add point by point: bases are tiled from 64 points with known discrete logs, so the
+    exact answer is (sum_i s_i k_{i mod 64}) G."""
+    G = O.G1 if gname == "G1" else O.G2
+    n = 1 << log_n
+    ks, pool = util.known_dlog_points(G, 64, seed=log_n, random_z=True)
+    raw = util.rand_scalars_bytes(n, seed=log_n)
+    bases = util.tiled_bases_bytes(G, pool, n)
+    fn = ctx.msm_g1 if G is O.G1 else ctx.msm_g2
+    out = fn(raw.tobytes(), bases.tobytes(), n)
+    exp = util.expected_from_dlogs(G, ks, util.column_sums(raw, 64))
+    assert G.equals(util.unpack_point(G, out), exp)
+
+
+def test_profiler_distribution_identical_bases(ctx):
+    """The reference profiler's input (VariableBaseMSMProfiling.java:20-31): N copies of the seed-10 generator and
+    scalars Fr(random long): half of them are r - |x|, so every high window has one bucket holding N/2 points, and
+    every bucket sees the same point again and again (doubling case)."""
+    n = 1 << 16
+    rng = O.JavaRandom(10)
+    g = O.G1.random(10)
+    scalars = [rng.next_long() % O.R for _ in range(n)]
+    out = ctx.msm_g1(O.pack_scalars(scalars), O.pack_g1([g]) * n, n)
+    exp = O.G1.mul(g, sum(scalars) % O.R)
+    assert O.G1.equals(O.unpack_g1(out)[0], exp)
+    stats = ctx.msm_last_stats()
+    assert stats[3] > 0 and stats[4] > 0          # the dense-bucket path really ran
+
+
+def test_device_resident_entry_point(ctx):
+    import torch
+    n = 1 << 12
+    ks, pool = util.known_dlog_points(O.G1, 16, seed=9)
+    raw = util.rand_scalars_bytes(n, seed=9)
+    bases = util.tiled_bases_bytes(O.G1, pool, n)
+    d_s = torch.from_numpy(raw.copy()).cuda()
+    d_b = torch.from_numpy(np.ascontiguousarray(bases)).cuda()
+    out = ctx.msm_g1_dev(d_s, d_b, n)
+    exp = util.expected_from_dlogs(O.G1, ks, util.column_sums(raw, 16))
+    assert O.G1.equals(O.unpack_g1(out)[0], exp)
