@@ -54,6 +54,8 @@ OZK_API void ozk_ctx_destroy(ozk_ctx* ctx);
 /* use an externally owned cudaStream_t (e.g. the caller's current stream) for all later work */
 OZK_API int ozk_ctx_set_stream(ozk_ctx* ctx, void* cuda_stream);
 OZK_API int ozk_ctx_sync(ozk_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py reports the per-step delta as gpu_launches) */
+OZK_API unsigned long long ozk_ctx_launches(ozk_ctx* ctx);
 OZK_API const char* ozk_last_error(void);
 OZK_API const char* ozk_version(void);
 
@@ -94,8 +96,23 @@ OZK_API int ozk_msm_g2(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* base
 OZK_API int ozk_msm_g2_dev(ozk_ctx* ctx, const void* d_scalars, const void* d_bases, size_t n, uint8_t out[192]);
 OZK_API int ozk_msm_g1g2(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* bases1, const uint8_t* bases2, size_t n, uint8_t out[288]);
 OZK_API int ozk_msm_g1g2_dev(ozk_ctx* ctx, const void* d_scalars, const void* d_bases1, const void* d_bases2, size_t n, uint8_t out[288]);
-/* shape of the last MSM on this context: {window bits, windows, buckets per window, overflow tasks, overflow buckets} */
+/* last MSM on this context: {window bits, windows, buckets per window, overflow tasks, overflow buckets,
+ * ms sort, ms convert, ms accumulate, ms merge, ms reduce+final} (device times from events on the context's stream;
+ * for the paired call the per-group phases are those of the G2 half) */
 OZK_API int ozk_msm_last_stats(ozk_ctx* ctx, double* out, int cap);
+
+/* ---- fixed-base batch MSM -----------------------------------------------------------------------------------
+ * out[i] = (scalars[i] mod 2^(outerc * windowSize)) * base, i.e. exactly the outerc windows of windowSize bits the
+ * reference walks (fixedbase_MSM_unit_processing_G1/G2, algebra_msm_FixedBaseMSM.cu:750-850; Java oracle
+ * FixedBaseMSM.serialMSM, src/main/java/algebra/msm/FixedBaseMSM.java:141-167).  Replaces
+ * Java_algebra_msm_FixedBaseMSM_batchMSMNativeHelper (algebra_msm_FixedBaseMSM.cu:1276-1384); the paired
+ * ...doubleBatchMSMNativeHelper (:1395-1491) is one G1 and one G2 call on the same scalars.
+ * base: one point (G1 96 B / G2 192 B), host memory in both variants.  scalars: n x 32 B (< r).
+ * out: n points in the wire layout, normalised to Z = 1 (infinity as (0,1,0)).  The window table is cached on the context. */
+OZK_API int ozk_fixed_g1(ozk_ctx* ctx, const uint8_t base[96], const uint8_t* scalars, size_t n, int outerc, int windowSize, uint8_t* out);
+OZK_API int ozk_fixed_g1_dev(ozk_ctx* ctx, const uint8_t base[96], const void* d_scalars, size_t n, int outerc, int windowSize, void* d_out);
+OZK_API int ozk_fixed_g2(ozk_ctx* ctx, const uint8_t base[192], const uint8_t* scalars, size_t n, int outerc, int windowSize, uint8_t* out);
+OZK_API int ozk_fixed_g2_dev(ozk_ctx* ctx, const uint8_t base[192], const void* d_scalars, size_t n, int outerc, int windowSize, void* d_out);
 
 /* ---- diagnostics ----------------------------------------------------------------------------------------- */
 /* Integer-pipe microbenchmark: independent 32x32+64 multiply-add chains on every SM; reports billions of

@@ -103,6 +103,7 @@ int ozk_ctx_create(int device, ozk_ctx** out) {
     OZK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     OZK_CUDA(cudaEventCreate(&c->ev0));
     OZK_CUDA(cudaEventCreate(&c->ev1));
+    for (auto& e : c->evs) OZK_CUDA(cudaEventCreate(&e));
     OZK_CUDA(cudaMallocHost(&c->pinned, 4096));
     *out = c;
     return OZK_OK;
@@ -121,6 +122,7 @@ void ozk_ctx_destroy(ozk_ctx* c) {
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    for (auto& e : c->evs) if (e) cudaEventDestroy(e);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -134,6 +136,8 @@ int ozk_ctx_set_stream(ozk_ctx* c, void* s) {
     return OZK_OK;
 }
 
+unsigned long long ozk_ctx_launches(ozk_ctx* c) { return c ? c->launches : 0; }
+
 int ozk_ctx_sync(ozk_ctx* c) {
     OZK_TRY(ctx_enter(c));
     OZK_CUDA(cudaStreamSynchronize(c->stream));
@@ -144,6 +148,7 @@ static int time_kernel(ozk_ctx* c, void (*k)(uint32_t*, uint32_t, int), int iter
     OZK_TRY(c->io_out.reserve(256, c->stream));
     int grid = c->sm_count * 8;
     k<<<grid, 256, 0, c->stream>>>((uint32_t*)c->io_out.p, 1u, 16);   // warm-up
+    c->launches += 4;
     float best = 1e30f;
     for (int rep = 0; rep < 3; rep++) {
         OZK_CUDA(cudaEventRecord(c->ev0, c->stream));

@@ -76,12 +76,14 @@ struct ozk_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = true;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t evs[8] = {};                   // phase marks of the last MSM (see ozk_msm_last_stats)
+    unsigned long long launches = 0;           // kernels launched through this context
     // scratch
     ozk::DevBuf io_a, io_b, io_c, io_out;     // staging for the host-pointer entry points
     ozk::DevBuf work;                          // NTT ping-pong buffer
     ozk::DevBuf msm[12];                       // MSM pipeline buffers (see msm.cu)
     ozk::DevBuf fb[4];                         // fixed-base buffers
-    double msm_stats[8] = {};                  // last MSM: window c, windows, buckets/window, overflow tasks, overflow buckets
+    double msm_stats[16] = {};                  // last MSM: window c, windows, buckets/window, overflow tasks, overflow buckets
     void* pinned = nullptr;                    // small pinned host block for flags / results
     std::map<std::string, ozk::NttPlan*> ntt_plans;
     std::map<std::string, ozk::FixedTable*> fixed_tables;

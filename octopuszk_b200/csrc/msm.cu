@@ -180,6 +180,7 @@ static int msm_sort(ozk_ctx* ctx, const void* d_scalars, size_t n, const MsmShap
                                        (OvfBucket*)ctx->msm[B_OVFBUCKET].p, misc + 2, sh.ovf_task_cap, sh.ovf_bucket_cap);
     msm_digits<1><<<grid, 256, 0, st>>>((const uint4*)d_scalars, n, sh.c, sh.nwin, (uint32_t*)ctx->msm[B_CURSOR].p,
                                         (uint32_t*)ctx->msm[B_SORTED].p, misc);
+    ctx->launches += 3;
     OZK_CUDA(cudaGetLastError());
     return OZK_OK;
 }
@@ -192,12 +193,17 @@ static int msm_buckets(ozk_ctx* ctx, const MsmLaunch& L, const void* d_bases, si
     OZK_TRY(ctx->msm[aff_slot].reserve(n * L.affine_bytes, st));
     OZK_TRY(ctx->msm[B_BUCKETS].reserve(nbt * L.xyzz_bytes, st));
     OZK_TRY(ctx->msm[B_OVFPART].reserve((size_t)sh.ovf_task_cap * L.xyzz_bytes, st));
+    OZK_CUDA(cudaEventRecord(ctx->evs[1], st));
     if (L.convert(st, d_bases, ctx->msm[aff_slot].p, n, misc, ctx->sm_count)) { set_error("msm: convert launch failed"); return OZK_ERR_CUDA; }
+    OZK_CUDA(cudaEventRecord(ctx->evs[2], st));
     if (L.accumulate(st, ctx->msm[aff_slot].p, (const uint32_t*)ctx->msm[B_SORTED].p, (const uint32_t*)ctx->msm[B_START].p,
                      (const uint32_t*)ctx->msm[B_COUNT].p, (const OvfTask*)ctx->msm[B_OVFTASK].p, misc + 1, (uint32_t)nbt, sh.log_nb, n,
                      sh.ovf_task_cap, ctx->msm[B_BUCKETS].p, ctx->msm[B_OVFPART].p)) { set_error("msm: accumulate launch failed"); return OZK_ERR_CUDA; }
+    OZK_CUDA(cudaEventRecord(ctx->evs[3], st));
     if (L.merge(st, (const OvfBucket*)ctx->msm[B_OVFBUCKET].p, misc + 2, std::min<uint32_t>(sh.ovf_bucket_cap, (uint32_t)nbt),
                 ctx->msm[B_OVFPART].p, ctx->msm[B_BUCKETS].p)) { set_error("msm: merge launch failed"); return OZK_ERR_CUDA; }
+    OZK_CUDA(cudaEventRecord(ctx->evs[4], st));
+    ctx->launches += 3;
 
     // hierarchical reduction.  scratch layout (in XYZZ elements per window): level arrays A_1.., acc arrays, sum temporaries
     uint32_t m[8], nlev = 0;
@@ -231,6 +237,7 @@ static int msm_buckets(ozk_ctx* ctx, const MsmLaunch& L, const void* d_bases, si
         void* run = take(m[l + 1]);
         void* acc = take(m[l + 1]);
         if (L.wsum(st, level_in, m[l], sh.nwin, run, acc)) { set_error("msm: wsum launch failed"); return OZK_ERR_CUDA; }
+        ctx->launches += 1;
         // sum acc over its m[l+1] groups
         const void* cur = acc;
         uint32_t k = m[l + 1];
@@ -238,6 +245,7 @@ static int msm_buckets(ozk_ctx* ctx, const MsmLaunch& L, const void* d_bases, si
             uint32_t k2 = (k + kWsumS - 1) / kWsumS;
             void* nxt = take(k2);
             if (L.sum(st, cur, k, sh.nwin, nxt)) { set_error("msm: sum launch failed"); return OZK_ERR_CUDA; }
+            ctx->launches += 1;
             cur = nxt;
             k = k2;
         }
@@ -250,6 +258,8 @@ static int msm_buckets(ozk_ctx* ctx, const MsmLaunch& L, const void* d_bases, si
     fa.c = sh.c;
     void* window_vals = take(1);
     if (L.final(st, fa, window_vals, d_out)) { set_error("msm: final launch failed"); return OZK_ERR_CUDA; }
+    ctx->launches += 1;
+    OZK_CUDA(cudaEventRecord(ctx->evs[5], st));
     OZK_CUDA(cudaGetLastError());
     return OZK_OK;
 }
@@ -263,6 +273,11 @@ static int msm_finish(ozk_ctx* ctx, const void* d_res, size_t bytes, uint8_t* ou
     const uint32_t* misc = (const uint32_t*)(pin + 1024);
     ctx->msm_stats[3] = misc[1];
     ctx->msm_stats[4] = misc[2];
+    for (int k = 0; k < 5; k++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->evs[k], ctx->evs[k + 1]) != cudaSuccess) { ms = -1.f; cudaGetLastError(); }
+        ctx->msm_stats[5 + k] = ms;
+    }
     if (misc[0] & 1u) { set_error("msm: a base coordinate is not reduced mod p"); return OZK_ERR_DOMAIN; }
     if (misc[0] & 2u) { set_error("msm: a scalar is not reduced mod r"); return OZK_ERR_DOMAIN; }
     memcpy(out, pin, bytes);
@@ -278,6 +293,7 @@ static void write_inf(uint8_t* out, size_t coord_bytes) {
 static int msm_run(ozk_ctx* ctx, const void* d_scalars, const void* d_b1, const void* d_b2, size_t n, uint8_t* out) {
     OZK_ARG(n > 0 && n < ((size_t)1 << 31), "msm: between 1 and 2^31 - 1 points per call");
     const MsmShape sh = msm_shape(n);
+    OZK_CUDA(cudaEventRecord(ctx->evs[0], ctx->stream));
     ctx->msm_stats[0] = sh.c;
     ctx->msm_stats[1] = sh.nwin;
     ctx->msm_stats[2] = sh.nb;
@@ -365,7 +381,7 @@ int ozk_msm_g1g2(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* bases1, co
 
 int ozk_msm_last_stats(ozk_ctx* ctx, double* out, int cap) {
     if (!ctx || !out) return 0;
-    int k = cap < 5 ? cap : 5;
+    int k = cap < 10 ? cap : 10;
     for (int i = 0; i < k; i++) out[i] = ctx->msm_stats[i];
     return k;
 }

@@ -1,6 +1,7 @@
-// G2 (Fq2) instantiation of the MSM kernels.
+// G2 (Fq2) instantiation of the MSM and fixed-base kernels.
 #include "common.h"
-#include "msm_impl.cuh"
+#include "fixed_impl.cuh"
 namespace ozk {
 OZK_DEFINE_MSM_LAUNCH(Fq2, kMsmG2)
+OZK_DEFINE_FIXED_LAUNCH(Fq2, kFixedG2)
 }  // namespace ozk

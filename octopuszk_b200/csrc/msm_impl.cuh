@@ -276,12 +276,12 @@ __global__ void __launch_bounds__(128) msm_wsum_level(const uint4* __restrict__ 
     XYZZ<F> run = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
     for (int j = (int)len - 1; j >= 1; j--) {
         XYZZ<F> q = load_xyzz<F>(in, base + j);
-        xyzz_add_ni(run, q);
-        xyzz_add_ni(acc, run);
+        xyzz_add(run, q);
+        xyzz_add(acc, run);
     }
     {
         XYZZ<F> q = load_xyzz<F>(in, base);
-        xyzz_add_ni(run, q);
+        xyzz_add(run, q);
     }
     store_xyzz<F>(run_out, (size_t)w * groups + g, run);
     store_xyzz<F>(acc_out, (size_t)w * groups + g, acc);
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(128) msm_sum_level(const uint4* __restrict__ i
     XYZZ<F> s = XYZZ<F>::inf();
     for (uint32_t j = 0; j < len; j++) {
         XYZZ<F> q = load_xyzz<F>(in, base + j);
-        xyzz_add_ni(s, q);
+        xyzz_add(s, q);
     }
     store_xyzz<F>(out, (size_t)w * groups + g, s);
 }
@@ -324,21 +324,21 @@ __global__ void msm_final(FinalArgs a, uint4* __restrict__ window_vals, uint4* _
     if (w < a.nwin) {
         XYZZ<F> T = XYZZ<F>::inf();
         for (int l = (int)a.nlevels - 1; l >= 0; l--) {
-            for (int d = 0; d < kWsumLogS; d++) xyzz_dbl_ni(T);
+            for (int d = 0; d < kWsumLogS; d++) T = xyzz_dbl(T);
             XYZZ<F> q = load_xyzz<F>(a.sum_acc[l], w);
-            xyzz_add_ni(T, q);
+            xyzz_add(T, q);
         }
         XYZZ<F> tot = load_xyzz<F>(a.total, w);
-        xyzz_add_ni(T, tot);
+        xyzz_add(T, tot);
         store_xyzz<F>(window_vals, w, T);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         XYZZ<F> res = XYZZ<F>::inf();
         for (int ww = (int)a.nwin - 1; ww >= 0; ww--) {
-            for (uint32_t d = 0; d < a.c; d++) xyzz_dbl_ni(res);
+            for (uint32_t d = 0; d < a.c; d++) res = xyzz_dbl(res);
             XYZZ<F> q = load_xyzz<F>(window_vals, ww);
-            xyzz_add_ni(res, q);
+            xyzz_add(res, q);
         }
         Jacobian<F> j = xyzz_to_jacobian(res);
         FieldIO<F>::store(out, F::from_mont(j.x));

@@ -426,6 +426,7 @@ static int launch_pass(ozk_ctx* ctx, int log_t, const PassArgs& a, uint32_t grid
         attr_done[ctx->device & 63] = true;
     }
     ntt_pass_kernel<LAST><<<grid, threads, smem, ctx->stream>>>(a);
+    ctx->launches += 1;
     OZK_CUDA(cudaGetLastError());
     return OZK_OK;
 }
@@ -523,6 +524,7 @@ static int scale_powers(ozk_ctx* ctx, const void* d_in, void* d_out, size_t n, c
     size_t blocks = (n + 255) / 256;
     size_t cap = (size_t)ctx->sm_count * 8;
     if (blocks > cap) blocks = cap;
+    ctx->launches += 1;
     fr_scale_powers_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>((const uint4*)d_in, (uint4*)d_out, n, s, g, scale ? 1 : 0, coset ? 1 : 0);
     OZK_CUDA(cudaGetLastError());
     return OZK_OK;

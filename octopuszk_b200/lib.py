@@ -36,6 +36,7 @@ SIGNATURES = {
     "ozk_ctx_destroy": (None, [_vp]),
     "ozk_ctx_set_stream": (_int, [_vp, _vp]),
     "ozk_ctx_sync": (_int, [_vp]),
+    "ozk_ctx_launches": (ctypes.c_ulonglong, [_vp]),
     "ozk_last_error": (ctypes.c_char_p, []),
     "ozk_version": (ctypes.c_char_p, []),
     "ozk_fr_scale": (_int, [_vp, _vp, _sz, _c_u8p, _vp]),
@@ -52,10 +53,10 @@ SIGNATURES = {
     "ozk_msm_g2_dev": (_int, [_vp, _vp, _vp, _sz, _vp]),
     "ozk_msm_g1g2": (_int, [_vp, _vp, _vp, _vp, _sz, _vp]),
     "ozk_msm_g1g2_dev": (_int, [_vp, _vp, _vp, _vp, _sz, _vp]),
-#    "ozk_fixed_g1": (_int, [_vp, _c_u8p, _vp, _sz, _int, _int, _vp]),
-#    "ozk_fixed_g1_dev": (_int, [_vp, _c_u8p, _vp, _sz, _int, _int, _vp]),
-#    "ozk_fixed_g2": (_int, [_vp, _c_u8p, _vp, _sz, _int, _int, _vp]),
-#    "ozk_fixed_g2_dev": (_int, [_vp, _c_u8p, _vp, _sz, _int, _int, _vp]),
+    "ozk_fixed_g1": (_int, [_vp, _c_u8p, _vp, _sz, _int, _int, _vp]),
+    "ozk_fixed_g1_dev": (_int, [_vp, _c_u8p, _vp, _sz, _int, _int, _vp]),
+    "ozk_fixed_g2": (_int, [_vp, _c_u8p, _vp, _sz, _int, _int, _vp]),
+    "ozk_fixed_g2_dev": (_int, [_vp, _c_u8p, _vp, _sz, _int, _int, _vp]),
     "ozk_msm_last_stats": (_int, [_vp, ctypes.POINTER(ctypes.c_double), _int]),
     # MSM_END
 }
@@ -130,6 +131,9 @@ class Context:
 
     def sync(self):
         self._check(self.lib.ozk_ctx_sync(self._h))
+
+    def launches(self) -> int:
+        return int(self.lib.ozk_ctx_launches(self._h))
 
     # ---- diagnostics
     def imad_peak(self) -> float:

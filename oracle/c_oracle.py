@@ -1,0 +1,81 @@
+"""ctypes loader for oracle/dizk_oracle.c (test infrastructure: see that file's header).  Only tests/, smoke() and
+bench.py's cpu_baseline / --impl reference legs import this."""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libdizk_oracle.so")
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    src = os.path.join(_HERE, "dizk_oracle.c")
+    if not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE])
+    lib = ctypes.CDLL(_SO)
+    vp, sz, i = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+    lib.oracle_msm_g1.argtypes = [vp, vp, sz, i, vp]
+    lib.oracle_g1_equal.argtypes = [vp, vp]
+    lib.oracle_g1_to_affine.argtypes = [vp, vp]
+    lib.oracle_fft_fr.argtypes = [vp, sz, vp]
+    lib.oracle_fft_fr_batch.argtypes = [vp, sz, sz, vp, i]
+    lib.oracle_fixed_g1.argtypes = [vp, vp, sz, i, i, i, vp]
+    lib.oracle_fr_scale.argtypes = [vp, sz, vp, vp]
+    _lib = lib
+    return lib
+
+
+def max_threads() -> int:
+    return load().oracle_max_threads()
+
+
+def _addr(x):
+    if isinstance(x, (bytes, ctypes.Array)):
+        return x
+    if hasattr(x, "ctypes"):
+        return x.ctypes.data
+    raise TypeError(type(x))
+
+
+def msm_g1(scalars, bases, n: int, threads: int = 1) -> bytes:
+    out = ctypes.create_string_buffer(96)
+    assert load().oracle_msm_g1(_addr(scalars), _addr(bases), n, threads, out) == 0
+    return out.raw
+
+
+def g1_equal(a: bytes, b: bytes) -> bool:
+    return bool(load().oracle_g1_equal(a, b))
+
+
+def g1_to_affine(a: bytes) -> bytes:
+    out = ctypes.create_string_buffer(96)
+    load().oracle_g1_to_affine(a, out)
+    return out.raw
+
+
+def fft_fr(data: bytes, omega: bytes) -> bytes:
+    n = len(data) // 32
+    buf = ctypes.create_string_buffer(bytes(data), len(data))
+    assert load().oracle_fft_fr(buf, n, omega) == 0
+    return buf.raw
+
+
+def fft_fr_batch_inplace(buf, n: int, batch: int, omega: bytes, threads: int):
+    assert load().oracle_fft_fr_batch(_addr(buf), n, batch, omega, threads) == 0
+
+
+def fixed_g1(base: bytes, scalars, n: int, scalar_size: int, window: int, threads: int = 1) -> bytes:
+    out = ctypes.create_string_buffer(96 * n)
+    assert load().oracle_fixed_g1(base, _addr(scalars), n, scalar_size, window, threads, out) == 0
+    return out.raw
+
+
+def fr_scale(a: bytes, b: bytes) -> bytes:
+    n = len(a) // 32
+    out = ctypes.create_string_buffer(32 * n)
+    load().oracle_fr_scale(a, n, b, out)
+    return out.raw
