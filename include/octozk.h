@@ -65,6 +65,12 @@ OZK_API const char* ozk_version(void);
 OZK_API int ozk_fr_scale(ozk_ctx* ctx, const uint8_t* a, size_t n, const uint8_t b[32], uint8_t* out);
 OZK_API int ozk_fr_scale_dev(ozk_ctx* ctx, const void* d_a, void* d_out, size_t n, const uint8_t b[32]);
 
+/* out[i] = a[i] * scale * coset^i (scale and/or coset may be NULL = 1).  FFTAuxiliary.multiplyByCoset
+ * (src/main/java/algebra/fft/FFTAuxiliary.java:224-232) and distributedMultiplyByCoset (:237-243) with `first_index` as the
+ * global index of a[0], so a shard of a larger vector can be scaled in place. */
+OZK_API int ozk_fr_scale_powers_dev(ozk_ctx* ctx, const void* d_a, void* d_out, size_t n, const uint8_t* scale, const uint8_t* coset,
+                            uint64_t first_index);
+
 /* ---- radix-2 NTT over Fr ---------------------------------------------------------------------------------
  * out[k] = sum_j in[j] * omega^(j k), natural order in and out, n a power of two <= 2^28, omega a primitive n-th
  * root of unity.  Replaces FFTAuxiliary.serialRadix2FFT (src/main/java/algebra/fft/FFTAuxiliary.java:60-124) and the
@@ -80,6 +86,12 @@ OZK_API int ozk_ntt_fr_dev(ozk_ctx* ctx, const void* d_in, void* d_out, size_t n
  *   divideByZOnCoset      : folds into post_scale */
 OZK_API int ozk_ntt_fr_ex_dev(ozk_ctx* ctx, const void* d_in, void* d_out, size_t n, const uint8_t omega[32],
                       const uint8_t* pre_coset, const uint8_t* post_scale, const uint8_t* post_coset);
+
+/* Cross-shard step of the multi-GPU transform (four-step with n = G * M, see octopuszk_b200/distributed.py, replacing the
+ * two Spark shuffles of FFTAuxiliary.distributedRadix2FFT, src/main/java/algebra/fft/FFTAuxiliary.java:129-219):
+ * out[k1 * len + j] = sum_{i1 < groups} in[i1 * len + j] * omega_g^(i1 k1), groups in {1,2,4,8}, omega_g a primitive
+ * groups-th root of unity.  d_in != d_out. */
+OZK_API int ozk_fr_dft_small_dev(ozk_ctx* ctx, const void* d_in, void* d_out, size_t groups, size_t len, const uint8_t omega_g[32]);
 
 /* ---- variable-base MSM --------------------------------------------------------------------------------------
  * out = sum_i scalars[i] * bases[i].  Replaces VariableBaseMSM.serialMSM's native leg

@@ -1,0 +1,336 @@
+// JNI shims: the six native methods the reference's Java declares, bound to the C ABI of include/octozk.h.
+//
+// Built three times (build.py) into the three libraries the Java static initialisers load:
+//   -DOZK_SHIM_VARMSM   -> libAlgebraMSMVariableBaseMSM.so  (System.loadLibrary, src/main/java/algebra/msm/VariableBaseMSM.java:31-34)
+//   -DOZK_SHIM_FIXEDMSM -> libAlgebraMSMFixedBaseMSM.so     (src/main/java/algebra/msm/FixedBaseMSM.java:44-47)
+//   -DOZK_SHIM_FFT      -> libAlgebraFFTAuxiliary.so        (src/main/java/algebra/fft/SerialFFT.java:20-23)
+// Symbol names, argument order and byte layouts are those of the javah headers (algebra_msm_VariableBaseMSM.h:10-24,
+// algebra_msm_FixedBaseMSM.h:10-32, algebra_fft_FFTAuxiliary.h:10-16) and of SURVEY.md Appendix A.  What changes:
+//   * arrays are pinned with Get/ReleasePrimitiveArrayCritical(JNI_ABORT) -- the reference calls GetByteArrayElements
+//     and never releases (algebra_msm_VariableBaseMSM.cu:1624,1634);
+//   * errors become java.lang.RuntimeException via ThrowNew and a NULL return -- the reference prints and continues or
+//     exit(-1)s (algebra_msm_VariableBaseMSM.cu:23-28,1417-1422);
+//   * one liboctozk context per (thread, device): Spark executor threads enter concurrently (hs_err_pid98479.log:260-272);
+//   * device = taskID % deviceCount as in the reference (algebra_msm_VariableBaseMSM.cu:1248-1257).
+// The "...Direct" natives take java.nio direct ByteBuffers of 32-byte elements in and out (no per-element BigInteger
+// marshalling, no 64-byte padding): the Java edits that call them are in INTEGRATION.md.
+// No JVM exists in this image: the shims are exercised through a fake JNIEnv (tests/fake_jni.cc).
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <vector>
+
+#include "jni_min.h"
+#include "octozk.h"
+
+namespace {
+
+struct ThreadCtx {
+    std::map<int, ozk_ctx*> by_device;
+    ~ThreadCtx() {
+        for (auto& kv : by_device) ozk_ctx_destroy(kv.second);
+    }
+};
+
+ozk_ctx* context_for_task(jint task_id) {
+    static thread_local ThreadCtx tc;
+    int ndev = ozk_device_count();
+    if (ndev <= 0) return nullptr;
+    int dev = (int)(((long long)task_id % ndev + ndev) % ndev);
+    auto it = tc.by_device.find(dev);
+    if (it != tc.by_device.end()) return it->second;
+    ozk_ctx* c = nullptr;
+    if (ozk_ctx_create(dev, &c) != OZK_OK) return nullptr;
+    tc.by_device[dev] = c;
+    return c;
+}
+
+jbyteArray fail(JNIEnv* env, const char* where) {
+    char msg[640];
+    snprintf(msg, sizeof msg, "%s: %s", where, ozk_last_error());
+    jclass cls = env->FindClass("java/lang/RuntimeException");
+    if (cls) env->ThrowNew(cls, msg);
+    return nullptr;
+}
+jbyteArray fail_msg(JNIEnv* env, const char* msg) {
+    jclass cls = env->FindClass("java/lang/RuntimeException");
+    if (cls) env->ThrowNew(cls, msg);
+    return nullptr;
+}
+
+// RAII pin of a Java byte[]
+struct Pinned {
+    JNIEnv* env;
+    jbyteArray arr;
+    void* p;
+    Pinned(JNIEnv* e, jbyteArray a) : env(e), arr(a), p(a ? e->GetPrimitiveArrayCritical(a, nullptr) : nullptr) {}
+    ~Pinned() {
+        if (p) env->ReleasePrimitiveArrayCritical(arr, p, JNI_ABORT);
+    }
+    const uint8_t* bytes() const { return (const uint8_t*)p; }
+};
+
+// 32-byte little-endian coordinates -> 64-byte slots, little-endian (variable-base, FFT) or big-endian (fixed-base,
+// field batch): SURVEY.md Appendix A.1 / A.2.
+void widen(const uint8_t* in, size_t coords, uint8_t* out, bool big_endian) {
+    for (size_t k = 0; k < coords; k++) {
+        uint8_t* o = out + 64 * k;
+        const uint8_t* s = in + 32 * k;
+        memset(o, 0, 64);
+        if (big_endian) {
+            for (int j = 0; j < 32; j++) o[63 - j] = s[j];
+        } else {
+            memcpy(o, s, 32);
+        }
+    }
+}
+
+jbyteArray to_java(JNIEnv* env, const std::vector<uint8_t>& v) {
+    if (v.size() > 0x7fffffffu) return fail_msg(env, "result exceeds the 2 GiB limit of a Java byte[]");
+    jbyteArray out = env->NewByteArray((jsize)v.size());
+    if (!out) return nullptr;
+    env->SetByteArrayRegion(out, 0, (jsize)v.size(), (const jbyte*)v.data());
+    return out;
+}
+
+bool long_enough(JNIEnv* env, jbyteArray a, size_t need) { return a && (size_t)env->GetArrayLength(a) >= need; }
+
+}  // namespace
+
+extern "C" {
+
+#ifdef OZK_SHIM_VARMSM
+// algebra_msm_VariableBaseMSM.h:10-16, reference implementation algebra_msm_VariableBaseMSM.cu:1614-1695
+JNIEXPORT jbyteArray JNICALL Java_algebra_msm_VariableBaseMSM_variableBaseSerialMSMNativeHelper(
+    JNIEnv* env, jclass, jbyteArray basesXYZ, jbyteArray scalars, jint batch_size, jint type, jint taskID) {
+    if (batch_size < 0) return fail_msg(env, "variableBaseSerialMSMNativeHelper: negative batch_size");
+    const size_t n = (size_t)batch_size;
+    const bool g1 = (type == 1);                     // anything else is G2, like the reference (:1631,:1661)
+    if (!long_enough(env, scalars, n * 32) || !long_enough(env, basesXYZ, n * (g1 ? 96 : 192)))
+        return fail_msg(env, "variableBaseSerialMSMNativeHelper: input arrays shorter than batch_size elements");
+    ozk_ctx* ctx = context_for_task(taskID);
+    if (!ctx) return fail(env, "variableBaseSerialMSMNativeHelper");
+    uint8_t res[192];
+    int rc;
+    {
+        Pinned s(env, scalars), b(env, basesXYZ);
+        if ((n && (!s.p || !b.p))) return fail_msg(env, "variableBaseSerialMSMNativeHelper: could not pin the input arrays");
+        rc = g1 ? ozk_msm_g1(ctx, s.bytes(), b.bytes(), n, res) : ozk_msm_g2(ctx, s.bytes(), b.bytes(), n, res);
+    }
+    if (rc != OZK_OK) return fail(env, "variableBaseSerialMSMNativeHelper");
+    std::vector<uint8_t> out(g1 ? 192 : 384);
+    widen(res, g1 ? 3 : 6, out.data(), false);
+    return to_java(env, out);
+}
+
+// algebra_msm_VariableBaseMSM.h:18-24, reference implementation algebra_msm_VariableBaseMSM.cu:1712-1788
+JNIEXPORT jbyteArray JNICALL Java_algebra_msm_VariableBaseMSM_variableBaseDoubleMSMNativeHelper(
+    JNIEnv* env, jclass, jbyteArray bases1, jbyteArray bases2, jbyteArray scalars, jint batch_size, jint taskID) {
+    if (batch_size < 0) return fail_msg(env, "variableBaseDoubleMSMNativeHelper: negative batch_size");
+    const size_t n = (size_t)batch_size;
+    if (!long_enough(env, scalars, n * 32) || !long_enough(env, bases1, n * 96) || !long_enough(env, bases2, n * 192))
+        return fail_msg(env, "variableBaseDoubleMSMNativeHelper: input arrays shorter than batch_size elements");
+    ozk_ctx* ctx = context_for_task(taskID);
+    if (!ctx) return fail(env, "variableBaseDoubleMSMNativeHelper");
+    uint8_t res[288];
+    int rc;
+    {
+        Pinned s(env, scalars), b1(env, bases1), b2(env, bases2);
+        if (n && (!s.p || !b1.p || !b2.p)) return fail_msg(env, "variableBaseDoubleMSMNativeHelper: could not pin the input arrays");
+        rc = ozk_msm_g1g2(ctx, s.bytes(), b1.bytes(), b2.bytes(), n, res);
+    }
+    if (rc != OZK_OK) return fail(env, "variableBaseDoubleMSMNativeHelper");
+    std::vector<uint8_t> out(576);
+    widen(res, 9, out.data(), false);                // G1 (X,Y,Z) || G2 (Xa,Xb,Ya,Yb,Za,Zb), :1781-1784
+    return to_java(env, out);
+}
+
+// North-star variant: direct ByteBuffers, 32-byte elements in and out.  type 1 = G1, 2 = G2, 3 = paired (bases2 used).
+// `out` receives 96 / 192 / 288 bytes.  Returns 0, or throws RuntimeException and returns -1.
+JNIEXPORT jint JNICALL Java_algebra_msm_VariableBaseMSM_variableBaseMSMDirect(
+    JNIEnv* env, jclass, jobject bases1, jobject bases2, jobject scalars, jint batch_size, jint type, jint taskID, jobject out) {
+    const size_t n = batch_size < 0 ? 0 : (size_t)batch_size;
+    const uint8_t* s = scalars ? (const uint8_t*)env->GetDirectBufferAddress(scalars) : nullptr;
+    const uint8_t* b1 = bases1 ? (const uint8_t*)env->GetDirectBufferAddress(bases1) : nullptr;
+    const uint8_t* b2 = bases2 ? (const uint8_t*)env->GetDirectBufferAddress(bases2) : nullptr;
+    uint8_t* o = out ? (uint8_t*)env->GetDirectBufferAddress(out) : nullptr;
+    const size_t out_need = type == 1 ? 96 : type == 2 ? 192 : 288;
+    if (batch_size < 0 || !o || (size_t)env->GetDirectBufferCapacity(out) < out_need ||
+        (n && (!s || (size_t)env->GetDirectBufferCapacity(scalars) < n * 32)) ||
+        (n && type != 2 && (!b1 || (size_t)env->GetDirectBufferCapacity(bases1) < n * 96)) ||
+        (n && type != 1 && (!b2 || (size_t)env->GetDirectBufferCapacity(bases2) < n * 192))) {
+        fail_msg(env, "variableBaseMSMDirect: buffers must be direct and hold batch_size elements");
+        return -1;
+    }
+    ozk_ctx* ctx = context_for_task(taskID);
+    if (!ctx) { fail(env, "variableBaseMSMDirect"); return -1; }
+    int rc = type == 1 ? ozk_msm_g1(ctx, s, b1, n, o) : type == 2 ? ozk_msm_g2(ctx, s, b2, n, o) : ozk_msm_g1g2(ctx, s, b1, b2, n, o);
+    if (rc != OZK_OK) { fail(env, "variableBaseMSMDirect"); return -1; }
+    return 0;
+}
+#endif  // OZK_SHIM_VARMSM
+
+#ifdef OZK_SHIM_FIXEDMSM
+// algebra_msm_FixedBaseMSM.h:10-16, reference implementation algebra_msm_FixedBaseMSM.cu:1276-1384.
+// out_len / inner_len / scalarSize describe the reference's own table and are not needed: the result is defined by
+// outerc windows of windowSize bits (algebra_msm_FixedBaseMSM.cu:765-779).
+JNIEXPORT jbyteArray JNICALL Java_algebra_msm_FixedBaseMSM_batchMSMNativeHelper(
+    JNIEnv* env, jclass, jint outerc, jint windowSize, jint out_len, jint inner_len, jint batch_size, jint scalarSize,
+    jbyteArray base, jbyteArray scalars, jint BNType, jint taskID) {
+    (void)out_len; (void)inner_len; (void)scalarSize;
+    if (batch_size < 0) return fail_msg(env, "batchMSMNativeHelper: negative batch_size");
+    const size_t n = (size_t)batch_size;
+    const bool g1 = (BNType == 1);
+    const size_t pt = g1 ? 96 : 192;
+    if (!long_enough(env, scalars, n * 32) || !long_enough(env, base, pt))
+        return fail_msg(env, "batchMSMNativeHelper: input arrays too short");
+    if (n * pt * 2 > 0x7fffffffu) return fail_msg(env, "batchMSMNativeHelper: result exceeds the 2 GiB limit of a Java byte[]");
+    ozk_ctx* ctx = context_for_task(taskID);
+    if (!ctx) return fail(env, "batchMSMNativeHelper");
+    std::vector<uint8_t> res(n * pt);
+    int rc;
+    {
+        Pinned s(env, scalars), b(env, base);
+        if (!b.p || (n && !s.p)) return fail_msg(env, "batchMSMNativeHelper: could not pin the input arrays");
+        rc = g1 ? ozk_fixed_g1(ctx, b.bytes(), s.bytes(), n, outerc, windowSize, res.data())
+                : ozk_fixed_g2(ctx, b.bytes(), s.bytes(), n, outerc, windowSize, res.data());
+    }
+    if (rc != OZK_OK) return fail(env, "batchMSMNativeHelper");
+    std::vector<uint8_t> out(n * pt * 2);
+    widen(res.data(), n * (g1 ? 3 : 6), out.data(), true);       // 64-byte big-endian coordinates, :783-787
+    return to_java(env, out);
+}
+
+// algebra_msm_FixedBaseMSM.h:18-24, reference implementation algebra_msm_FixedBaseMSM.cu:1395-1491:
+// element i of the result = G1 (X,Y,Z) || G2 (Xa,Xb,Ya,Yb,Za,Zb), 9 x 64 bytes big-endian.
+JNIEXPORT jbyteArray JNICALL Java_algebra_msm_FixedBaseMSM_doubleBatchMSMNativeHelper(
+    JNIEnv* env, jclass, jint outerc1, jint windowSize1, jint outerc2, jint windowSize2, jint out_len1, jint inner_len1,
+    jint out_len2, jint inner_len2, jint batch_size, jbyteArray baseG1, jbyteArray baseG2, jbyteArray scalars, jint taskID) {
+    (void)out_len1; (void)inner_len1; (void)out_len2; (void)inner_len2;
+    if (batch_size < 0) return fail_msg(env, "doubleBatchMSMNativeHelper: negative batch_size");
+    const size_t n = (size_t)batch_size;
+    if (!long_enough(env, scalars, n * 32) || !long_enough(env, baseG1, 96) || !long_enough(env, baseG2, 192))
+        return fail_msg(env, "doubleBatchMSMNativeHelper: input arrays too short");
+    if (n * 576 > 0x7fffffffu) return fail_msg(env, "doubleBatchMSMNativeHelper: result exceeds the 2 GiB limit of a Java byte[]");
+    ozk_ctx* ctx = context_for_task(taskID);
+    if (!ctx) return fail(env, "doubleBatchMSMNativeHelper");
+    std::vector<uint8_t> r1(n * 96), r2(n * 192);
+    int rc;
+    {
+        Pinned s(env, scalars), b1(env, baseG1), b2(env, baseG2);
+        if (!b1.p || !b2.p || (n && !s.p)) return fail_msg(env, "doubleBatchMSMNativeHelper: could not pin the input arrays");
+        rc = ozk_fixed_g1(ctx, b1.bytes(), s.bytes(), n, outerc1, windowSize1, r1.data());
+        if (rc == OZK_OK) rc = ozk_fixed_g2(ctx, b2.bytes(), s.bytes(), n, outerc2, windowSize2, r2.data());
+    }
+    if (rc != OZK_OK) return fail(env, "doubleBatchMSMNativeHelper");
+    std::vector<uint8_t> out(n * 576);
+    for (size_t i = 0; i < n; i++) {
+        widen(r1.data() + 96 * i, 3, out.data() + 576 * i, true);
+        widen(r2.data() + 192 * i, 6, out.data() + 576 * i + 192, true);
+    }
+    return to_java(env, out);
+}
+
+// algebra_msm_FixedBaseMSM.h:26-32, reference implementation algebra_msm_FixedBaseMSM.cu:1500-1558: the input holds
+// batch_size scalars followed by the multiplier (:1520-1522); the result is batch_size x 64 bytes big-endian.
+JNIEXPORT jbyteArray JNICALL Java_algebra_msm_FixedBaseMSM_fieldBatchMSMNativeHelper(
+    JNIEnv* env, jclass, jbyteArray scalarsPlusBase, jint batch_size, jint taskID) {
+    if (batch_size < 0) return fail_msg(env, "fieldBatchMSMNativeHelper: negative batch_size");
+    const size_t n = (size_t)batch_size;
+    if (!long_enough(env, scalarsPlusBase, (n + 1) * 32)) return fail_msg(env, "fieldBatchMSMNativeHelper: input array too short");
+    if (n * 64 > 0x7fffffffu) return fail_msg(env, "fieldBatchMSMNativeHelper: result exceeds the 2 GiB limit of a Java byte[]");
+    ozk_ctx* ctx = context_for_task(taskID);
+    if (!ctx) return fail(env, "fieldBatchMSMNativeHelper");
+    std::vector<uint8_t> res(n * 32);
+    int rc;
+    {
+        Pinned a(env, scalarsPlusBase);
+        if (!a.p) return fail_msg(env, "fieldBatchMSMNativeHelper: could not pin the input array");
+        rc = ozk_fr_scale(ctx, a.bytes(), n, a.bytes() + n * 32, res.data());
+    }
+    if (rc != OZK_OK) return fail(env, "fieldBatchMSMNativeHelper");
+    std::vector<uint8_t> out(n * 64);
+    widen(res.data(), n, out.data(), true);
+    return to_java(env, out);
+}
+
+// North-star variant of batchMSM: direct buffers, 32-byte coordinates, BNType 1 = G1, 2 = G2; out holds n points.
+JNIEXPORT jint JNICALL Java_algebra_msm_FixedBaseMSM_batchMSMDirect(
+    JNIEnv* env, jclass, jint outerc, jint windowSize, jint batch_size, jobject base, jobject scalars, jint BNType, jint taskID, jobject out) {
+    const size_t n = batch_size < 0 ? 0 : (size_t)batch_size;
+    const size_t pt = BNType == 1 ? 96 : 192;
+    const uint8_t* b = base ? (const uint8_t*)env->GetDirectBufferAddress(base) : nullptr;
+    const uint8_t* s = scalars ? (const uint8_t*)env->GetDirectBufferAddress(scalars) : nullptr;
+    uint8_t* o = out ? (uint8_t*)env->GetDirectBufferAddress(out) : nullptr;
+    if (batch_size < 0 || !b || (size_t)env->GetDirectBufferCapacity(base) < pt ||
+        (n && (!s || !o || (size_t)env->GetDirectBufferCapacity(scalars) < n * 32 || (size_t)env->GetDirectBufferCapacity(out) < n * pt))) {
+        fail_msg(env, "batchMSMDirect: buffers must be direct and hold batch_size elements");
+        return -1;
+    }
+    ozk_ctx* ctx = context_for_task(taskID);
+    if (!ctx) { fail(env, "batchMSMDirect"); return -1; }
+    int rc = BNType == 1 ? ozk_fixed_g1(ctx, b, s, n, outerc, windowSize, o) : ozk_fixed_g2(ctx, b, s, n, outerc, windowSize, o);
+    if (rc != OZK_OK) { fail(env, "batchMSMDirect"); return -1; }
+    return 0;
+}
+#endif  // OZK_SHIM_FIXEDMSM
+
+#ifdef OZK_SHIM_FFT
+// algebra_fft_FFTAuxiliary.h:10-16, reference implementation algebra_fft_FFTAuxiliary.cu:219-260.  `input` is a
+// java.util.List<byte[]>; every element is a little-endian array whose length is a multiple of 4 and at most 32
+// (FFTAuxiliary.java:41-51); the result is n x 64 bytes little-endian (:252-255).  Dormant in the reference's Java
+// (the call is commented out, FFTAuxiliary.java:72-97) but part of the library's interface.
+JNIEXPORT jbyteArray JNICALL Java_algebra_fft_FFTAuxiliary_serialRadix2FFTNativeHelper(
+    JNIEnv* env, jclass, jobject input, jbyteArray omega, jint taskID) {
+    if (!input || !omega) return fail_msg(env, "serialRadix2FFTNativeHelper: null argument");
+    jclass list_cls = env->FindClass("java/util/List");
+    if (!list_cls) return nullptr;
+    jmethodID m_size = env->GetMethodID(list_cls, "size", "()I");
+    jmethodID m_get = env->GetMethodID(list_cls, "get", "(I)Ljava/lang/Object;");
+    if (!m_size || !m_get) return nullptr;
+    const jint n = env->CallIntMethod(input, m_size);
+    if (n < 0) return fail_msg(env, "serialRadix2FFTNativeHelper: negative list size");
+    if ((size_t)n * 64 > 0x7fffffffu) return fail_msg(env, "serialRadix2FFTNativeHelper: result exceeds the 2 GiB limit of a Java byte[]");
+    std::vector<uint8_t> data((size_t)n * 32, 0);
+    for (jint i = 0; i < n; i++) {
+        jbyteArray e = (jbyteArray)env->CallObjectMethod(input, m_get, i);
+        if (!e) return fail_msg(env, "serialRadix2FFTNativeHelper: null list element");
+        jsize len = env->GetArrayLength(e);
+        if (len > 32) {
+            // BigInteger.toByteArray may add a sign byte: the padded array is then 36 bytes with zeros above byte 31
+            len = 32;
+        }
+        env->GetByteArrayRegion(e, 0, len, (jbyte*)(data.data() + 32 * (size_t)i));
+        env->DeleteLocalRef(e);
+    }
+    uint8_t w[32] = {0};
+    jsize wl = env->GetArrayLength(omega);
+    env->GetByteArrayRegion(omega, 0, wl > 32 ? 32 : wl, (jbyte*)w);
+    ozk_ctx* ctx = context_for_task(taskID);
+    if (!ctx) return fail(env, "serialRadix2FFTNativeHelper");
+    if (n > 0 && ozk_ntt_fr(ctx, data.data(), (size_t)n, w) != OZK_OK) return fail(env, "serialRadix2FFTNativeHelper");
+    std::vector<uint8_t> out((size_t)n * 64);
+    widen(data.data(), (size_t)n, out.data(), false);
+    return to_java(env, out);
+}
+
+// Bulk variant the reference's own TODOs ask for (algebra_fft_FFTAuxiliary.cu:226,251): one direct ByteBuffer of
+// n x 32 bytes, transformed in place.
+JNIEXPORT jint JNICALL Java_algebra_fft_FFTAuxiliary_serialRadix2FFTDirect(
+    JNIEnv* env, jclass, jobject data, jint n, jbyteArray omega, jint taskID) {
+    uint8_t* d = data ? (uint8_t*)env->GetDirectBufferAddress(data) : nullptr;
+    if (n < 0 || !omega || (n && (!d || (size_t)env->GetDirectBufferCapacity(data) < (size_t)n * 32))) {
+        fail_msg(env, "serialRadix2FFTDirect: data must be a direct buffer of n 32-byte elements");
+        return -1;
+    }
+    uint8_t w[32] = {0};
+    jsize wl = env->GetArrayLength(omega);
+    env->GetByteArrayRegion(omega, 0, wl > 32 ? 32 : wl, (jbyte*)w);
+    ozk_ctx* ctx = context_for_task(taskID);
+    if (!ctx) { fail(env, "serialRadix2FFTDirect"); return -1; }
+    if (n > 0 && ozk_ntt_fr(ctx, d, (size_t)n, w) != OZK_OK) { fail(env, "serialRadix2FFTDirect"); return -1; }
+    return 0;
+}
+#endif  // OZK_SHIM_FFT
+
+}  // extern "C"

@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_kernel(PassArgs a) {
 // ---- elementwise helpers ---------------------------------------------------------------------------------------
 // out[i] = in[i] * scale * coset^i   (scale / coset given in Montgomery form; `has_coset` selects the power term)
 __global__ void __launch_bounds__(256) fr_scale_powers_kernel(const uint4* in, uint4* out, size_t n, Fr scale_canon, Fr coset_canon,
-                                                              int has_scale, int has_coset) {
+                                                              int has_scale, int has_coset, unsigned long long first_index) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     if (i >= n) return;
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(256) fr_scale_powers_kernel(const uint4* in, u
         // f = scale * coset^i, step = coset^stride
         const Fr coset = Fr::to_mont(coset_canon);
         Fr b = coset;
-        size_t e = i;
+        unsigned long long e = first_index + i;
         while (e) {
             if (e & 1) f = Fr::mul(f, b);
             b = Fr::sqr(b);
@@ -337,6 +337,24 @@ __global__ void __launch_bounds__(256) fr_scale_powers_kernel(const uint4* in, u
         v = Fr::mul(v, f);
         store_fr(out + i * 2, v);
         if (has_coset) f = Fr::mul(f, step);
+    }
+}
+
+// ---- small cross-shard DFT (the second step of the multi-GPU transform) ---------------------------------------------------
+// out[k1 * len + j] = sum_{i1 < G} in[i1 * len + j] * omega_G^(i1 k1), G = 2^Q <= 8: one thread per j, all G values in registers.
+template <int Q>
+__global__ void __launch_bounds__(256) fr_dft_small_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, size_t len,
+                                                           const Fr* __restrict__ wtab) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= len) return;
+    Fr x[1 << Q];
+#pragma unroll
+    for (int u = 0; u < (1 << Q); u++) x[u] = load_fr(in + ((size_t)u * len + j) * 2);
+    dif_step<Q, true>(x, wtab, 0, 0, Q);
+#pragma unroll
+    for (int u = 0; u < (1 << Q); u++) {
+        const uint32_t k1 = __brev((uint32_t)u) >> (32 - Q);
+        store_fr(out + ((size_t)k1 * len + j) * 2, x[u]);
     }
 }
 
@@ -502,7 +520,8 @@ static bool fr_bytes_canonical(const uint8_t* b) {
     return false;
 }
 
-static int scale_powers(ozk_ctx* ctx, const void* d_in, void* d_out, size_t n, const uint8_t* scale, const uint8_t* coset) {
+static int scale_powers(ozk_ctx* ctx, const void* d_in, void* d_out, size_t n, const uint8_t* scale, const uint8_t* coset,
+                        unsigned long long first_index = 0) {
     Fr s, g;
     memset(&s, 0, sizeof s);
     memset(&g, 0, sizeof g);
@@ -525,7 +544,7 @@ static int scale_powers(ozk_ctx* ctx, const void* d_in, void* d_out, size_t n, c
     size_t cap = (size_t)ctx->sm_count * 8;
     if (blocks > cap) blocks = cap;
     ctx->launches += 1;
-    fr_scale_powers_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>((const uint4*)d_in, (uint4*)d_out, n, s, g, scale ? 1 : 0, coset ? 1 : 0);
+    fr_scale_powers_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>((const uint4*)d_in, (uint4*)d_out, n, s, g, scale ? 1 : 0, coset ? 1 : 0, first_index);
     OZK_CUDA(cudaGetLastError());
     return OZK_OK;
 }
@@ -579,6 +598,35 @@ int ozk_fr_scale_dev(ozk_ctx* ctx, const void* d_a, void* d_out, size_t n, const
     OZK_ARG(d_a && d_out && b, "ozk_fr_scale_dev: null pointer");
     if (n == 0) return OZK_OK;
     return scale_powers(ctx, d_a, d_out, n, b, nullptr);
+}
+
+int ozk_fr_dft_small_dev(ozk_ctx* ctx, const void* d_in, void* d_out, size_t groups, size_t len, const uint8_t omega_g[32]) {
+    OZK_TRY(ctx_enter(ctx));
+    OZK_ARG(d_in && d_out && omega_g && d_in != d_out, "ozk_fr_dft_small_dev: null or aliased pointers");
+    int q = ilog2_exact(groups);
+    OZK_ARG(q >= 0 && q <= 3, "ozk_fr_dft_small_dev: groups must be 1, 2, 4 or 8");
+    if (len == 0) return OZK_OK;
+    if (q == 0) {
+        OZK_CUDA(cudaMemcpyAsync(d_out, d_in, len * 32, cudaMemcpyDeviceToDevice, ctx->stream));
+        return OZK_OK;
+    }
+    NttPlan* p;
+    OZK_TRY(ntt_get_plan(ctx, q, omega_g, &p));       // validates omega_g and holds omega_g^t, t < groups / 2
+    const unsigned grid = (unsigned)((len + 255) / 256);
+    if (q == 1) fr_dft_small_kernel<1><<<grid, 256, 0, ctx->stream>>>((const uint4*)d_in, (uint4*)d_out, len, p->wsub[0]);
+    else if (q == 2) fr_dft_small_kernel<2><<<grid, 256, 0, ctx->stream>>>((const uint4*)d_in, (uint4*)d_out, len, p->wsub[0]);
+    else fr_dft_small_kernel<3><<<grid, 256, 0, ctx->stream>>>((const uint4*)d_in, (uint4*)d_out, len, p->wsub[0]);
+    ctx->launches += 1;
+    OZK_CUDA(cudaGetLastError());
+    return OZK_OK;
+}
+
+int ozk_fr_scale_powers_dev(ozk_ctx* ctx, const void* d_a, void* d_out, size_t n, const uint8_t* scale, const uint8_t* coset,
+                            uint64_t first_index) {
+    OZK_TRY(ctx_enter(ctx));
+    OZK_ARG(n == 0 || (d_a && d_out), "ozk_fr_scale_powers_dev: null pointer");
+    if (n == 0) return OZK_OK;
+    return scale_powers(ctx, d_a, d_out, n, scale, coset, first_index);
 }
 
 int ozk_fr_scale(ozk_ctx* ctx, const uint8_t* a, size_t n, const uint8_t b[32], uint8_t* out) {

@@ -1,0 +1,125 @@
+"""Multi-GPU forms of the hot path: one process per GPU, torch.distributed for the plumbing.
+
+Replaces the reference's Spark distribution:
+  * VariableBaseMSM.distributedMSM (src/main/java/algebra/msm/VariableBaseMSM.java:772-786: mapPartitions + reduce(add))
+    -> every rank runs the full single-GPU MSM on its contiguous shard; the only exchange is an all_gather of the
+       96/192-byte partial sums, added on every rank.  No data-path collective.
+  * FFTAuxiliary.distributedRadix2FFT (src/main/java/algebra/fft/FFTAuxiliary.java:129-219: two shuffles)
+    -> four-step with n = G * M over G ranks and ONE all-to-all:
+         input  : rank d holds x[d + G * i2], i2 < M                      (cyclic shard)
+         step 1 : local M-point transform over i2 with omega^G             (the single-GPU kernel)
+         twiddle: Y[k2] *= omega^(d * k2)
+         exchange: all_to_all of M/G-element chunks (chunk c = k2 in [c M/G, (c+1) M/G) goes to rank c)
+         step 2 : G-point transform across the received chunks with omega^M
+         output : rank d holds X[k1 * M + d * M/G + t] at [k1][t]           (G chunks of M/G, k1-major)
+       `ntt_gather_natural` turns the distributed output into the natural-order vector for checks.
+
+The local compute is behind a small `ops` object so the index logic and the collectives can be exercised on CPU with
+the gloo backend (tests/test_distributed_cpu.py plugs the oracle in there); `GpuOps` is the product path."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+FR_MODULUS = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+
+
+def _le32(x: int) -> bytes:
+    return x.to_bytes(32, "little")
+
+
+class GpuOps:
+    """Product path: liboctozk kernels on this rank's GPU; tensors are uint8 CUDA tensors of 32-byte elements."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.device = torch.device("cuda", ctx.device)
+
+    def empty_like(self, t):
+        return torch.empty_like(t)
+
+    def ntt(self, x, n, omega):
+        self.ctx.ntt_dev(x, x, n, _le32(omega))
+
+    def scale_powers(self, x, n, coset):
+        self.ctx.fr_scale_powers_dev(x, x, n, None, _le32(coset), 0)
+
+    def dft_small(self, x, out, groups, length, omega_g):
+        self.ctx.fr_dft_small_dev(x, out, groups, length, _le32(omega_g))
+
+    def msm_g1(self, scalars, bases, n):
+        return self.ctx.msm_g1_dev(scalars, bases, n)
+
+    def msm_g2(self, scalars, bases, n):
+        return self.ctx.msm_g2_dev(scalars, bases, n)
+
+    def to_device(self, b: bytes):
+        return torch.frombuffer(bytearray(b), dtype=torch.uint8).to(self.device)
+
+
+def _world(group):
+    return dist.get_world_size(group) if dist.is_initialized() else 1
+
+
+def _rank(group):
+    return dist.get_rank(group) if dist.is_initialized() else 0
+
+
+def msm_distributed(ops, scalars_local, bases_local, n_local: int, g2: bool = False, group=None) -> bytes:
+    """sum over all ranks' shards of scalars[i] * bases[i]; every rank returns the same point (wire format)."""
+    world = _world(group)
+    fn = ops.msm_g2 if g2 else ops.msm_g1
+    part = fn(scalars_local, bases_local, n_local)
+    if world == 1:
+        return part
+    size = 192 if g2 else 96
+    mine = ops.to_device(part)
+    gathered = torch.empty((world * size,), dtype=torch.uint8, device=mine.device)
+    dist.all_gather_into_tensor(gathered, mine, group=group)
+    ones = bytearray(32 * world)
+    for r in range(world):
+        ones[32 * r] = 1
+    return fn(ops.to_device(bytes(ones)), gathered, world)
+
+
+def ntt_distributed(ops, x_local, n: int, omega: int, group=None):
+    """Forward transform of a length-n vector sharded cyclically over the ranks (see the module docstring for layouts).
+    x_local: uint8 tensor of M * 32 bytes, overwritten.  Returns a uint8 tensor of the same size laid out [k1][t]."""
+    world = _world(group)
+    rank = _rank(group)
+    assert n % world == 0 and world in (1, 2, 4, 8)
+    m = n // world
+    assert x_local.numel() == m * 32
+    if world == 1:
+        ops.ntt(x_local, n, omega)
+        return x_local
+    assert m % world == 0
+    ops.ntt(x_local, m, pow(omega, world, FR_MODULUS))                       # step 1
+    ops.scale_powers(x_local, m, pow(omega, rank, FR_MODULUS))               # twiddle omega^(d * k2)
+    recv = ops.empty_like(x_local)
+    dist.all_to_all_single(recv, x_local, group=group)                       # chunk c -> rank c
+    out = ops.empty_like(x_local)
+    ops.dft_small(recv, out, world, m // world, pow(omega, m, FR_MODULUS))   # step 2
+    return out
+
+
+def ntt_scatter_cyclic(x: bytes, world: int, rank: int) -> bytes:
+    """The cyclic shard of a natural-order vector: elements rank, rank + world, ..."""
+    n = len(x) // 32
+    return b"".join(x[32 * i:32 * i + 32] for i in range(rank, n, world))
+
+
+def ntt_gather_natural(shards, n: int) -> bytes:
+    """Natural-order vector from the per-rank outputs of ntt_distributed (shards[d] = bytes of rank d's output)."""
+    world = len(shards)
+    m = n // world
+    c = m // world
+    out = bytearray(n * 32)
+    for d, sh in enumerate(shards):
+        for k1 in range(world):
+            src = sh[(k1 * c) * 32:(k1 * c + c) * 32]
+            dst = (k1 * m + d * c) * 32
+            out[dst:dst + c * 32] = src
+    return bytes(out)

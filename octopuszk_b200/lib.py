@@ -41,6 +41,8 @@ SIGNATURES = {
     "ozk_version": (ctypes.c_char_p, []),
     "ozk_fr_scale": (_int, [_vp, _vp, _sz, _c_u8p, _vp]),
     "ozk_fr_scale_dev": (_int, [_vp, _vp, _vp, _sz, _c_u8p]),
+    "ozk_fr_scale_powers_dev": (_int, [_vp, _vp, _vp, _sz, _c_u8p, _c_u8p, ctypes.c_uint64]),
+    "ozk_fr_dft_small_dev": (_int, [_vp, _vp, _vp, _sz, _sz, _c_u8p]),
     "ozk_ntt_fr": (_int, [_vp, _vp, _sz, _c_u8p]),
     "ozk_ntt_fr_dev": (_int, [_vp, _vp, _vp, _sz, _c_u8p]),
     "ozk_ntt_fr_ex_dev": (_int, [_vp, _vp, _vp, _sz, _c_u8p, _c_u8p, _c_u8p, _c_u8p]),
@@ -155,6 +157,12 @@ class Context:
 
     def fr_scale_dev(self, d_a, d_out, n: int, b: bytes):
         self._check(self.lib.ozk_fr_scale_dev(self._h, _ptr(d_a), _ptr(d_out), n, b))
+
+    def fr_scale_powers_dev(self, d_a, d_out, n: int, scale=None, coset=None, first_index: int = 0):
+        self._check(self.lib.ozk_fr_scale_powers_dev(self._h, _ptr(d_a), _ptr(d_out), n, scale, coset, first_index))
+
+    def fr_dft_small_dev(self, d_in, d_out, groups: int, length: int, omega_g: bytes):
+        self._check(self.lib.ozk_fr_dft_small_dev(self._h, _ptr(d_in), _ptr(d_out), groups, length, omega_g))
 
     # ---- NTT
     def ntt(self, data: bytes, omega: bytes) -> bytes:

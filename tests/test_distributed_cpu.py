@@ -1,0 +1,122 @@
+"""World-size-2 gloo tests (CPU) of the multi-GPU host logic: sharding, the all-gather of MSM partial sums and the
+one-all-to-all four-step transform.  The local compute is the oracle here (tests only) -- what is under test is the
+index arithmetic and the collectives of octopuszk_b200/distributed.py, checked against the serial oracle results the
+reference's DistributedFFTTest / DistributedVariableBaseMSMTest compare with."""
+import os
+import random
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import c_oracle as C
+from oracle import dizk_oracle as O
+from tests import util
+
+
+class OracleOps:
+    """CPU stand-in for GpuOps (same method names), backed by the oracle."""
+
+    def empty_like(self, t):
+        return torch.empty_like(t)
+
+    def to_device(self, b):
+        return torch.frombuffer(bytearray(b), dtype=torch.uint8)
+
+    def ntt(self, x, n, omega):
+        out = C.fft_fr(x.numpy().tobytes(), O.le32(omega))
+        x.copy_(torch.frombuffer(bytearray(out), dtype=torch.uint8))
+
+    def scale_powers(self, x, n, coset):
+        v = [O.from_le(bytes(x[32 * i:32 * i + 32].tolist())) for i in range(n)]
+        O.multiply_by_coset(v, coset)
+        x.copy_(torch.frombuffer(bytearray(O.pack_scalars(v)), dtype=torch.uint8))
+
+    def dft_small(self, x, out, groups, length, omega_g):
+        raw = x.numpy().tobytes()
+        v = [O.from_le(raw[32 * i:32 * i + 32]) for i in range(groups * length)]
+        res = [0] * (groups * length)
+        for j in range(length):
+            col = [v[i1 * length + j] for i1 in range(groups)]
+            for k1 in range(groups):
+                res[k1 * length + j] = sum(col[i1] * pow(omega_g, i1 * k1, O.R) for i1 in range(groups)) % O.R
+        out.copy_(torch.frombuffer(bytearray(O.pack_scalars(res)), dtype=torch.uint8))
+
+    def msm_g1(self, scalars, bases, n):
+        return C.msm_g1(scalars.numpy().tobytes(), bases.numpy().tobytes(), n, 1)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from octopuszk_b200 import distributed as D
+    ops = OracleOps()
+    # ---- NTT: cyclic shards in, [k1][t] chunks out, one all-to-all
+    n = 64
+    rng = random.Random(5)
+    x = [rng.randrange(O.R) for _ in range(n)]
+    omega = O.root_of_unity(n)
+    shard = torch.frombuffer(bytearray(D.ntt_scatter_cyclic(O.pack_scalars(x), world, rank)), dtype=torch.uint8)
+    out = D.ntt_distributed(ops, shard, n, omega)
+    # ---- MSM: contiguous shards, all-gather of partial sums
+    ks, pool = util.known_dlog_points(O.G1, 8, seed=3)
+    total = 40
+    bases = [pool[i % 8] for i in range(total)]
+    scalars = [rng.randrange(O.R) for _ in range(total)]
+    lo, hi = rank * total // world, (rank + 1) * total // world
+    res = D.msm_distributed(ops, torch.frombuffer(bytearray(O.pack_scalars(scalars[lo:hi])), dtype=torch.uint8),
+                            torch.frombuffer(bytearray(O.pack_g1(bases[lo:hi])), dtype=torch.uint8), hi - lo)
+    q.put((rank, out.numpy().tobytes(), res, x, scalars, bases))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_world_size_2_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted([q.get(timeout=240) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    from octopuszk_b200 import distributed as D
+    x = results[0][3]
+    n = len(x)
+    exp = list(x)
+    O.serial_radix2_fft(exp, O.root_of_unity(n))                       # DistributedFFTTest.java:41-67: distributed == serial
+    got = D.ntt_gather_natural([r[1] for r in results], n)
+    assert [O.from_le(got[32 * i:32 * i + 32]) for i in range(n)] == exp
+    scalars, bases = results[0][4], results[0][5]
+    e = O.pippenger_msm(O.G1, scalars, bases)
+    for r in results:                                                  # every rank holds the same global sum
+        assert O.G1.equals(O.unpack_g1(r[2])[0], e)
+
+
+def test_scatter_gather_layouts_single_process():
+    from octopuszk_b200 import distributed as D
+    n, world = 32, 4
+    x = O.pack_scalars(list(range(1, n + 1)))
+    shards = [D.ntt_scatter_cyclic(x, world, r) for r in range(world)]
+    assert O.from_le(shards[1][:32]) == 2 and O.from_le(shards[1][32:64]) == 6
+    # gather is the inverse of "rank d holds X[k1*M + d*M/G + t] at [k1][t]"
+    m, c = n // world, n // world // world
+    outs = []
+    for d in range(world):
+        outs.append(b"".join(x[(k1 * m + d * c + t) * 32:(k1 * m + d * c + t) * 32 + 32] for k1 in range(world) for t in range(c)))
+    assert D.ntt_gather_natural(outs, n) == x

@@ -1,0 +1,120 @@
+"""GPU checks of the multi-GPU building blocks.  On a single GPU the ranks are emulated in one process (the
+all-to-all becomes tensor indexing), which exercises the real kernels of every step; with >= 2 GPUs the real NCCL path
+runs under torch.multiprocessing."""
+import os
+import random
+import socket
+
+import pytest
+import torch
+
+from oracle import dizk_oracle as O
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _emulated_ntt(ctx, x, n, omega, world):
+    from octopuszk_b200 import distributed as D
+    ops = D.GpuOps(ctx)
+    m = n // world
+    c = m // world
+    xb = O.pack_scalars(x)
+    locals_ = []
+    for d in range(world):
+        t = ops.to_device(D.ntt_scatter_cyclic(xb, world, d))
+        ops.ntt(t, m, pow(omega, world, O.R))
+        ops.scale_powers(t, m, pow(omega, d, O.R))
+        locals_.append(t.view(world, c * 32))
+    outs = []
+    for d in range(world):
+        recv = torch.stack([locals_[i1][d] for i1 in range(world)]).contiguous().view(-1)     # what all_to_all delivers
+        out = torch.empty_like(recv)
+        ops.dft_small(recv, out, world, c, pow(omega, m, O.R))
+        ctx.sync()
+        outs.append(out.cpu().numpy().tobytes())
+    return D.ntt_gather_natural(outs, n)
+
+
+@pytest.mark.parametrize("world,log_n", [(2, 8), (4, 10), (8, 12), (8, 16)])
+def test_four_step_emulated_ranks(world, log_n):
+    from octopuszk_b200 import Context
+    ctx = Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    rng = random.Random(log_n)
+    n = 1 << log_n
+    x = [rng.randrange(O.R) for _ in range(n)]
+    omega = O.root_of_unity(n)
+    got = _emulated_ntt(ctx, x, n, omega, world)
+    ref = ctx.ntt(O.pack_scalars(x), O.le32(omega))            # single-GPU transform, itself checked against the oracle
+    assert got == ref
+    if log_n <= 10:
+        exp = list(x)
+        O.serial_radix2_fft(exp, omega)
+        assert [O.from_le(got[32 * i:32 * i + 32]) for i in range(n)] == exp
+    ctx.close()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _nccl_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from octopuszk_b200 import Context
+    from octopuszk_b200 import distributed as D
+    ctx = Context(rank, stream=torch.cuda.current_stream().cuda_stream)
+    ops = D.GpuOps(ctx)
+    n = 1 << 14
+    rng = random.Random(9)
+    x = [rng.randrange(O.R) for _ in range(n)]
+    omega = O.root_of_unity(n)
+    shard = ops.to_device(D.ntt_scatter_cyclic(O.pack_scalars(x), world, rank))
+    out = D.ntt_distributed(ops, shard, n, omega)
+    ks, pool = util.known_dlog_points(O.G1, 16, seed=4)
+    total = 1 << 12
+    raw = util.rand_scalars_bytes(total, seed=4)
+    bases = util.tiled_bases_bytes(O.G1, pool, total)
+    lo, hi = rank * total // world, (rank + 1) * total // world
+    res = D.msm_distributed(ops, torch.from_numpy(raw[lo:hi].copy()).cuda(), torch.from_numpy(bases[lo:hi].copy()).cuda(), hi - lo)
+    torch.cuda.synchronize()
+    q.put((rank, out.cpu().numpy().tobytes(), res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_gpus_nccl():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from octopuszk_b200 import distributed as D
+    world = 2
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    port = _free_port()
+    procs = [mpc.Process(target=_nccl_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted([q.get(timeout=500) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n = 1 << 14
+    rng = random.Random(9)
+    x = [rng.randrange(O.R) for _ in range(n)]
+    from oracle import c_oracle as C
+    exp = C.fft_fr(O.pack_scalars(x), O.le32(O.root_of_unity(n)))
+    assert D.ntt_gather_natural([r[1] for r in results], n) == exp
+    ks, pool = util.known_dlog_points(O.G1, 16, seed=4)
+    raw = util.rand_scalars_bytes(1 << 12, seed=4)
+    e = util.expected_from_dlogs(O.G1, ks, util.column_sums(raw, 16))
+    for r in results:
+        assert O.G1.equals(O.unpack_g1(r[2])[0], e)
