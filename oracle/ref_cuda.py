@@ -1,0 +1,69 @@
+"""ctypes loader for oracle/_ref/ -- the reference's own CUDA sources compiled unmodified for sm_100a by
+oracle/Makefile.ref (test infrastructure; needs a GPU to run).  Byte layouts are the reference's JNI formats
+(SURVEY.md Appendix A): 32-byte LE inputs, 64-byte LE (variable-base, FFT) or 64-byte BE (fixed-base, field) outputs."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_REF = os.path.join(_HERE, "_ref")
+vp, sz, i32 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+
+
+def available(name: str) -> bool:
+    return os.path.exists(os.path.join(_REF, f"libref_{name}.so"))
+
+
+def _load(name):
+    return ctypes.CDLL(os.path.join(_REF, f"libref_{name}.so"))
+
+
+def var_msm(bases: bytes, scalars: bytes, n: int, type_: int) -> bytes:
+    lib = _load("varmsm")
+    lib.ref_var_msm.restype = ctypes.c_long
+    lib.ref_var_msm.argtypes = [vp, sz, vp, sz, i32, i32, vp, sz]
+    out = ctypes.create_string_buffer(384)
+    r = lib.ref_var_msm(bases, len(bases), scalars, len(scalars), n, type_, out, 384)
+    assert r in (192, 384), r
+    return out.raw[:r]
+
+
+def var_double_msm(bases1: bytes, bases2: bytes, scalars: bytes, n: int) -> bytes:
+    lib = _load("varmsm")
+    lib.ref_var_double_msm.restype = ctypes.c_long
+    lib.ref_var_double_msm.argtypes = [vp, sz, vp, sz, vp, sz, i32, vp, sz]
+    out = ctypes.create_string_buffer(576)
+    r = lib.ref_var_double_msm(bases1, len(bases1), bases2, len(bases2), scalars, len(scalars), n, out, 576)
+    assert r == 576, r
+    return out.raw
+
+
+def fixed_batch(outerc, window, out_len, inner_len, n, scalar_size, base: bytes, scalars: bytes, bn_type: int) -> bytes:
+    lib = _load("fixedmsm")
+    lib.ref_fixed_batch.restype = ctypes.c_long
+    lib.ref_fixed_batch.argtypes = [i32, i32, i32, i32, i32, i32, vp, sz, vp, sz, i32, vp, sz]
+    cap = n * (192 if bn_type == 1 else 384)
+    out = ctypes.create_string_buffer(cap)
+    r = lib.ref_fixed_batch(outerc, window, out_len, inner_len, n, scalar_size, base, len(base), scalars, len(scalars), bn_type, out, cap)
+    assert r == cap, r
+    return out.raw
+
+
+def field_batch(scalars_plus_base: bytes, n: int) -> bytes:
+    lib = _load("fixedmsm")
+    lib.ref_field_batch.restype = ctypes.c_long
+    lib.ref_field_batch.argtypes = [vp, sz, i32, vp, sz]
+    out = ctypes.create_string_buffer(n * 64)
+    r = lib.ref_field_batch(scalars_plus_base, len(scalars_plus_base), n, out, n * 64)
+    assert r == n * 64, r
+    return out.raw
+
+
+def fft(data: bytes, omega: bytes) -> bytes:
+    lib = _load("fft")
+    lib.ref_fft.restype = ctypes.c_long
+    lib.ref_fft.argtypes = [vp, i32, i32, vp, i32, vp, sz]
+    n = len(data) // 32
+    out = ctypes.create_string_buffer(n * 64)
+    r = lib.ref_fft(data, n, 32, omega, len(omega), out, n * 64)
+    assert r == n * 64, r
+    return out.raw

@@ -1,0 +1,96 @@
+"""Cross-check against the REFERENCE ITSELF: the reference's own CUDA sources (algebra_msm_VariableBaseMSM.cu,
+algebra_fft_FFTAuxiliary.cu, algebra_msm_FixedBaseMSM.cu), compiled unmodified for sm_100a into oracle/_ref/ by
+oracle/Makefile.ref and driven through their own Java_* entry points, run on the same B200 and must agree with
+liboctozk (as group elements / bit-exact field values) and with the Python oracle.  Skipped when oracle/_ref was not
+built (it needs /root/reference, which only the build container has; the .so files travel with the snapshot)."""
+import random
+
+import pytest
+
+from oracle import dizk_oracle as O
+from oracle import ref_cuda as R
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from octopuszk_b200 import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.skipif(not R.available("varmsm"), reason="oracle/_ref/libref_varmsm.so not built")
+@pytest.mark.parametrize("n", [4, 100, 1023, 4096])
+def test_var_msm_g1_matches_reference_cuda(ctx, n):
+    rng = random.Random(n)
+    ks, pool = util.known_dlog_points(O.G1, 16, seed=n, random_z=True)
+    bases = [pool[rng.randrange(16)] for _ in range(n)]
+    scalars = [rng.randrange(O.R) for _ in range(n)]
+    if n == 4:
+        bases = [O.G1.mul(O.G1.generator, k) for k in (5, 2, 7, 3)]
+        scalars = [3, 11, 2, 8]
+    sb, bb = O.pack_scalars(scalars), O.pack_g1(bases)
+    ref = O.unpack_g1(R.var_msm(bb, sb, n, 1), stride=64)[0]
+    ours = O.unpack_g1(ctx.msm_g1(sb, bb, n))[0]
+    assert O.G1.equals(ours, ref)
+    if n <= 1023:
+        assert O.G1.equals(ref, O.pippenger_msm(O.G1, scalars, bases))      # pins the oracle on the reference's own output
+
+
+@pytest.mark.skipif(not R.available("varmsm"), reason="oracle/_ref/libref_varmsm.so not built")
+def test_var_msm_g2_and_double_match_reference_cuda(ctx):
+    rng = random.Random(5)
+    n = 64
+    k1, p1 = util.known_dlog_points(O.G1, 8, seed=1)
+    k2, p2 = util.known_dlog_points(O.G2, 8, seed=2)
+    b1 = [p1[i % 8] for i in range(n)]
+    b2 = [p2[i % 8] for i in range(n)]
+    scalars = [rng.randrange(O.R) for _ in range(n)]
+    sb = O.pack_scalars(scalars)
+    ref2 = O.unpack_g2(R.var_msm(O.pack_g2(b2), sb, n, 2), stride=64)[0]
+    assert O.G2.equals(O.unpack_g2(ctx.msm_g2(sb, O.pack_g2(b2), n))[0], ref2)
+    assert O.G2.equals(ref2, O.pippenger_msm(O.G2, scalars, b2))
+    d = R.var_double_msm(O.pack_g1(b1), O.pack_g2(b2), sb, n)
+    ours = ctx.msm_g1g2(sb, O.pack_g1(b1), O.pack_g2(b2), n)
+    assert O.G1.equals(O.unpack_g1(ours[:96])[0], O.unpack_g1(d[:192], stride=64)[0])
+    assert O.G2.equals(O.unpack_g2(ours[96:])[0], O.unpack_g2(d[192:], stride=64)[0])
+
+
+@pytest.mark.skipif(not R.available("fft"), reason="oracle/_ref/libref_fft.so not built")
+@pytest.mark.parametrize("log_n", [2, 6, 10])
+def test_fft_matches_reference_cuda(ctx, log_n):
+    rng = random.Random(log_n)
+    n = 1 << log_n
+    x = [rng.randrange(O.R) for _ in range(n)]
+    if log_n == 2:
+        x = [2, 5, 3, 8]
+    omega = O.root_of_unity(n)
+    ref = R.fft(O.pack_scalars(x), O.le32(omega))
+    ref_vals = [int.from_bytes(ref[64 * i:64 * i + 64], "little") for i in range(n)]
+    ours = ctx.ntt(O.pack_scalars(x), O.le32(omega))
+    assert [O.from_le(ours[32 * i:32 * i + 32]) for i in range(n)] == ref_vals
+    exp = list(x)
+    O.serial_radix2_fft(exp, omega)
+    assert ref_vals == exp
+
+
+@pytest.mark.skipif(not R.available("fixedmsm"), reason="oracle/_ref/libref_fixedmsm.so not built")
+def test_fixed_base_and_field_match_reference_cuda(ctx):
+    rng = random.Random(8)
+    n = 64
+    base = O.G1.random(10)
+    ss, w = 253, 5
+    outerc = (ss + w - 1) // w
+    scalars = [0, 1, O.R - 1] + [rng.randrange(O.R) for _ in range(n - 3)]
+    sb = O.pack_scalars(scalars)
+    ref = O.unpack_g1(R.fixed_batch(outerc, w, outerc, 1 << w, n, ss, O.pack_g1([base]), sb, 1), stride=64, big_endian=True)
+    ours = O.unpack_g1(ctx.fixed_g1(O.pack_g1([base]), sb, n, outerc, w))
+    exp = O.fixed_batch_msm(O.G1, ss, w, base, scalars)
+    for a, b, e in zip(ours, ref, exp):
+        assert O.G1.equals(a, b) and O.G1.equals(b, e)
+    b = rng.randrange(O.R)
+    rf = R.field_batch(sb + O.le32(b), n)
+    assert [int.from_bytes(rf[64 * i:64 * i + 64], "big") for i in range(n)] == O.field_batch_msm(scalars, b)
