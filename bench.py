@@ -62,14 +62,15 @@ def _clock_summary(samples):
     return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(samples)}
 
 
-def _make_inputs(n, seed):
+def _make_inputs(n, seed, random_z=True):
     """Synthetic workload: uniform scalars below 2^253 (< r) and bases tiled from 64 points with
-    known discrete logs, Jacobian with random Z (what fixed-base outputs look like on the reference's wire), so the
-    exact answer is known at any n."""
+    known discrete logs, so the exact answer is known at any n.  Bases are supplied affine (Z = 1) for the device-resident
+    number and as random-Z Jacobian triples (what the reference's own fixed-base outputs look like on the wire) for the
+    JNI-facing end-to-end number, as section 8d prescribes."""
     import numpy as np
     from oracle import dizk_oracle as O
     from tests import util
-    ks, pool = util.known_dlog_points(O.G1, 64, seed=seed, random_z=True)
+    ks, pool = util.known_dlog_points(O.G1, 64, seed=seed, random_z=random_z)
     raw = util.rand_scalars_bytes(n, seed=seed)
     bases = np.ascontiguousarray(util.tiled_bases_bytes(O.G1, pool, n))
     expected = util.expected_from_dlogs(O.G1, ks, util.column_sums(raw, 64))
@@ -129,11 +130,15 @@ def run_ours(args):
     ctx = Context(local_rank, stream=torch.cuda.current_stream().cuda_stream)
 
     n = 1 << args.log_n
-    raw, bases, expected = _make_inputs(n, seed=100 + rank)
+    raw, bases, expected = _make_inputs(n, seed=100 + rank, random_z=True)     # wire form for the e2e path
     h_s = torch.from_numpy(raw).pin_memory()
     h_b = torch.from_numpy(bases).pin_memory()
     d_s = h_s.to(dev)
-    d_b = h_b.to(dev)
+    d_bz = h_b.to(dev)
+    from tests import util as _util
+    _ks, _pool = _util.known_dlog_points(O.G1, 64, seed=100 + rank, random_z=True)
+    _pool = [O.G1.to_affine(p) for p in _pool]                                          # the same points with Z = 1
+    d_b = torch.from_numpy(np.ascontiguousarray(_util.tiled_bases_bytes(O.G1, _pool, n))).to(dev)
     ones = torch.zeros((world, 32), dtype=torch.uint8, device=dev)
     ones[:, 0] = 1
 
@@ -201,6 +206,14 @@ def run_ours(args):
         assert torch.equal(mx, mn), "bench: ranks disagree on the global MSM result"
     ms_step = ms_total / args.steps
     value = world * n / (ms_step * 1e-3)
+    # the same device-resident call on random-Z Jacobian bases (adds the batched normalisation)
+    for _ in range(2):
+        ctx.msm_g1_dev(d_s, d_bz, n)
+    ms_rz, out_rz, _ = timed(lambda: ctx.msm_g1_dev(d_s, d_bz, n), max(1, min(args.steps, 3)))
+    ms_rz /= max(1, min(args.steps, 3))
+    if world == 1:
+        assert O.G1.equals(O.unpack_g1(out_rz)[0], expected), "bench: random-Z MSM result differs from the known answer"
+    del d_bz
 
     for _ in range(min(args.warmup, 2)):
         step_e2e()
@@ -274,13 +287,14 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32x8 (256-bit integers mod p, Montgomery form)", "data": "synthetic",
             "config": {"workload": f"BN254 G1 variable-base MSM, 2^{args.log_n} pairs per GPU (BASELINE.json configs[1]); "
-                                   "uniform scalars < 2^253, Jacobian bases with random Z",
+                                   "uniform scalars < 2^253; bases affine (Z = 1) for value, random-Z Jacobian for e2e (SURVEY.md 8d)",
                        "l2": "inputs (2 GiB) and the sorted index (1 GiB) exceed the 126 MB L2; no flush needed",
                        "partition": f"{world} x 2^{args.log_n} pairs, all_gather of 96-byte partial sums"},
             "clocks": _clock_summary(samples),
             "e2e": {"value": e2e_value, "unit": "points/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": n * 128,
                     "d2h_bytes_per_step": 96},
             "gpu_launches": launches,
+            "value_random_z_bases": {"value": world * n / (ms_rz * 1e-3), "unit": "points/s", "ms_per_step": ms_rz},
             "roofline": {"bound": "imad", "kernel": "msm_accumulate", "achieved": achieved, "peak": imad_peak, "unit": "GIMAD/s",
                          "frac": achieved / imad_peak, "traffic": traffic, "kernel_ms": acc,
                          "peak_source": "ozk_imad_peak, measured live (MEASURED_PEAKS.json has no integer-pipe figure)",

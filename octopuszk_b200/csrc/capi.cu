@@ -104,6 +104,8 @@ int ozk_ctx_create(int device, ozk_ctx** out) {
     OZK_CUDA(cudaEventCreate(&c->ev0));
     OZK_CUDA(cudaEventCreate(&c->ev1));
     for (auto& e : c->evs) OZK_CUDA(cudaEventCreate(&e));
+    OZK_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (auto& e : c->copy_ev) OZK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     OZK_CUDA(cudaMallocHost(&c->pinned, 4096));
     *out = c;
     return OZK_OK;
@@ -123,6 +125,8 @@ void ozk_ctx_destroy(ozk_ctx* c) {
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (auto& e : c->evs) if (e) cudaEventDestroy(e);
+    for (auto& e : c->copy_ev) if (e) cudaEventDestroy(e);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }

@@ -76,12 +76,14 @@ struct ozk_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = true;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t copy_stream = nullptr;        // second stream for chunked host->device uploads (host-pointer MSM entry)
+    cudaEvent_t copy_ev[20] = {};
     cudaEvent_t evs[8] = {};                   // phase marks of the last MSM (see ozk_msm_last_stats)
     unsigned long long launches = 0;           // kernels launched through this context
     // scratch
     ozk::DevBuf io_a, io_b, io_c, io_out;     // staging for the host-pointer entry points
     ozk::DevBuf work;                          // NTT ping-pong buffer
-    ozk::DevBuf msm[12];                       // MSM pipeline buffers (see msm.cu)
+    ozk::DevBuf msm[16];                       // MSM pipeline buffers (see msm.cu)
     ozk::DevBuf fb[4];                         // fixed-base buffers
     double msm_stats[16] = {};                  // last MSM: window c, windows, buckets/window, overflow tasks, overflow buckets
     void* pinned = nullptr;                    // small pinned host block for flags / results
@@ -90,6 +92,7 @@ struct ozk_ctx {
 };
 
 namespace ozk {
+static constexpr int kCopyChunks = 8;      // chunks per uploaded base array (<= 2 arrays x 8 + 1 events)
 // activates ctx->device for the calling thread
 int ctx_enter(ozk_ctx* ctx);
 }  // namespace ozk

@@ -40,14 +40,14 @@ __global__ void fixed_powers(const uint4* __restrict__ base_canon, uint4* __rest
 }
 
 // in-place style normalisation of an XYZZ array: out_aff[i] = affine(in[i]) (Montgomery, (0,0) for infinity).
-// One thread per kConvBatch strided elements, one inversion per thread (same scheme as msm_convert_bases).
+// One thread per `batch` strided elements, one inversion per thread (same scheme as msm_convert_bases).
 template <class F>
-__global__ void __launch_bounds__(128) xyzz_to_affine_batch(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n) {
+__global__ void __launch_bounds__(128) xyzz_to_affine_batch(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n, int batch) {
     const size_t nthreads = (size_t)gridDim.x * blockDim.x;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    F prefix[kConvBatch];
+    F prefix[kConvBatchMax];
 #pragma unroll 1
-    for (int k = 0; k < kConvBatch; k++) {
+    for (int k = 0; k < batch; k++) {
         size_t i = tid + (size_t)k * nthreads;
         F d = F::one();
         if (i < n) {
@@ -56,9 +56,9 @@ __global__ void __launch_bounds__(128) xyzz_to_affine_batch(const uint4* __restr
         }
         prefix[k] = k ? F::mul(prefix[k - 1], d) : d;
     }
-    F inv = field_inv_ni(prefix[kConvBatch - 1]);
+    F inv = field_inv_ni(prefix[batch - 1]);
 #pragma unroll 1
-    for (int k = kConvBatch - 1; k >= 0; k--) {
+    for (int k = batch - 1; k >= 0; k--) {
         size_t i = tid + (size_t)k * nthreads;
         XYZZ<F> p = XYZZ<F>::inf();
         F d = F::one();
@@ -80,13 +80,13 @@ __global__ void __launch_bounds__(128) xyzz_to_affine_batch(const uint4* __restr
 
 // same, but writes the canonical Jacobian wire format (x, y, 1) / (0, 1, 0)
 template <class F>
-__global__ void __launch_bounds__(128) xyzz_to_wire_batch(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n) {
+__global__ void __launch_bounds__(128) xyzz_to_wire_batch(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n, int batch) {
     constexpr int U = FieldIO<F>::kU4;
     const size_t nthreads = (size_t)gridDim.x * blockDim.x;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    F prefix[kConvBatch];
+    F prefix[kConvBatchMax];
 #pragma unroll 1
-    for (int k = 0; k < kConvBatch; k++) {
+    for (int k = 0; k < batch; k++) {
         size_t i = tid + (size_t)k * nthreads;
         F d = F::one();
         if (i < n) {
@@ -95,10 +95,10 @@ __global__ void __launch_bounds__(128) xyzz_to_wire_batch(const uint4* __restric
         }
         prefix[k] = k ? F::mul(prefix[k - 1], d) : d;
     }
-    F inv = field_inv_ni(prefix[kConvBatch - 1]);
+    F inv = field_inv_ni(prefix[batch - 1]);
     const F one_c = canon_one((F*)nullptr);
 #pragma unroll 1
-    for (int k = kConvBatch - 1; k >= 0; k--) {
+    for (int k = batch - 1; k >= 0; k--) {
         size_t i = tid + (size_t)k * nthreads;
         XYZZ<F> p = XYZZ<F>::inf();
         F d = F::one();
@@ -219,16 +219,17 @@ extern const FixedLaunch kFixedG2;
         return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                                   \
     }                                                                                                                        \
     static unsigned NAME##_batch_grid(size_t n) {                                                                            \
-        size_t threads = (n + kConvBatch - 1) / kConvBatch;                                                                  \
+        const int batch = conv_batch_for(n);                                                                                 \
+        size_t threads = (n + batch - 1) / batch;                                                                            \
         unsigned g = (unsigned)((threads + 127) / 128);                                                                      \
         return g ? g : 1;                                                                                                    \
     }                                                                                                                        \
     static int NAME##_to_affine(cudaStream_t s, const void* in, void* out, size_t n) {                                       \
-        xyzz_to_affine_batch<F><<<NAME##_batch_grid(n), 128, 0, s>>>((const uint4*)in, (uint4*)out, n);                      \
+        xyzz_to_affine_batch<F><<<NAME##_batch_grid(n), 128, 0, s>>>((const uint4*)in, (uint4*)out, n, conv_batch_for(n));   \
         return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                                   \
     }                                                                                                                        \
     static int NAME##_to_wire(cudaStream_t s, const void* in, void* out, size_t n) {                                         \
-        xyzz_to_wire_batch<F><<<NAME##_batch_grid(n), 128, 0, s>>>((const uint4*)in, (uint4*)out, n);                        \
+        xyzz_to_wire_batch<F><<<NAME##_batch_grid(n), 128, 0, s>>>((const uint4*)in, (uint4*)out, n, conv_batch_for(n));     \
         return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                                   \
     }                                                                                                                        \
     static int NAME##_table(cudaStream_t s, const void* pw, void* tb, uint32_t t, uint32_t nwin) {                           \

@@ -119,6 +119,74 @@ __global__ void __launch_bounds__(1024) msm_scan(const uint32_t* __restrict__ co
     }
 }
 
+// ---- bucket order -----------------------------------------------------------------------------------------------
+// Counting sort of the bucket ids by run length (clamped to kSeg), longest first.  msm_accumulate walks the buckets in
+// this order so that the lanes of a warp do the same number of additions (run lengths are ~Poisson, otherwise every
+// warp waits for its longest lane), and long runs start first.
+static constexpr int kOrderKeys = kSeg + 1;
+
+__global__ void __launch_bounds__(256) msm_order_hist(const uint32_t* __restrict__ count, uint32_t nbt, uint32_t* __restrict__ ohist) {
+    __shared__ uint32_t h[kOrderKeys];
+    for (int k = threadIdx.x; k < kOrderKeys; k += blockDim.x) h[k] = 0;
+    __syncthreads();
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nbt) atomicAdd(&h[kSeg - min(count[b], (uint32_t)kSeg)], 1u);
+    __syncthreads();
+    for (int k = threadIdx.x; k < kOrderKeys; k += blockDim.x)
+        if (h[k]) atomicAdd(&ohist[k], h[k]);
+}
+
+__global__ void __launch_bounds__(1024) msm_order_scan(const uint32_t* __restrict__ ohist, uint32_t* __restrict__ ocursor) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < (uint32_t)kOrderKeys; base += 1024) {
+        const uint32_t k = base + threadIdx.x;
+        const uint32_t v = k < (uint32_t)kOrderKeys ? ohist[k] : 0;
+        uint32_t x = v;
+        const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        for (int off = 1; off < 32; off <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, off);
+            if (lane >= off) x += y;
+        }
+        if (lane == 31) warp_sums[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t ws = warp_sums[lane];
+            for (int off = 1; off < 32; off <<= 1) {
+                uint32_t y = __shfl_up_sync(0xffffffffu, ws, off);
+                if (lane >= off) ws += y;
+            }
+            warp_sums[lane] = ws;
+        }
+        __syncthreads();
+        const uint32_t excl = carry_s + (wid ? warp_sums[wid - 1] : 0) + x - v;
+        if (k < (uint32_t)kOrderKeys) ocursor[k] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = excl + v;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) msm_order_scatter(const uint32_t* __restrict__ count, uint32_t nbt, uint32_t* __restrict__ ocursor,
+                                                         uint32_t* __restrict__ order) {
+    __shared__ uint32_t h[kOrderKeys];
+    for (int k = threadIdx.x; k < kOrderKeys; k += blockDim.x) h[k] = 0;
+    __syncthreads();
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t key = 0, rank = 0;
+    if (b < nbt) {
+        key = kSeg - min(count[b], (uint32_t)kSeg);
+        rank = atomicAdd(&h[key], 1u);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < kOrderKeys; k += blockDim.x)
+        if (h[k]) h[k] = atomicAdd(&ocursor[k], h[k]);      // h[k] becomes this block's base for key k
+    __syncthreads();
+    if (b < nbt) order[h[key] + rank] = b;
+}
+
 // ---- window choice ---------------------------------------------------------------------------------------------
 // Cost model: nwin(c) * (n mixed adds + 2 * 2^(c-1) full adds at ~1.5x the cost of a mixed add), and short runs waste
 // lanes (one thread per bucket), so prefer c with at least ~64 points per bucket when n allows.
@@ -157,7 +225,8 @@ static MsmShape msm_shape(size_t n) {
 }
 
 // buffers in ctx->msm[]
-enum { B_AFF1 = 0, B_AFF2, B_COUNT, B_START, B_CURSOR, B_SORTED, B_BUCKETS, B_OVFTASK, B_OVFBUCKET, B_OVFPART, B_SCRATCH, B_MISC };
+enum { B_AFF1 = 0, B_AFF2, B_COUNT, B_START, B_CURSOR, B_SORTED, B_BUCKETS, B_OVFTASK, B_OVFBUCKET, B_OVFPART, B_SCRATCH, B_MISC, B_ORDER };
+static constexpr int kMiscOhist = 64, kMiscOcursor = 2048, kMiscWords = 4096;   // word offsets inside B_MISC
 
 // sort phase shared by G1 / G2 / paired calls: fills start/count/sorted and the overflow lists
 static int msm_sort(ozk_ctx* ctx, const void* d_scalars, size_t n, const MsmShape& sh) {
@@ -169,9 +238,10 @@ static int msm_sort(ozk_ctx* ctx, const void* d_scalars, size_t n, const MsmShap
     OZK_TRY(ctx->msm[B_SORTED].reserve((size_t)sh.nwin * n * 4, st));
     OZK_TRY(ctx->msm[B_OVFTASK].reserve((size_t)sh.ovf_task_cap * sizeof(OvfTask), st));
     OZK_TRY(ctx->msm[B_OVFBUCKET].reserve((size_t)sh.ovf_bucket_cap * sizeof(OvfBucket), st));
-    OZK_TRY(ctx->msm[B_MISC].reserve(256, st));
-    uint32_t* misc = (uint32_t*)ctx->msm[B_MISC].p;      // [0] flag, [1] ovf task count, [2] ovf bucket count
-    OZK_CUDA(cudaMemsetAsync(misc, 0, 64, st));
+    OZK_TRY(ctx->msm[B_MISC].reserve(kMiscWords * 4, st));
+    OZK_TRY(ctx->msm[B_ORDER].reserve(nbt * 4, st));
+    uint32_t* misc = (uint32_t*)ctx->msm[B_MISC].p;      // [0] flag, [1] ovf task count, [2] ovf bucket count, run-length histogram
+    OZK_CUDA(cudaMemsetAsync(misc, 0, kMiscWords * 4, st));
     OZK_CUDA(cudaMemsetAsync(ctx->msm[B_COUNT].p, 0, nbt * 4, st));
     const unsigned grid = (unsigned)((n + 255) / 256);
     msm_digits<0><<<grid, 256, 0, st>>>((const uint4*)d_scalars, n, sh.c, sh.nwin, (uint32_t*)ctx->msm[B_COUNT].p, nullptr, misc);
@@ -180,13 +250,21 @@ static int msm_sort(ozk_ctx* ctx, const void* d_scalars, size_t n, const MsmShap
                                        (OvfBucket*)ctx->msm[B_OVFBUCKET].p, misc + 2, sh.ovf_task_cap, sh.ovf_bucket_cap);
     msm_digits<1><<<grid, 256, 0, st>>>((const uint4*)d_scalars, n, sh.c, sh.nwin, (uint32_t*)ctx->msm[B_CURSOR].p,
                                         (uint32_t*)ctx->msm[B_SORTED].p, misc);
-    ctx->launches += 3;
+    {
+        const unsigned og = (unsigned)((nbt + 255) / 256);
+        msm_order_hist<<<og, 256, 0, st>>>((const uint32_t*)ctx->msm[B_COUNT].p, (uint32_t)nbt, misc + kMiscOhist);
+        msm_order_scan<<<1, 1024, 0, st>>>(misc + kMiscOhist, misc + kMiscOcursor);
+        msm_order_scatter<<<og, 256, 0, st>>>((const uint32_t*)ctx->msm[B_COUNT].p, (uint32_t)nbt, misc + kMiscOcursor,
+                                              (uint32_t*)ctx->msm[B_ORDER].p);
+    }
+    ctx->launches += 6;
     OZK_CUDA(cudaGetLastError());
     return OZK_OK;
 }
 
 // bucket phase for one group: convert bases, accumulate, reduce, final -> d_out (jac_bytes, canonical)
-static int msm_buckets(ozk_ctx* ctx, const MsmLaunch& L, const void* d_bases, size_t n, const MsmShape& sh, int aff_slot, void* d_out) {
+static int msm_buckets(ozk_ctx* ctx, const MsmLaunch& L, const void* d_bases, size_t n, const MsmShape& sh, int aff_slot, void* d_out,
+                       bool preconverted = false) {
     cudaStream_t st = ctx->stream;
     const size_t nbt = (size_t)sh.nwin * sh.nb;
     uint32_t* misc = (uint32_t*)ctx->msm[B_MISC].p;
@@ -194,10 +272,11 @@ static int msm_buckets(ozk_ctx* ctx, const MsmLaunch& L, const void* d_bases, si
     OZK_TRY(ctx->msm[B_BUCKETS].reserve(nbt * L.xyzz_bytes, st));
     OZK_TRY(ctx->msm[B_OVFPART].reserve((size_t)sh.ovf_task_cap * L.xyzz_bytes, st));
     OZK_CUDA(cudaEventRecord(ctx->evs[1], st));
-    if (L.convert(st, d_bases, ctx->msm[aff_slot].p, n, misc, ctx->sm_count)) { set_error("msm: convert launch failed"); return OZK_ERR_CUDA; }
+    if (!preconverted && L.convert(st, d_bases, ctx->msm[aff_slot].p, n, misc, ctx->sm_count)) { set_error("msm: convert launch failed"); return OZK_ERR_CUDA; }
     OZK_CUDA(cudaEventRecord(ctx->evs[2], st));
     if (L.accumulate(st, ctx->msm[aff_slot].p, (const uint32_t*)ctx->msm[B_SORTED].p, (const uint32_t*)ctx->msm[B_START].p,
-                     (const uint32_t*)ctx->msm[B_COUNT].p, (const OvfTask*)ctx->msm[B_OVFTASK].p, misc + 1, (uint32_t)nbt, sh.log_nb, n,
+                     (const uint32_t*)ctx->msm[B_COUNT].p, (const OvfTask*)ctx->msm[B_OVFTASK].p, misc + 1, (const uint32_t*)ctx->msm[B_ORDER].p,
+                     (uint32_t)nbt, sh.log_nb, n,
                      sh.ovf_task_cap, ctx->msm[B_BUCKETS].p, ctx->msm[B_OVFPART].p)) { set_error("msm: accumulate launch failed"); return OZK_ERR_CUDA; }
     OZK_CUDA(cudaEventRecord(ctx->evs[3], st));
     if (L.merge(st, (const OvfBucket*)ctx->msm[B_OVFBUCKET].p, misc + 2, std::min<uint32_t>(sh.ovf_bucket_cap, (uint32_t)nbt),
@@ -312,20 +391,69 @@ static int msm_run(ozk_ctx* ctx, const void* d_scalars, const void* d_b1, const 
     return msm_finish(ctx, d_res, bytes, out);
 }
 
+// Host-pointer entry: scalars go up first and are sorted while the (3x larger) bases are still crossing PCIe on a second
+// stream in chunks; each chunk is normalised as soon as it lands.  Only the bucket phase needs everything.
 static int msm_run_host(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* b1, const uint8_t* b2, size_t n, uint8_t* out) {
-    {
-        OZK_TRY(ctx->io_a.reserve(n * 32, ctx->stream));
-        OZK_CUDA(cudaMemcpyAsync(ctx->io_a.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-        if (b1) {
-            OZK_TRY(ctx->io_b.reserve(n * 96, ctx->stream));
-            OZK_CUDA(cudaMemcpyAsync(ctx->io_b.p, b1, n * 96, cudaMemcpyHostToDevice, ctx->stream));
-        }
-        if (b2) {
-            OZK_TRY(ctx->io_c.reserve(n * 192, ctx->stream));
-            OZK_CUDA(cudaMemcpyAsync(ctx->io_c.p, b2, n * 192, cudaMemcpyHostToDevice, ctx->stream));
+    OZK_ARG(n > 0 && n < ((size_t)1 << 31), "msm: between 1 and 2^31 - 1 points per call");
+    cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
+    const MsmShape sh = msm_shape(n);
+    ctx->msm_stats[0] = sh.c;
+    ctx->msm_stats[1] = sh.nwin;
+    ctx->msm_stats[2] = sh.nb;
+    OZK_TRY(ctx->io_a.reserve(n * 32, st));
+    if (b1) OZK_TRY(ctx->io_b.reserve(n * 96, st));
+    if (b2) OZK_TRY(ctx->io_c.reserve(n * 192, st));
+    if (b1) OZK_TRY(ctx->msm[B_AFF1].reserve(n * kMsmG1.affine_bytes, st));
+    if (b2) OZK_TRY(ctx->msm[B_AFF2].reserve(n * kMsmG2.affine_bytes, st));
+    OZK_TRY(ctx->msm[B_MISC].reserve(kMiscWords * 4, st));
+    OZK_CUDA(cudaEventRecord(ctx->evs[0], st));
+    OZK_CUDA(cudaMemcpyAsync(ctx->io_a.p, scalars, n * 32, cudaMemcpyHostToDevice, st));
+    // the copy stream must not overtake earlier work on the main stream that still reads the staging buffers
+    OZK_CUDA(cudaEventRecord(ctx->copy_ev[2 * kCopyChunks], st));
+    OZK_CUDA(cudaStreamWaitEvent(cs, ctx->copy_ev[2 * kCopyChunks], 0));
+    const size_t chunk = (n + kCopyChunks - 1) / kCopyChunks;
+    int nev = 0;
+    struct Part { const uint8_t* h; char* d; size_t stride; int first_ev; };
+    Part parts[2] = {{b1, (char*)ctx->io_b.p, 96, 0}, {b2, (char*)ctx->io_c.p, 192, 0}};
+    for (auto& pt : parts) {
+        if (!pt.h) continue;
+        pt.first_ev = nev;
+        for (size_t lo = 0; lo < n; lo += chunk) {
+            const size_t len = std::min(chunk, n - lo);
+            OZK_CUDA(cudaMemcpyAsync(pt.d + lo * pt.stride, pt.h + lo * pt.stride, len * pt.stride, cudaMemcpyHostToDevice, cs));
+            OZK_CUDA(cudaEventRecord(ctx->copy_ev[nev++], cs));
         }
     }
-    return msm_run(ctx, ctx->io_a.p, b1 ? ctx->io_b.p : nullptr, b2 ? ctx->io_c.p : nullptr, n, out);
+    OZK_TRY(msm_sort(ctx, ctx->io_a.p, n, sh));          // clears the flag word before any convert kernel runs
+    uint32_t* misc = (uint32_t*)ctx->msm[B_MISC].p;
+    for (int g = 0; g < 2; g++) {
+        const Part& pt = parts[g];
+        if (!pt.h) continue;
+        const MsmLaunch& L = g == 0 ? kMsmG1 : kMsmG2;
+        char* aff = (char*)ctx->msm[g == 0 ? B_AFF1 : B_AFF2].p;
+        int ev = pt.first_ev;
+        for (size_t lo = 0; lo < n; lo += chunk) {
+            const size_t len = std::min(chunk, n - lo);
+            OZK_CUDA(cudaStreamWaitEvent(st, ctx->copy_ev[ev++], 0));
+            if (L.convert(st, pt.d + lo * pt.stride, aff + lo * L.affine_bytes, len, misc, ctx->sm_count)) {
+                set_error("msm: convert launch failed");
+                return OZK_ERR_CUDA;
+            }
+            ctx->launches += 1;
+        }
+    }
+    OZK_TRY(ctx->io_out.reserve(512, st));
+    char* d_res = (char*)ctx->io_out.p;
+    size_t bytes = 0;
+    if (b1) {
+        OZK_TRY(msm_buckets(ctx, kMsmG1, ctx->io_b.p, n, sh, B_AFF1, d_res, true));
+        bytes += 96;
+    }
+    if (b2) {
+        OZK_TRY(msm_buckets(ctx, kMsmG2, ctx->io_c.p, n, sh, B_AFF2, d_res + bytes, true));
+        bytes += 192;
+    }
+    return msm_finish(ctx, d_res, bytes, out);
 }
 
 }  // namespace ozk

@@ -18,7 +18,12 @@ namespace ozk {
 static constexpr int kSeg = 1024;        // longest run of points a single accumulate task handles
 static constexpr int kWsumS = 32;        // group size of the hierarchical bucket reduction (log2 = 5)
 static constexpr int kWsumLogS = 5;
-static constexpr int kConvBatch = 16;    // points per thread in the batched base normalisation
+static constexpr int kConvBatchMax = 64; // most points per thread in the batched normalisations (one inversion per thread)
+// points per thread: large batches amortise the ~380-product inversion, small inputs keep enough threads in flight
+static inline int conv_batch_for(size_t n) {
+    size_t b = n / 32768;
+    return b < 8 ? 8 : (b > (size_t)kConvBatchMax ? kConvBatchMax : (int)b);
+}
 
 struct OvfTask {
     uint32_t bucket;   // w * nb + b
@@ -125,18 +130,18 @@ __device__ __forceinline__ Fq2 canon_one(Fq2*) { return {canon_one((Fq*)nullptr)
 // in : n x [X|Y|Z] canonical little-endian (the reference wire format, VariableBaseMSM.java:224-227 / :279-285)
 // out: n x [x|y] Montgomery, (0,0) for infinity.  flag |= 1 when a coordinate is not reduced.
 template <class F>
-__global__ void __launch_bounds__(128) msm_convert_bases(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n, uint32_t* flag) {
+__global__ void __launch_bounds__(128) msm_convert_bases(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n, uint32_t* flag, int batch) {
     constexpr int U = FieldIO<F>::kU4;
     const size_t nthreads = (size_t)gridDim.x * blockDim.x;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    F prefix[kConvBatch];
-    F zm[kConvBatch];
+    F prefix[kConvBatchMax];
+    F zm[kConvBatchMax];
     bool all_unit = true;
     bool bad = false;
     const F one_canon = canon_one((F*)nullptr);
     // forward: running product of the Z's (Z == 0 counts as 1)
 #pragma unroll 1
-    for (int k = 0; k < kConvBatch; k++) {
+    for (int k = 0; k < batch; k++) {
         size_t i = tid + (size_t)k * nthreads;
         F z = F::one();
         if (i < n) {
@@ -153,9 +158,9 @@ __global__ void __launch_bounds__(128) msm_convert_bases(const uint4* __restrict
         prefix[k] = k ? F::mul(prefix[k - 1], z) : z;
     }
     F inv = F::one();
-    if (!all_unit) inv = field_inv_ni(prefix[kConvBatch - 1]);
+    if (!all_unit) inv = field_inv_ni(prefix[batch - 1]);
 #pragma unroll 1
-    for (int k = kConvBatch - 1; k >= 0; k--) {
+    for (int k = batch - 1; k >= 0; k--) {
         size_t i = tid + (size_t)k * nthreads;
         F zi = F::one();
         if (!all_unit) {
@@ -191,12 +196,14 @@ template <class F>
 __global__ void __launch_bounds__(128) msm_accumulate(const uint4* __restrict__ bases, const uint32_t* __restrict__ sorted,
                                                       const uint32_t* __restrict__ start, const uint32_t* __restrict__ count,
                                                       const OvfTask* __restrict__ ovf_tasks, const uint32_t* __restrict__ ovf_count,
+                                                      const uint32_t* __restrict__ order,
                                                       uint32_t nbuckets_total, uint32_t log_nb, size_t n,
                                                       uint4* __restrict__ buckets, uint4* __restrict__ ovf_partial) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t bucket, seg;
     if (t < nbuckets_total) {
-        bucket = t;
+        // buckets are visited in order of decreasing run length, so the 32 lanes of a warp have (nearly) equal work
+        bucket = order[t];
         seg = 0;
     } else {
         const uint32_t k = t - nbuckets_total;
@@ -351,7 +358,7 @@ __global__ void msm_final(FinalArgs a, uint4* __restrict__ window_vals, uint4* _
 struct MsmLaunch {
     int (*convert)(cudaStream_t, const void* in, void* out, size_t n, uint32_t* flag, int sm_count);
     int (*accumulate)(cudaStream_t, const void* bases, const uint32_t* sorted, const uint32_t* start, const uint32_t* count,
-                      const OvfTask* tasks, const uint32_t* ovf_count, uint32_t nbuckets_total, uint32_t log_nb, size_t n,
+                      const OvfTask* tasks, const uint32_t* ovf_count, const uint32_t* order, uint32_t nbuckets_total, uint32_t log_nb, size_t n,
                       uint32_t ovf_cap, void* buckets, void* ovf_partial);
     int (*merge)(cudaStream_t, const OvfBucket* ob, const uint32_t* ob_count, uint32_t ob_cap, const void* ovf_partial, void* buckets);
     int (*wsum)(cudaStream_t, const void* in, uint32_t m_in, uint32_t nwin, void* run_out, void* acc_out);
@@ -367,19 +374,20 @@ extern const MsmLaunch kMsmG2;
 
 #define OZK_DEFINE_MSM_LAUNCH(F, NAME)                                                                                         \
     static int NAME##_convert(cudaStream_t s, const void* in, void* out, size_t n, uint32_t* flag, int sm_count) {             \
-        size_t threads_needed = (n + kConvBatch - 1) / kConvBatch;                                                             \
+        const int batch = conv_batch_for(n);                                                                                   \
+        size_t threads_needed = (n + batch - 1) / batch;                                                                       \
         unsigned grid = (unsigned)((threads_needed + 127) / 128);                                                              \
         if (grid == 0) grid = 1;                                                                                               \
         (void)sm_count;                                                                                                        \
-        msm_convert_bases<F><<<grid, 128, 0, s>>>((const uint4*)in, (uint4*)out, n, flag);                                     \
+        msm_convert_bases<F><<<grid, 128, 0, s>>>((const uint4*)in, (uint4*)out, n, flag, batch);                              \
         return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                                     \
     }                                                                                                                          \
     static int NAME##_accumulate(cudaStream_t s, const void* bases, const uint32_t* sorted, const uint32_t* start,             \
-                                 const uint32_t* count, const OvfTask* tasks, const uint32_t* ovf_count, uint32_t nbt,         \
-                                 uint32_t log_nb, size_t n, uint32_t ovf_cap, void* buckets, void* ovf_partial) {              \
+                                 const uint32_t* count, const OvfTask* tasks, const uint32_t* ovf_count, const uint32_t* order, \
+                                 uint32_t nbt, uint32_t log_nb, size_t n, uint32_t ovf_cap, void* buckets, void* ovf_partial) { \
         size_t total = (size_t)nbt + ovf_cap;                                                                                  \
         unsigned grid = (unsigned)((total + 127) / 128);                                                                       \
-        msm_accumulate<F><<<grid, 128, 0, s>>>((const uint4*)bases, sorted, start, count, tasks, ovf_count, nbt, log_nb, n,    \
+        msm_accumulate<F><<<grid, 128, 0, s>>>((const uint4*)bases, sorted, start, count, tasks, ovf_count, order, nbt, log_nb, n, \
                                                (uint4*)buckets, (uint4*)ovf_partial);                                          \
         return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                                     \
     }                                                                                                                          \

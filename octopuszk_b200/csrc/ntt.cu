@@ -37,6 +37,7 @@ struct NttPlan {
     Fr* wsub[kMaxPasses] = {};    // per pass: omega_{n_j}^t, t < n_j/2 (Montgomery form)
     Fr* tlo = nullptr;            // omega_n^e, e < 2^H
     Fr* thi = nullptr;            // omega_n^(e 2^H), e < 2^(log_n - H)
+    Fr* tdir[kMaxPasses] = {};    // per pass: direct inter-pass twiddles omega_n^(outer * e), e < n_j * inner, when that range is small
     void* block = nullptr;
 };
 
@@ -92,6 +93,7 @@ struct PassArgs {
     const Fr* wsub;
     const Fr* tlo;
     const Fr* thi;
+    const Fr* tdir;        // direct table of this pass's inter-pass twiddles, or null
     uint32_t H;
     uint32_t log_n;
     uint32_t log_inner;    // non-last passes: stride of the transform dimension
@@ -294,10 +296,15 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_kernel(PassArgs a) {
         Fr v = lds_fr(lo, hi, Layout<LAST>::slot(pos, c, LOGT, log_c));
         if (!LAST) {
             // inter-pass twiddle omega_n^(outer * column * k)
-            const uint32_t e = (((col0 + c) * k) << a.log_outer);
-            if (e != 0) {
-                Fr w = Fr::mul(a.tlo[e & ((1u << a.H) - 1)], a.thi[e >> a.H]);
-                v = Fr::mul(v, w);
+            const uint32_t ek = (col0 + c) * k;
+            if (ek != 0) {
+                if (a.tdir) {
+                    v = Fr::mul(v, a.tdir[ek]);
+                } else {
+                    const uint32_t e = ek << a.log_outer;
+                    Fr w = Fr::mul(a.tlo[e & ((1u << a.H) - 1)], a.thi[e >> a.H]);
+                    v = Fr::mul(v, w);
+                }
             }
             store_fr(a.out + (out_base + ((size_t)k << a.log_inner) + c) * 2, v);
         } else {
@@ -411,6 +418,21 @@ static int ntt_get_plan(ozk_ctx* ctx, int log_n, const uint8_t omega[32], NttPla
     count += (size_t)1 << p->H;
     size_t off_hi = count;
     count += (size_t)1 << (log_n - p->H);
+    // direct tables: pass j (not the last) needs exponents (column * k) < n_j * inner_j = 2^(log_n - log_outer_j)
+    size_t off_dir[kMaxPasses] = {};
+    int dir_log[kMaxPasses] = {};
+    {
+        int log_outer = 0;
+        for (int j = 0; j + 1 < p->npass; j++) {
+            const int range_log = log_n - log_outer;
+            if (range_log <= 20) {
+                off_dir[j] = count;
+                dir_log[j] = range_log;
+                count += (size_t)1 << range_log;
+            }
+            log_outer += p->logt[j];
+        }
+    }
     OZK_CUDA(cudaMalloc(&p->block, count * sizeof(Fr)));
     Fr* base = (Fr*)p->block;
     for (int j = 0; j < p->npass; j++) {
@@ -425,6 +447,17 @@ static int ntt_get_plan(ozk_ctx* ctx, int log_n, const uint8_t omega[32], NttPla
         ntt_gen_table<<<(cnt + 127) / 128, 128, 0, ctx->stream>>>(p->tlo, cnt, 1u, om);
         cnt = 1u << (log_n - p->H);
         ntt_gen_table<<<(cnt + 127) / 128, 128, 0, ctx->stream>>>(p->thi, cnt, 1u << p->H, om);
+    }
+    {
+        int log_outer = 0;
+        for (int j = 0; j + 1 < p->npass; j++) {
+            if (dir_log[j]) {
+                p->tdir[j] = base + off_dir[j];
+                uint32_t cnt = 1u << dir_log[j];
+                ntt_gen_table<<<(cnt + 127) / 128, 128, 0, ctx->stream>>>(p->tdir[j], cnt, 1u << log_outer, om);
+            }
+            log_outer += p->logt[j];
+        }
     }
     OZK_CUDA(cudaGetLastError());
     ctx->ntt_plans[key] = p;
@@ -475,6 +508,7 @@ static int ntt_run(ozk_ctx* ctx, const void* d_in, void* d_out, int log_n, const
         a.wsub = p->wsub[j];
         a.tlo = p->tlo;
         a.thi = p->thi;
+        a.tdir = last ? nullptr : p->tdir[j];
         a.H = p->H;
         a.log_n = log_n;
         a.log_inner = log_inner;

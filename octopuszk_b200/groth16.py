@@ -1,0 +1,250 @@
+"""Host driver restating the reference's serial Groth16 setup and prover on top of the GPU operator mirror
+(SURVEY.md section 8f-1): the callers either side of the hot path, so that a whole proof can be produced with every MSM
+and every FFT on the GPU and compared point for point with the reference's result.
+
+Mirrors (reference paths under src/main/java/):
+  SerialSetup.generate     zk_proof_systems/zkSNARK/SerialSetup.java:32-192   (pairing value alphaG1betaG2 omitted)
+  SerialProver.prove       zk_proof_systems/zkSNARK/SerialProver.java:26-119
+  R1CStoQAPRelation        reductions/r1cs_to_qap/R1CStoQAP.java:38-97       (host-side field loops, as in the Java)
+  R1CStoQAPWitness         reductions/r1cs_to_qap/R1CStoQAP.java:126-238     (7 transforms on the GPU, device resident)
+  R1CSConstruction.serialConstruct  profiler/generation/R1CSConstruction.java:31-110 (synthetic circuit)
+Every random() is Fp.random(seed 10) as in the reference's Configuration (configuration/Configuration.java:52).
+
+As in the Java, the O(n) field loops (linear-combination evaluation, Lagrange coefficients) run on the host; all group
+arithmetic and all transforms go through liboctozk.  Single scalar multiplications and additions of the Java
+(AbstractGroup.mul / add, SerialProver.java:67,106-114) are issued as tiny MSMs."""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import torch
+
+from .algebra import FR_MODULUS as R
+from .algebra import FR_MULTIPLICATIVE_GENERATOR, FR_ROOT, FixedBaseMSM, SerialFFT, VariableBaseMSM, _le32
+from .lib import Context
+
+G1_ONE = (1, 2, 1)                      # BN254aG1Parameters.java:24
+G2_ONE = ((10857046999023057135944570762232829481370756359578518086990519993285655852781,
+           11559732032986387107991004021392285783925812861821192530917403151452391805634),
+          (8495653923123431417604973247489272438418190587263600148770280649306958101930,
+           4082367875863433681332203403145435568316851327593401208105741076214120093531),
+          (1, 0))                        # BN254aG2Parameters.java:25-32
+
+
+def java_random_next_long(seed: int) -> int:
+    """new java.util.Random(seed).nextLong()."""
+    mult, mask = 0x5DEECE66D, (1 << 48) - 1
+    s = (seed ^ mult) & mask
+    out = []
+    for _ in range(2):
+        s = (s * mult + 0xB) & mask
+        v = s >> 16
+        out.append(v - (1 << 32) if v >= 1 << 31 else v)
+    v = ((out[0] << 32) + out[1]) & ((1 << 64) - 1)
+    return v - (1 << 64) if v >= 1 << 63 else v
+
+
+def fr_random(seed: int = 10) -> int:
+    """Fp.random(seed) (algebra/fields/Fp.java:72-80)."""
+    return java_random_next_long(seed) % R
+
+
+def bit_size(p) -> int:
+    """BNG1.bitSize / BNG2.bitSize (BNG1.java:174-176): the largest coordinate bit length."""
+    flat = [c for f in p for c in (f if isinstance(f, (tuple, list)) else (f,))]
+    return max(v.bit_length() for v in flat)
+
+
+class Groth16:
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        self.msm = VariableBaseMSM(ctx)
+        self.fixed = FixedBaseMSM(ctx)
+
+    # ---- small group helpers (AbstractGroup.mul / add on the GPU)
+    def mul(self, p, s: int):
+        return self.msm.serialMSM([s % R], [p])
+
+    def add(self, *pts):
+        return self.msm.serialMSM([1] * len(pts), list(pts))
+
+    def random_g1(self, seed: int = 10):
+        """BNG1.random (BNG1.java:125-127) = one().mul(Fr.random(seed)).  NOTE: the Jacobian representative differs from
+        the Java's double-and-add result, so bitSize() must not be taken from it (see scalar sizes below)."""
+        return self.mul(G1_ONE, fr_random(seed))
+
+    def random_g2(self, seed: int = 10):
+        return self.mul(G2_ONE, fr_random(seed))
+
+    # ---- synthetic circuit
+    @staticmethod
+    def serial_construct(num_constraints: int, num_inputs: int):
+        num_auxiliary = 3 + num_constraints - num_inputs
+        num_variables = num_inputs + num_auxiliary
+        a = fr_random()
+        b = fr_random()
+        full = [1, a, b]
+        cons = []
+        for i in range(num_constraints - 1):
+            if i % 2 != 0:
+                A, B, C = [(i + 1, 1)], [(i + 2, 1)], [(i + 3, 1)]
+                tmp = a * b % R
+            else:
+                A, B, C = [(i + 1, 1), (i + 2, 1)], [(0, 1)], [(i + 3, 1)]
+                tmp = (a + b) % R
+            a, b = b, tmp
+            full.append(tmp)
+            cons.append((A, B, C))
+        lc = [(i, 1) for i in range(1, num_variables - 1)]
+        res = sum(full[1:num_variables - 1]) % R
+        full.append(res * res % R)
+        cons.append((lc, list(lc), [(num_variables - 1, 1)]))
+        return cons, num_inputs, num_auxiliary, full[:num_inputs], full[num_inputs:]
+
+    # ---- R1CS -> QAP
+    @staticmethod
+    def _evaluate(lc, assignment) -> int:
+        acc = 0
+        for idx, val in lc:
+            acc += val * assignment[idx]
+        return acc % R
+
+    @staticmethod
+    def _lagrange(t: int, m: int) -> List[int]:
+        """FFTAuxiliary.serialRadix2LagrangeCoefficients (algebra/fft/FFTAuxiliary.java:249-302)."""
+        if m == 1:
+            return [1]
+        omega = pow(FR_ROOT, R // m, R)
+        out = [0] * m
+        if pow(t, m, R) == 1:
+            w = 1
+            for i in range(m):
+                if w == t:
+                    out[i] = 1
+                    return out
+                w = w * omega % R
+        Z = (pow(t, m, R) - 1) % R
+        l = Z * pow(m, -1, R) % R
+        r = 1
+        for i in range(m):
+            out[i] = l * pow((t - r) % R, -1, R) % R
+            l = l * omega % R
+            r = r * omega % R
+        return out
+
+    def r1cs_to_qap_relation(self, cons, num_inputs, num_variables, t):
+        num_constraints = len(cons)
+        dom = SerialFFT(self.ctx, num_constraints + num_inputs)
+        At, Bt, Ct = [0] * num_variables, [0] * num_variables, [0] * num_variables
+        lag = self._lagrange(t, dom.domainSize)
+        for i in range(num_inputs):
+            At[i] = lag[num_constraints + i]
+        for i, (A, B, C) in enumerate(cons):
+            li = lag[i]
+            for idx, val in A:
+                At[idx] = (At[idx] + li * val) % R
+            for idx, val in B:
+                Bt[idx] = (Bt[idx] + li * val) % R
+            for idx, val in C:
+                Ct[idx] = (Ct[idx] + li * val) % R
+        Ht, ti = [], 1
+        for _ in range(dom.domainSize + 1):
+            Ht.append(ti)
+            ti = ti * t % R
+        return {"At": At, "Bt": Bt, "Ct": Ct, "Ht": Ht, "Zt": dom.computeZ(t), "degree": dom.domainSize}
+
+    def r1cs_to_qap_witness(self, cons, num_inputs, primary, auxiliary) -> List[int]:
+        """R1CStoQAPWitness with the seven transforms on the GPU; A, B, C and H never leave the device between them."""
+        ctx = self.ctx
+        num_constraints = len(cons)
+        g = FR_MULTIPLICATIVE_GENERATOR
+        dom = SerialFFT(ctx, num_constraints + num_inputs)
+        n = dom.domainSize
+        full = list(primary) + list(auxiliary)
+        A, B, C = [0] * n, [0] * n, [0] * n
+        for i in range(num_inputs):
+            A[i + num_constraints] = full[i]
+        for i, (a, b, c) in enumerate(cons):
+            A[i] = (self._evaluate(a, full) + A[i]) % R
+            B[i] = self._evaluate(b, full)
+            C[i] = self._evaluate(c, full)
+        dev = torch.device("cuda", ctx.device)
+
+        def up(v):
+            return torch.frombuffer(bytearray(b"".join(_le32(x) for x in v)), dtype=torch.uint8).to(dev)
+
+        w, winv = _le32(dom.omega), _le32(pow(dom.omega, -1, R))
+        ninv = _le32(pow(n, -1, R))
+        dA, dB, dC = up(A), up(B), up(C)
+        for d in (dA, dB, dC):
+            ctx.ntt_ex_dev(d, d, n, winv, None, ninv, None)                 # radix2InverseFFT
+            ctx.ntt_ex_dev(d, d, n, w, _le32(g), None, None)                # radix2CosetFFT
+        ctx.sync()
+        # pointwise (A*B - C) on the host, as the Java loops do (R1CStoQAP.java:180-214)
+        hA, hB, hC = (d.cpu().numpy().tobytes() for d in (dA, dB, dC))
+        H = [(int.from_bytes(hA[32 * i:32 * i + 32], "little") * int.from_bytes(hB[32 * i:32 * i + 32], "little")
+              - int.from_bytes(hC[32 * i:32 * i + 32], "little")) % R for i in range(n)]
+        dH = up(H)
+        inv_z = pow(dom.computeZ(g), -1, R)                                 # divideByZOnCoset folded into the post-scale
+        scale = pow(n, -1, R) * inv_z % R
+        ctx.ntt_ex_dev(dH, dH, n, winv, None, _le32(scale), _le32(pow(g, -1, R)))   # (divide by Z) + radix2CosetInverseFFT
+        ctx.sync()
+        hb = dH.cpu().numpy().tobytes()
+        H = [int.from_bytes(hb[32 * i:32 * i + 32], "little") for i in range(n)]
+        H.append(0)
+        return H
+
+    # ---- setup
+    def setup(self, cons, num_inputs, num_variables, scalar_size_g1: int = 253, scalar_size_g2: int = 254):
+        """SerialSetup.generate.  scalarSize is generator.bitSize() of the *Java* representative (253 / 254 for the seed-10
+        generators); it only matters when outerc * window < 254."""
+        t = alpha = beta = gamma = delta = fr_random()
+        inv_gamma, inv_delta = pow(gamma, -1, R), pow(delta, -1, R)
+        qap = self.r1cs_to_qap_relation(cons, num_inputs, num_variables, t)
+        abc = [(beta * qap["At"][i] + alpha * qap["Bt"][i] + qap["Ct"][i]) % R for i in range(num_variables)]
+        gammaABC = [abc[i] * inv_gamma % R for i in range(num_inputs)]
+        deltaABC = [abc[i] * inv_delta % R for i in range(num_inputs, num_variables)]
+        non_zero_at = sum(1 for v in qap["At"] if v)
+        non_zero_bt = sum(1 for v in qap["Bt"] if v)
+        g1, g2 = self.random_g1(), self.random_g2()
+        w1 = FixedBaseMSM.getWindowSize(non_zero_at + non_zero_bt + num_variables, g1)
+        w2 = FixedBaseMSM.getWindowSize(non_zero_bt, g2)
+        fb = self.fixed
+        inverse_delta_zt = qap["Zt"] * inv_delta % R
+        Ht = [h * inverse_delta_zt % R for h in qap["Ht"]]
+        pk = {
+            "alphaG1": self.mul(g1, alpha), "betaG1": self.mul(g1, beta), "betaG2": self.mul(g2, beta),
+            "deltaG1": self.mul(g1, delta), "deltaG2": self.mul(g2, delta),
+            "deltaABCG1": fb.batchMSM(scalar_size_g1, w1, g1, deltaABC),
+            "queryA": fb.batchMSM(scalar_size_g1, w1, g1, qap["At"]),
+            "queryB": fb.doubleBatchMSM(scalar_size_g1, w1, scalar_size_g2, w2, g1, g2, qap["Bt"]),
+            "queryH": fb.batchMSM(scalar_size_g1, w1, g1, Ht),
+        }
+        vk = {"gammaG2": self.mul(g2, gamma), "deltaG2": pk["deltaG2"], "gammaABCG1": fb.batchMSM(scalar_size_g1, w1, g1, gammaABC)}
+        return pk, vk, {"g1": g1, "g2": g2, "windowSizeG1": w1, "windowSizeG2": w2}
+
+    # ---- prover
+    def prove(self, pk, cons, num_inputs, primary: Sequence[int], auxiliary: Sequence[int]):
+        """SerialProver.prove: returns ((A, B, C), coefficientsH)."""
+        msm = self.msm
+        H = self.r1cs_to_qap_witness(cons, num_inputs, primary, auxiliary)
+        r = s = fr_random()
+        num_variables = len(primary) + len(auxiliary)
+        rs_delta = self.mul(pk["deltaG1"], r * s % R)
+        qa, qb = pk["queryA"], pk["queryB"]
+        ev_at = self.add(msm.serialMSM(primary, qa[:num_inputs]), msm.serialMSM(auxiliary, qa[num_inputs:num_variables]))
+        bp1, bp2 = msm.doubleMSM(primary, qb[:num_inputs])
+        bw1, bw2 = msm.doubleMSM(auxiliary, qb[num_inputs:num_variables])
+        ev_b1, ev_b2 = self.add(bp1, bw1), self.add(bp2, bw2)
+        ev_h = msm.serialMSM(H, pk["queryH"])
+        num_witness = num_variables - num_inputs
+        ev_abc = self.add(msm.serialMSM(auxiliary[:num_witness], pk["deltaABCG1"][:num_witness]), ev_h)
+        A = self.add(pk["alphaG1"], ev_at, self.mul(pk["deltaG1"], r))
+        B1 = self.add(pk["betaG1"], ev_b1, self.mul(pk["deltaG1"], s))
+        B2 = self.add(pk["betaG2"], ev_b2, self.mul(pk["deltaG2"], s))
+        neg_rs_delta = (rs_delta[0], (-rs_delta[1]) % FQ, rs_delta[2])
+        C = self.add(ev_abc, self.mul(A, s), self.mul(B1, r), neg_rs_delta)
+        return (A, B2, C), H
+
+
+FQ = 21888242871839275222246405745257275088696311157297823662689037894645226208583

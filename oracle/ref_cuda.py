@@ -67,3 +67,35 @@ def fft(data: bytes, omega: bytes) -> bytes:
     r = lib.ref_fft(data, n, 32, omega, len(omega), out, n * 64)
     assert r == n * 64, r
     return out.raw
+
+
+# ---- isolation -------------------------------------------------------------------------------------------------------
+# The reference's code leaks device memory, synchronises the whole device and exit(-1)s on CUDA errors
+# (algebra_msm_VariableBaseMSM.cu:1417-1422), so tests call it in a child process with a time limit: a crash or a hang of
+# the reference can then neither take the test process down nor stall the suite.
+def _child(name, args, q):
+    try:
+        q.put(("ok", globals()[name](*args)))
+    except BaseException as e:      # noqa: BLE001
+        q.put(("err", repr(e)))
+
+
+def isolated(name: str, *args, timeout: float = 180.0):
+    """Run ref_cuda.<name>(*args) in a spawned child; returns its result, or raises TimeoutError / RuntimeError."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    p = ctx.Process(target=_child, args=(name, args, q), daemon=True)
+    p.start()
+    try:
+        status, val = q.get(timeout=timeout)
+    except Exception:
+        p.kill()
+        p.join(10)
+        raise TimeoutError(f"reference CUDA call {name} did not answer within {timeout} s")
+    p.join(30)
+    if p.is_alive():
+        p.kill()
+    if status != "ok":
+        raise RuntimeError(f"reference CUDA call {name} failed: {val}")
+    return val

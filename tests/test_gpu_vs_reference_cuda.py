@@ -14,6 +14,14 @@ from tests import util
 pytestmark = pytest.mark.gpu
 
 
+def _ref(name, *args):
+    """The reference's CUDA runs in a child process with a time limit (it leaks, device-synchronises and exit()s)."""
+    try:
+        return R.isolated(name, *args, timeout=240.0)
+    except TimeoutError as e:
+        pytest.skip(str(e))
+
+
 @pytest.fixture(scope="module")
 def ctx():
     from octopuszk_b200 import Context
@@ -33,7 +41,7 @@ def test_var_msm_g1_matches_reference_cuda(ctx, n):
         bases = [O.G1.mul(O.G1.generator, k) for k in (5, 2, 7, 3)]
         scalars = [3, 11, 2, 8]
     sb, bb = O.pack_scalars(scalars), O.pack_g1(bases)
-    ref = O.unpack_g1(R.var_msm(bb, sb, n, 1), stride=64)[0]
+    ref = O.unpack_g1(_ref('var_msm', bb, sb, n, 1), stride=64)[0]
     ours = O.unpack_g1(ctx.msm_g1(sb, bb, n))[0]
     assert O.G1.equals(ours, ref)
     if n <= 1023:
@@ -50,10 +58,10 @@ def test_var_msm_g2_and_double_match_reference_cuda(ctx):
     b2 = [p2[i % 8] for i in range(n)]
     scalars = [rng.randrange(O.R) for _ in range(n)]
     sb = O.pack_scalars(scalars)
-    ref2 = O.unpack_g2(R.var_msm(O.pack_g2(b2), sb, n, 2), stride=64)[0]
+    ref2 = O.unpack_g2(_ref('var_msm', O.pack_g2(b2), sb, n, 2), stride=64)[0]
     assert O.G2.equals(O.unpack_g2(ctx.msm_g2(sb, O.pack_g2(b2), n))[0], ref2)
     assert O.G2.equals(ref2, O.pippenger_msm(O.G2, scalars, b2))
-    d = R.var_double_msm(O.pack_g1(b1), O.pack_g2(b2), sb, n)
+    d = _ref('var_double_msm', O.pack_g1(b1), O.pack_g2(b2), sb, n)
     ours = ctx.msm_g1g2(sb, O.pack_g1(b1), O.pack_g2(b2), n)
     assert O.G1.equals(O.unpack_g1(ours[:96])[0], O.unpack_g1(d[:192], stride=64)[0])
     assert O.G2.equals(O.unpack_g2(ours[96:])[0], O.unpack_g2(d[192:], stride=64)[0])
@@ -61,20 +69,25 @@ def test_var_msm_g2_and_double_match_reference_cuda(ctx):
 
 @pytest.mark.skipif(not R.available("fft"), reason="oracle/_ref/libref_fft.so not built")
 @pytest.mark.parametrize("log_n", [2, 6, 10])
-def test_fft_matches_reference_cuda(ctx, log_n):
+def test_fft_against_reference_cuda(ctx, log_n):
+    """The reference's GPU FFT is dormant (its only Java call site is commented out, FFTAuxiliary.java:72-97) and its
+    kernel builds the twiddle exponents in `Scalar` locals of which only limb 0 is written
+    (algebra_fft_FFTAuxiliary.cu:117-119,129-131: limbs 1..15 are uninitialised stack), so its output is undefined.
+    Ours must equal the oracle (= the active Java loop); agreement of the reference kernel is recorded, not required."""
     rng = random.Random(log_n)
     n = 1 << log_n
     x = [rng.randrange(O.R) for _ in range(n)]
     if log_n == 2:
         x = [2, 5, 3, 8]
     omega = O.root_of_unity(n)
-    ref = R.fft(O.pack_scalars(x), O.le32(omega))
-    ref_vals = [int.from_bytes(ref[64 * i:64 * i + 64], "little") for i in range(n)]
-    ours = ctx.ntt(O.pack_scalars(x), O.le32(omega))
-    assert [O.from_le(ours[32 * i:32 * i + 32]) for i in range(n)] == ref_vals
     exp = list(x)
     O.serial_radix2_fft(exp, omega)
-    assert ref_vals == exp
+    ours = ctx.ntt(O.pack_scalars(x), O.le32(omega))
+    assert [O.from_le(ours[32 * i:32 * i + 32]) for i in range(n)] == exp
+    ref = _ref('fft', O.pack_scalars(x), O.le32(omega))
+    ref_vals = [int.from_bytes(ref[64 * i:64 * i + 64], "little") for i in range(n)]
+    if ref_vals != exp:
+        pytest.xfail("the reference's dormant GPU FFT kernel reads uninitialised limbs (algebra_fft_FFTAuxiliary.cu:117-119,129-131)")
 
 
 @pytest.mark.skipif(not R.available("fixedmsm"), reason="oracle/_ref/libref_fixedmsm.so not built")
@@ -86,11 +99,11 @@ def test_fixed_base_and_field_match_reference_cuda(ctx):
     outerc = (ss + w - 1) // w
     scalars = [0, 1, O.R - 1] + [rng.randrange(O.R) for _ in range(n - 3)]
     sb = O.pack_scalars(scalars)
-    ref = O.unpack_g1(R.fixed_batch(outerc, w, outerc, 1 << w, n, ss, O.pack_g1([base]), sb, 1), stride=64, big_endian=True)
+    ref = O.unpack_g1(_ref('fixed_batch', outerc, w, outerc, 1 << w, n, ss, O.pack_g1([base]), sb, 1), stride=64, big_endian=True)
     ours = O.unpack_g1(ctx.fixed_g1(O.pack_g1([base]), sb, n, outerc, w))
     exp = O.fixed_batch_msm(O.G1, ss, w, base, scalars)
     for a, b, e in zip(ours, ref, exp):
         assert O.G1.equals(a, b) and O.G1.equals(b, e)
     b = rng.randrange(O.R)
-    rf = R.field_batch(sb + O.le32(b), n)
+    rf = _ref('field_batch', sb + O.le32(b), n)
     assert [int.from_bytes(rf[64 * i:64 * i + 64], "big") for i in range(n)] == O.field_batch_msm(scalars, b)

@@ -1,0 +1,90 @@
+"""Sweep of BASELINE.json configs[1..3] on one GPU, device-resident, CUDA-event timed (median of 5 after 2 warm-ups):
+G1 / G2 variable-base MSM, NTT, fixed-base batch MSM.  Prints one JSON line per point; used for profiles/rNN_sweep.jsonl.
+
+    python tools/sweep.py [msm|msm2|ntt|fixed|fixed2 ...]"""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from octopuszk_b200 import Context  # noqa: E402
+from oracle import dizk_oracle as O  # noqa: E402
+from tests import util  # noqa: E402
+
+ctx = Context(0, stream=torch.cuda.current_stream().cuda_stream)
+what = [a for a in sys.argv[1:] if not a.startswith("-")] or ["msm", "msm2", "ntt", "fixed", "fixed2"]
+
+
+def timeit(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return sorted(ts)[len(ts) // 2]
+
+
+def msm_sweep(G, logs, name):
+    ks, pool = util.known_dlog_points(G, 64, seed=1, random_z=False)
+    pool = [G.to_affine(p) for p in pool]
+    for log_n in logs:
+        n = 1 << log_n
+        raw = util.rand_scalars_bytes(n, seed=log_n)
+        d_s = torch.from_numpy(raw).cuda()
+        d_b = torch.from_numpy(np.ascontiguousarray(util.tiled_bases_bytes(G, pool, n))).cuda()
+        fn = ctx.msm_g1_dev if G is O.G1 else ctx.msm_g2_dev
+        out = fn(d_s, d_b, n)
+        ok = G.equals(util.unpack_point(G, out), util.expected_from_dlogs(G, ks, util.column_sums(raw, 64)))
+        ms = timeit(lambda: fn(d_s, d_b, n))
+        st = ctx.msm_last_stats()
+        print(json.dumps({"op": name, "log_n": log_n, "ok": ok, "ms": ms, "Mpairs_per_s": n / ms / 1e3, "window_bits": st[0],
+                          "phases_ms": {"sort": st[5], "convert": st[6], "accumulate": st[7], "merge": st[8], "reduce_final": st[9]}}), flush=True)
+        del d_s, d_b
+
+
+if "msm" in what:
+    msm_sweep(O.G1, [16, 18, 20, 22, 24, 26], "varmsm_g1")
+if "msm2" in what:
+    msm_sweep(O.G2, [16, 18, 20, 22], "varmsm_g2")
+if "ntt" in what:
+    for log_n in [16, 18, 20, 22, 24, 26, 28]:
+        n = 1 << log_n
+        d = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device="cuda")
+        d[:, 31] &= 0x1F
+        o = torch.empty_like(d)
+        omega = O.le32(O.root_of_unity(n))
+        ms = timeit(lambda: ctx.ntt_dev(d, o, n, omega))
+        print(json.dumps({"op": "ntt_fr", "log_n": log_n, "ms": ms, "alg_GBps": n * 128 / ms / 1e6, "Gmodmul_per_s_alg": n * log_n / 2 / ms / 1e6}), flush=True)
+        del d, o
+for key, G, logs in (("fixed", O.G1, [20, 22, 24]), ("fixed2", O.G2, [20, 22])):
+    if key not in what:
+        continue
+    base_pt = G.random(10)
+    base = O.pack_g1([base_pt]) if G is O.G1 else O.pack_g2([base_pt])
+    ss = G.bit_size(base_pt)
+    for log_n in logs:
+        n = 1 << log_n
+        w = O.get_window_size(n, G)
+        outerc = (ss + w - 1) // w
+        raw = util.rand_scalars_bytes(n, seed=log_n)
+        d_s = torch.from_numpy(raw).cuda()
+        d_o = torch.empty((n, 96 if G is O.G1 else 192), dtype=torch.uint8, device="cuda")
+        fn = ctx.fixed_g1_dev if G is O.G1 else ctx.fixed_g2_dev
+        ms = timeit(lambda: fn(base, d_s, n, outerc, w, d_o))
+        # spot check three outputs
+        outb = d_o[:3].cpu().numpy().tobytes()
+        pts = O.unpack_g1(outb) if G is O.G1 else O.unpack_g2(outb)
+        sc = util.scalars_from_bytes(raw[:3])
+        ok = all(G.equals(p, e) for p, e in zip(pts, O.fixed_batch_msm(G, ss, w, base_pt, sc)))
+        print(json.dumps({"op": "fixed_" + ("g1" if G is O.G1 else "g2"), "log_n": log_n, "window": w, "outerc": outerc, "ok": ok, "ms": ms,
+                          "Mscalars_per_s": n / ms / 1e3}), flush=True)
+        del d_s, d_o
