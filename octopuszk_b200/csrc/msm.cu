@@ -5,6 +5,7 @@
 // the result as a group element: signed digits (half the buckets), all windows processed at once, a counting sort of
 // 4-byte point indices instead of scattering whole 192-byte points per window (:758), no host round trips.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.h"
@@ -240,8 +241,8 @@ static int msm_sort(ozk_ctx* ctx, const void* d_scalars, size_t n, const MsmShap
     OZK_TRY(ctx->msm[B_OVFBUCKET].reserve((size_t)sh.ovf_bucket_cap * sizeof(OvfBucket), st));
     OZK_TRY(ctx->msm[B_MISC].reserve(kMiscWords * 4, st));
     OZK_TRY(ctx->msm[B_ORDER].reserve(nbt * 4, st));
-    uint32_t* misc = (uint32_t*)ctx->msm[B_MISC].p;      // [0] flag, [1] ovf task count, [2] ovf bucket count, run-length histogram
-    OZK_CUDA(cudaMemsetAsync(misc, 0, kMiscWords * 4, st));
+    uint32_t* misc = (uint32_t*)ctx->msm[B_MISC].p;      // [0] flag (cleared by the caller), [1] ovf task count, [2] ovf bucket count, run-length histogram
+    OZK_CUDA(cudaMemsetAsync(misc + 1, 0, (kMiscWords - 1) * 4, st));
     OZK_CUDA(cudaMemsetAsync(ctx->msm[B_COUNT].p, 0, nbt * 4, st));
     const unsigned grid = (unsigned)((n + 255) / 256);
     msm_digits<0><<<grid, 256, 0, st>>>((const uint4*)d_scalars, n, sh.c, sh.nwin, (uint32_t*)ctx->msm[B_COUNT].p, nullptr, misc);
@@ -372,6 +373,8 @@ static void write_inf(uint8_t* out, size_t coord_bytes) {
 static int msm_run(ozk_ctx* ctx, const void* d_scalars, const void* d_b1, const void* d_b2, size_t n, uint8_t* out) {
     OZK_ARG(n > 0 && n < ((size_t)1 << 31), "msm: between 1 and 2^31 - 1 points per call");
     const MsmShape sh = msm_shape(n);
+    OZK_TRY(ctx->msm[B_MISC].reserve(kMiscWords * 4, ctx->stream));
+    OZK_CUDA(cudaMemsetAsync(ctx->msm[B_MISC].p, 0, 4, ctx->stream));
     OZK_CUDA(cudaEventRecord(ctx->evs[0], ctx->stream));
     ctx->msm_stats[0] = sh.c;
     ctx->msm_stats[1] = sh.nwin;
@@ -391,68 +394,65 @@ static int msm_run(ozk_ctx* ctx, const void* d_scalars, const void* d_b1, const 
     return msm_finish(ctx, d_res, bytes, out);
 }
 
-// Host-pointer entry: scalars go up first and are sorted while the (3x larger) bases are still crossing PCIe on a second
-// stream in chunks; each chunk is normalised as soon as it lands.  Only the bucket phase needs everything.
+// Host-pointer entry.  Large inputs are cut into up to kCopyChunks slices: slice k+1 crosses PCIe on a second stream
+// while slice k is sorted, normalised and accumulated, and the partial sums are added at the end.  (An MSM is a sum over
+// points, so slices are independent; this is the same partition-then-add the Java does with its 2^23-element chunks,
+// VariableBaseMSM.java:211-265, except that here it only exists to overlap the copies.)
 static int msm_run_host(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* b1, const uint8_t* b2, size_t n, uint8_t* out) {
     OZK_ARG(n > 0 && n < ((size_t)1 << 31), "msm: between 1 and 2^31 - 1 points per call");
     cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
-    const MsmShape sh = msm_shape(n);
-    ctx->msm_stats[0] = sh.c;
-    ctx->msm_stats[1] = sh.nwin;
-    ctx->msm_stats[2] = sh.nb;
+    int nslices = 1;
+    if (n >= ((size_t)1 << 22)) nslices = 4;
+    else if (n >= ((size_t)1 << 20)) nslices = 2;
+    if (const char* e = getenv("OZK_HOST_SLICES")) nslices = std::max(1, std::min(kCopyChunks, atoi(e)));
+    const size_t slice = (n + nslices - 1) / nslices;
     OZK_TRY(ctx->io_a.reserve(n * 32, st));
     if (b1) OZK_TRY(ctx->io_b.reserve(n * 96, st));
     if (b2) OZK_TRY(ctx->io_c.reserve(n * 192, st));
-    if (b1) OZK_TRY(ctx->msm[B_AFF1].reserve(n * kMsmG1.affine_bytes, st));
-    if (b2) OZK_TRY(ctx->msm[B_AFF2].reserve(n * kMsmG2.affine_bytes, st));
     OZK_TRY(ctx->msm[B_MISC].reserve(kMiscWords * 4, st));
+    OZK_TRY(ctx->io_out.reserve(512 + (size_t)kCopyChunks * 2 * 288, st));
+    OZK_CUDA(cudaMemsetAsync(ctx->msm[B_MISC].p, 0, 4, st));
     OZK_CUDA(cudaEventRecord(ctx->evs[0], st));
-    OZK_CUDA(cudaMemcpyAsync(ctx->io_a.p, scalars, n * 32, cudaMemcpyHostToDevice, st));
-    // the copy stream must not overtake earlier work on the main stream that still reads the staging buffers
+    // the copy stream must not overtake earlier work on the main stream that still uses the staging buffers
     OZK_CUDA(cudaEventRecord(ctx->copy_ev[2 * kCopyChunks], st));
     OZK_CUDA(cudaStreamWaitEvent(cs, ctx->copy_ev[2 * kCopyChunks], 0));
-    const size_t chunk = (n + kCopyChunks - 1) / kCopyChunks;
-    int nev = 0;
-    struct Part { const uint8_t* h; char* d; size_t stride; int first_ev; };
-    Part parts[2] = {{b1, (char*)ctx->io_b.p, 96, 0}, {b2, (char*)ctx->io_c.p, 192, 0}};
-    for (auto& pt : parts) {
-        if (!pt.h) continue;
-        pt.first_ev = nev;
-        for (size_t lo = 0; lo < n; lo += chunk) {
-            const size_t len = std::min(chunk, n - lo);
-            OZK_CUDA(cudaMemcpyAsync(pt.d + lo * pt.stride, pt.h + lo * pt.stride, len * pt.stride, cudaMemcpyHostToDevice, cs));
-            OZK_CUDA(cudaEventRecord(ctx->copy_ev[nev++], cs));
-        }
+    int k = 0;
+    for (size_t lo = 0; lo < n; lo += slice, k++) {
+        const size_t len = std::min(slice, n - lo);
+        OZK_CUDA(cudaMemcpyAsync((char*)ctx->io_a.p + lo * 32, scalars + lo * 32, len * 32, cudaMemcpyHostToDevice, cs));
+        if (b1) OZK_CUDA(cudaMemcpyAsync((char*)ctx->io_b.p + lo * 96, b1 + lo * 96, len * 96, cudaMemcpyHostToDevice, cs));
+        if (b2) OZK_CUDA(cudaMemcpyAsync((char*)ctx->io_c.p + lo * 192, b2 + lo * 192, len * 192, cudaMemcpyHostToDevice, cs));
+        OZK_CUDA(cudaEventRecord(ctx->copy_ev[k], cs));
     }
-    OZK_TRY(msm_sort(ctx, ctx->io_a.p, n, sh));          // clears the flag word before any convert kernel runs
-    uint32_t* misc = (uint32_t*)ctx->msm[B_MISC].p;
-    for (int g = 0; g < 2; g++) {
-        const Part& pt = parts[g];
-        if (!pt.h) continue;
-        const MsmLaunch& L = g == 0 ? kMsmG1 : kMsmG2;
-        char* aff = (char*)ctx->msm[g == 0 ? B_AFF1 : B_AFF2].p;
-        int ev = pt.first_ev;
-        for (size_t lo = 0; lo < n; lo += chunk) {
-            const size_t len = std::min(chunk, n - lo);
-            OZK_CUDA(cudaStreamWaitEvent(st, ctx->copy_ev[ev++], 0));
-            if (L.convert(st, pt.d + lo * pt.stride, aff + lo * L.affine_bytes, len, misc, ctx->sm_count)) {
-                set_error("msm: convert launch failed");
-                return OZK_ERR_CUDA;
-            }
-            ctx->launches += 1;
+    nslices = k;
+    char* d_res = (char*)ctx->io_out.p;                 // final result
+    char* d_parts1 = d_res + 512;                        // per-slice partial sums, G1 then G2
+    char* d_parts2 = d_parts1 + (size_t)kCopyChunks * 96;
+    k = 0;
+    for (size_t lo = 0; lo < n; lo += slice, k++) {
+        const size_t len = std::min(slice, n - lo);
+        const MsmShape sh = msm_shape(len);
+        if (k == 0) {
+            ctx->msm_stats[0] = sh.c;
+            ctx->msm_stats[1] = sh.nwin;
+            ctx->msm_stats[2] = sh.nb;
         }
+        OZK_CUDA(cudaStreamWaitEvent(st, ctx->copy_ev[k], 0));
+        OZK_TRY(msm_sort(ctx, (char*)ctx->io_a.p + lo * 32, len, sh));
+        if (b1) OZK_TRY(msm_buckets(ctx, kMsmG1, (char*)ctx->io_b.p + lo * 96, len, sh, B_AFF1, nslices == 1 ? d_res : d_parts1 + (size_t)k * 96));
+        if (b2) OZK_TRY(msm_buckets(ctx, kMsmG2, (char*)ctx->io_c.p + lo * 192, len, sh, B_AFF2,
+                                    nslices == 1 ? d_res + (b1 ? 96 : 0) : d_parts2 + (size_t)k * 192));
     }
-    OZK_TRY(ctx->io_out.reserve(512, st));
-    char* d_res = (char*)ctx->io_out.p;
     size_t bytes = 0;
     if (b1) {
-        OZK_TRY(msm_buckets(ctx, kMsmG1, ctx->io_b.p, n, sh, B_AFF1, d_res, true));
+        if (nslices > 1 && kMsmG1.sum_wire(st, d_parts1, (uint32_t)nslices, d_res)) { set_error("msm: sum launch failed"); return OZK_ERR_CUDA; }
         bytes += 96;
     }
     if (b2) {
-        OZK_TRY(msm_buckets(ctx, kMsmG2, ctx->io_c.p, n, sh, B_AFF2, d_res + bytes, true));
+        if (nslices > 1 && kMsmG2.sum_wire(st, d_parts2, (uint32_t)nslices, d_res + bytes)) { set_error("msm: sum launch failed"); return OZK_ERR_CUDA; }
         bytes += 192;
     }
+    if (nslices > 1) ctx->launches += (b1 ? 1 : 0) + (b2 ? 1 : 0);
     return msm_finish(ctx, d_res, bytes, out);
 }
 

@@ -354,6 +354,30 @@ __global__ void msm_final(FinalArgs a, uint4* __restrict__ window_vals, uint4* _
     }
 }
 
+// out = sum of k points given in the canonical Jacobian wire format (partial results of a chunked MSM), same format out
+template <class F>
+__global__ void msm_sum_wire_points(const uint4* __restrict__ in, uint32_t k, uint4* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    constexpr int U = FieldIO<F>::kU4;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t i = 0; i < k; i++) {
+        const uint4* p = in + (size_t)i * (3 * U);
+        F zc = FieldIO<F>::load(p + 2 * U);
+        if (zc.is_zero()) continue;
+        F z = F::to_mont(zc);
+        XYZZ<F> q;
+        q.x = F::to_mont(FieldIO<F>::load(p));
+        q.y = F::to_mont(FieldIO<F>::load(p + U));
+        q.zz = F::sqr(z);
+        q.zzz = F::mul(q.zz, z);
+        xyzz_add_ni(acc, q);
+    }
+    Jacobian<F> j = xyzz_to_jacobian(acc);
+    FieldIO<F>::store(out, F::from_mont(j.x));
+    FieldIO<F>::store(out + U, F::from_mont(j.y));
+    FieldIO<F>::store(out + 2 * U, F::from_mont(j.z));
+}
+
 // ---- host-side launch wrappers (declared here, defined per field in msm_g1.cu / msm_g2.cu) --------------------------
 struct MsmLaunch {
     int (*convert)(cudaStream_t, const void* in, void* out, size_t n, uint32_t* flag, int sm_count);
@@ -364,6 +388,7 @@ struct MsmLaunch {
     int (*wsum)(cudaStream_t, const void* in, uint32_t m_in, uint32_t nwin, void* run_out, void* acc_out);
     int (*sum)(cudaStream_t, const void* in, uint32_t m_in, uint32_t nwin, void* out);
     int (*final)(cudaStream_t, const FinalArgs& a, void* window_vals, void* out);
+    int (*sum_wire)(cudaStream_t, const void* in, uint32_t k, void* out);
     size_t affine_bytes;     // per point
     size_t jac_bytes;        // per point, wire format
     size_t xyzz_bytes;
@@ -414,7 +439,11 @@ extern const MsmLaunch kMsmG2;
         msm_final<F><<<1, 256, 0, s>>>(a, (uint4*)window_vals, (uint4*)out);                                                   \
         return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                                     \
     }                                                                                                                          \
-    const MsmLaunch NAME = {NAME##_convert, NAME##_accumulate, NAME##_merge, NAME##_wsum, NAME##_sum, NAME##_final,            \
+    static int NAME##_sum_wire(cudaStream_t s, const void* in, uint32_t k, void* out) {                                        \
+        msm_sum_wire_points<F><<<1, 32, 0, s>>>((const uint4*)in, k, (uint4*)out);                                             \
+        return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                                     \
+    }                                                                                                                          \
+    const MsmLaunch NAME = {NAME##_convert, NAME##_accumulate, NAME##_merge, NAME##_wsum, NAME##_sum, NAME##_final, NAME##_sum_wire, \
                             sizeof(Affine<F>), sizeof(Jacobian<F>), sizeof(XYZZ<F>)};
 
 }  // namespace ozk
