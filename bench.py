@@ -83,7 +83,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import c_oracle as C
-    threads = C.max_threads()
+    threads = os.cpu_count() or C.max_threads()          # explicit: torchrun exports OMP_NUM_THREADS=1
     log_s = args.ref_log_n
     n = 1 << log_s
     raw, bases, expected = _make_inputs(n, seed=7)
@@ -262,7 +262,7 @@ def run_ours(args):
     cpu = None
     if rank == 0 and not args.no_cpu:
         from oracle import c_oracle as C
-        threads = C.max_threads()
+        threads = os.cpu_count() or C.max_threads()      # explicit: torchrun exports OMP_NUM_THREADS=1
         ls = args.ref_log_n
         m = 1 << ls
         sb, bb = raw[:m].tobytes(), bases[:m].tobytes()

@@ -68,11 +68,11 @@ __global__ void __launch_bounds__(256) msm_digits(const uint4* __restrict__ scal
 }
 
 // One CTA per window: exclusive scan of the bucket counts -> window-local start offsets (also copied to `cursor`),
-// and the overflow work list for buckets with more than kSeg entries.
+// and the overflow work list for buckets with more than seg_len entries.
 __global__ void __launch_bounds__(1024) msm_scan(const uint32_t* __restrict__ count, uint32_t nb, uint32_t* __restrict__ start,
                                                  uint32_t* __restrict__ cursor, OvfTask* __restrict__ ovf_tasks,
                                                  uint32_t* __restrict__ ovf_task_count, OvfBucket* __restrict__ ovf_buckets,
-                                                 uint32_t* __restrict__ ovf_bucket_count, uint32_t ovf_task_cap, uint32_t ovf_bucket_cap) {
+                                                 uint32_t* __restrict__ ovf_bucket_count, uint32_t ovf_task_cap, uint32_t ovf_bucket_cap, uint32_t seg_len) {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t carry_s;
     const uint32_t w = blockIdx.x;
@@ -104,8 +104,8 @@ __global__ void __launch_bounds__(1024) msm_scan(const uint32_t* __restrict__ co
         if (b < nb) {
             start[(size_t)w * nb + b] = excl;
             cursor[(size_t)w * nb + b] = excl;
-            if (v > (uint32_t)kSeg) {
-                const uint32_t extra = (v - 1) / kSeg;
+            if (v > seg_len) {
+                const uint32_t extra = (v - 1) / seg_len;
                 const uint32_t t0 = atomicAdd(ovf_task_count, extra);
                 const uint32_t k = atomicAdd(ovf_bucket_count, 1u);
                 if (k < ovf_bucket_cap && t0 + extra <= ovf_task_cap) {
@@ -121,17 +121,17 @@ __global__ void __launch_bounds__(1024) msm_scan(const uint32_t* __restrict__ co
 }
 
 // ---- bucket order -----------------------------------------------------------------------------------------------
-// Counting sort of the bucket ids by run length (clamped to kSeg), longest first.  msm_accumulate walks the buckets in
+// Counting sort of the bucket ids by run length (clamped to seg_len), longest first.  msm_accumulate walks the buckets in
 // this order so that the lanes of a warp do the same number of additions (run lengths are ~Poisson, otherwise every
 // warp waits for its longest lane), and long runs start first.
-static constexpr int kOrderKeys = kSeg + 1;
+static constexpr int kOrderKeys = kSegMax + 1;
 
-__global__ void __launch_bounds__(256) msm_order_hist(const uint32_t* __restrict__ count, uint32_t nbt, uint32_t* __restrict__ ohist) {
+__global__ void __launch_bounds__(256) msm_order_hist(const uint32_t* __restrict__ count, uint32_t nbt, uint32_t* __restrict__ ohist, uint32_t seg_len) {
     __shared__ uint32_t h[kOrderKeys];
     for (int k = threadIdx.x; k < kOrderKeys; k += blockDim.x) h[k] = 0;
     __syncthreads();
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < nbt) atomicAdd(&h[kSeg - min(count[b], (uint32_t)kSeg)], 1u);
+    if (b < nbt) atomicAdd(&h[seg_len - min(count[b], seg_len)], 1u);
     __syncthreads();
     for (int k = threadIdx.x; k < kOrderKeys; k += blockDim.x)
         if (h[k]) atomicAdd(&ohist[k], h[k]);
@@ -171,14 +171,14 @@ __global__ void __launch_bounds__(1024) msm_order_scan(const uint32_t* __restric
 }
 
 __global__ void __launch_bounds__(256) msm_order_scatter(const uint32_t* __restrict__ count, uint32_t nbt, uint32_t* __restrict__ ocursor,
-                                                         uint32_t* __restrict__ order) {
+                                                         uint32_t* __restrict__ order, uint32_t seg_len) {
     __shared__ uint32_t h[kOrderKeys];
     for (int k = threadIdx.x; k < kOrderKeys; k += blockDim.x) h[k] = 0;
     __syncthreads();
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t key = 0, rank = 0;
     if (b < nbt) {
-        key = kSeg - min(count[b], (uint32_t)kSeg);
+        key = seg_len - min(count[b], seg_len);
         rank = atomicAdd(&h[key], 1u);
     }
     __syncthreads();
@@ -210,6 +210,7 @@ static uint32_t choose_window(size_t n) {
 
 struct MsmShape {
     uint32_t c, nwin, nb, log_nb;
+    uint32_t seg;                      // longest run one accumulate task handles
     uint32_t ovf_task_cap, ovf_bucket_cap;
 };
 
@@ -219,7 +220,12 @@ static MsmShape msm_shape(size_t n) {
     s.nwin = (255 + s.c - 1) / s.c;
     s.log_nb = s.c - 1;
     s.nb = 1u << s.log_nb;
-    size_t cap = ((size_t)s.nwin * n) / kSeg + 1;
+    // task length: long enough to amortise a task, short enough that the serial chain of one task (about 2.3 us per
+    // addition) does not dominate small inputs: aim for ~2^17 tasks
+    size_t want = ((size_t)s.nwin * n) >> 17;
+    s.seg = 32;
+    while (s.seg < (uint32_t)kSegMax && s.seg * 2 <= want) s.seg *= 2;
+    size_t cap = ((size_t)s.nwin * n) / s.seg + 1;
     s.ovf_task_cap = (uint32_t)std::min<size_t>(cap, 0x7fffffffu);
     s.ovf_bucket_cap = s.ovf_task_cap;
     return s;
@@ -248,15 +254,15 @@ static int msm_sort(ozk_ctx* ctx, const void* d_scalars, size_t n, const MsmShap
     msm_digits<0><<<grid, 256, 0, st>>>((const uint4*)d_scalars, n, sh.c, sh.nwin, (uint32_t*)ctx->msm[B_COUNT].p, nullptr, misc);
     msm_scan<<<sh.nwin, 1024, 0, st>>>((const uint32_t*)ctx->msm[B_COUNT].p, sh.nb, (uint32_t*)ctx->msm[B_START].p,
                                        (uint32_t*)ctx->msm[B_CURSOR].p, (OvfTask*)ctx->msm[B_OVFTASK].p, misc + 1,
-                                       (OvfBucket*)ctx->msm[B_OVFBUCKET].p, misc + 2, sh.ovf_task_cap, sh.ovf_bucket_cap);
+                                       (OvfBucket*)ctx->msm[B_OVFBUCKET].p, misc + 2, sh.ovf_task_cap, sh.ovf_bucket_cap, sh.seg);
     msm_digits<1><<<grid, 256, 0, st>>>((const uint4*)d_scalars, n, sh.c, sh.nwin, (uint32_t*)ctx->msm[B_CURSOR].p,
                                         (uint32_t*)ctx->msm[B_SORTED].p, misc);
     {
         const unsigned og = (unsigned)((nbt + 255) / 256);
-        msm_order_hist<<<og, 256, 0, st>>>((const uint32_t*)ctx->msm[B_COUNT].p, (uint32_t)nbt, misc + kMiscOhist);
+        msm_order_hist<<<og, 256, 0, st>>>((const uint32_t*)ctx->msm[B_COUNT].p, (uint32_t)nbt, misc + kMiscOhist, sh.seg);
         msm_order_scan<<<1, 1024, 0, st>>>(misc + kMiscOhist, misc + kMiscOcursor);
         msm_order_scatter<<<og, 256, 0, st>>>((const uint32_t*)ctx->msm[B_COUNT].p, (uint32_t)nbt, misc + kMiscOcursor,
-                                              (uint32_t*)ctx->msm[B_ORDER].p);
+                                              (uint32_t*)ctx->msm[B_ORDER].p, sh.seg);
     }
     ctx->launches += 6;
     OZK_CUDA(cudaGetLastError());
@@ -277,7 +283,7 @@ static int msm_buckets(ozk_ctx* ctx, const MsmLaunch& L, const void* d_bases, si
     OZK_CUDA(cudaEventRecord(ctx->evs[2], st));
     if (L.accumulate(st, ctx->msm[aff_slot].p, (const uint32_t*)ctx->msm[B_SORTED].p, (const uint32_t*)ctx->msm[B_START].p,
                      (const uint32_t*)ctx->msm[B_COUNT].p, (const OvfTask*)ctx->msm[B_OVFTASK].p, misc + 1, (const uint32_t*)ctx->msm[B_ORDER].p,
-                     (uint32_t)nbt, sh.log_nb, n,
+                     (uint32_t)nbt, sh.log_nb, n, sh.seg,
                      sh.ovf_task_cap, ctx->msm[B_BUCKETS].p, ctx->msm[B_OVFPART].p)) { set_error("msm: accumulate launch failed"); return OZK_ERR_CUDA; }
     OZK_CUDA(cudaEventRecord(ctx->evs[3], st));
     if (L.merge(st, (const OvfBucket*)ctx->msm[B_OVFBUCKET].p, misc + 2, std::min<uint32_t>(sh.ovf_bucket_cap, (uint32_t)nbt),

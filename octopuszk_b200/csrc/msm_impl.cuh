@@ -15,9 +15,9 @@
 
 namespace ozk {
 
-static constexpr int kSeg = 1024;        // longest run of points a single accumulate task handles
-static constexpr int kWsumS = 32;        // group size of the hierarchical bucket reduction (log2 = 5)
-static constexpr int kWsumLogS = 5;
+static constexpr int kSegMax = 1024;     // longest run of points a single accumulate task handles (runtime value <= this)
+static constexpr int kWsumS = 8;         // group size of the hierarchical bucket reduction (log2 = 3): short serial chains
+static constexpr int kWsumLogS = 3;
 static constexpr int kConvBatchMax = 64; // most points per thread in the batched normalisations (one inversion per thread)
 // points per thread: large batches amortise the ~380-product inversion, small inputs keep enough threads in flight
 static inline int conv_batch_for(size_t n) {
@@ -189,15 +189,15 @@ __global__ void __launch_bounds__(128) msm_convert_bases(const uint4* __restrict
 }
 
 // ---- accumulate ---------------------------------------------------------------------------------------------------
-// task t < nbuckets_total : bucket t, entries [0, min(cnt, SEG)) of its run           -> buckets[t]
-// task t >= nbuckets_total: overflow task (bucket, seg), entries [seg*SEG, ...)        -> ovf_partial[t - nbuckets_total]
+// task t < nbuckets_total : bucket order[t], entries [0, min(cnt, seg_len)) of its run  -> buckets[bucket]
+// task t >= nbuckets_total: overflow task (bucket, seg), entries [seg*seg_len, ...)     -> ovf_partial[t - nbuckets_total]
 // sorted[w * n + pos] = point index | sign << 31 ; start/count are per (window, bucket), start is window-local.
 template <class F>
 __global__ void __launch_bounds__(128) msm_accumulate(const uint4* __restrict__ bases, const uint32_t* __restrict__ sorted,
                                                       const uint32_t* __restrict__ start, const uint32_t* __restrict__ count,
                                                       const OvfTask* __restrict__ ovf_tasks, const uint32_t* __restrict__ ovf_count,
                                                       const uint32_t* __restrict__ order,
-                                                      uint32_t nbuckets_total, uint32_t log_nb, size_t n,
+                                                      uint32_t nbuckets_total, uint32_t log_nb, size_t n, uint32_t seg_len,
                                                       uint4* __restrict__ buckets, uint4* __restrict__ ovf_partial) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t bucket, seg;
@@ -213,8 +213,8 @@ __global__ void __launch_bounds__(128) msm_accumulate(const uint4* __restrict__ 
     }
     const uint32_t cnt = count[bucket];
     const uint32_t w = bucket >> log_nb;
-    uint32_t lo = seg * kSeg;
-    uint32_t hi = min(cnt, lo + kSeg);
+    uint32_t lo = seg * seg_len;
+    uint32_t hi = min(cnt, lo + seg_len);
     const uint32_t* run = sorted + (size_t)w * n + start[bucket];
     XYZZ<F> acc = XYZZ<F>::inf();
     if (lo < hi) {
@@ -238,34 +238,53 @@ __global__ void __launch_bounds__(128) msm_accumulate(const uint4* __restrict__ 
     else store_xyzz<F>(ovf_partial, t - nbuckets_total, acc);
 }
 
-// one warp per overflow bucket: buckets[b] += sum of its overflow partials
+// buckets[b] += sum of the overflow partials of bucket b.  One warp per 32 overflow buckets: buckets with at most 32 partials
+// are summed by a single lane each (cheap, all lanes busy); denser buckets are then reduced cooperatively, one after the
+// other, with lane-strided sums and a shuffle butterfly.
 template <class F>
 __global__ void __launch_bounds__(128) msm_merge_overflow(const OvfBucket* __restrict__ ovf_buckets, const uint32_t* __restrict__ ovf_bucket_count,
                                                           const uint4* __restrict__ ovf_partial, uint4* __restrict__ buckets) {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
-    if (warp >= *ovf_bucket_count) return;
-    const OvfBucket ob = ovf_buckets[warp];
-    XYZZ<F> acc = XYZZ<F>::inf();
-    for (uint32_t k = lane; k < ob.ntasks; k += 32) {
-        XYZZ<F> q = load_xyzz<F>(ovf_partial, ob.first_task + k);
-        xyzz_add_ni(acc, q);
+    const uint32_t total = *ovf_bucket_count;
+    if (warp * 32 >= total) return;
+    const uint32_t idx = warp * 32 + lane;
+    OvfBucket ob = {0, 0, 0};
+    if (idx < total) ob = ovf_buckets[idx];
+    if (ob.ntasks > 0 && ob.ntasks <= 32) {
+        XYZZ<F> acc = load_xyzz<F>(buckets, ob.bucket);
+        for (uint32_t k = 0; k < ob.ntasks; k++) {
+            XYZZ<F> q = load_xyzz<F>(ovf_partial, ob.first_task + k);
+            xyzz_add_ni(acc, q);
+        }
+        store_xyzz<F>(buckets, ob.bucket, acc);
     }
-    // butterfly reduction across the warp
-    constexpr int W = sizeof(XYZZ<F>) / 4;
+    const uint32_t dense = __ballot_sync(0xffffffffu, ob.ntasks > 32);
+    for (uint32_t m = dense; m; m &= m - 1) {
+        const int src = __ffs(m) - 1;
+        const uint32_t nt = __shfl_sync(0xffffffffu, ob.ntasks, src);
+        const uint32_t ft = __shfl_sync(0xffffffffu, ob.first_task, src);
+        const uint32_t bk = __shfl_sync(0xffffffffu, ob.bucket, src);
+        XYZZ<F> acc = XYZZ<F>::inf();
+        for (uint32_t k = lane; k < nt; k += 32) {
+            XYZZ<F> q = load_xyzz<F>(ovf_partial, ft + k);
+            xyzz_add_ni(acc, q);
+        }
+        constexpr int W = sizeof(XYZZ<F>) / 4;
 #pragma unroll 1
-    for (int off = 16; off >= 1; off >>= 1) {
-        XYZZ<F> other;
-        uint32_t* src = reinterpret_cast<uint32_t*>(&acc);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&other);
+        for (int off = 16; off >= 1; off >>= 1) {
+            XYZZ<F> other;
+            uint32_t* sp = reinterpret_cast<uint32_t*>(&acc);
+            uint32_t* dp = reinterpret_cast<uint32_t*>(&other);
 #pragma unroll
-        for (int i = 0; i < W; i++) dst[i] = __shfl_xor_sync(0xffffffffu, src[i], off);
-        xyzz_add_ni(acc, other);
-    }
-    if (lane == 0) {
-        XYZZ<F> b = load_xyzz<F>(buckets, ob.bucket);
-        xyzz_add_ni(b, acc);
-        store_xyzz<F>(buckets, ob.bucket, b);
+            for (int i = 0; i < W; i++) dp[i] = __shfl_xor_sync(0xffffffffu, sp[i], off);
+            xyzz_add_ni(acc, other);
+        }
+        if (lane == 0) {
+            XYZZ<F> bsum = load_xyzz<F>(buckets, bk);
+            xyzz_add_ni(bsum, acc);
+            store_xyzz<F>(buckets, bk, bsum);
+        }
     }
 }
 
@@ -383,6 +402,7 @@ struct MsmLaunch {
     int (*convert)(cudaStream_t, const void* in, void* out, size_t n, uint32_t* flag, int sm_count);
     int (*accumulate)(cudaStream_t, const void* bases, const uint32_t* sorted, const uint32_t* start, const uint32_t* count,
                       const OvfTask* tasks, const uint32_t* ovf_count, const uint32_t* order, uint32_t nbuckets_total, uint32_t log_nb, size_t n,
+                      uint32_t seg_len,
                       uint32_t ovf_cap, void* buckets, void* ovf_partial);
     int (*merge)(cudaStream_t, const OvfBucket* ob, const uint32_t* ob_count, uint32_t ob_cap, const void* ovf_partial, void* buckets);
     int (*wsum)(cudaStream_t, const void* in, uint32_t m_in, uint32_t nwin, void* run_out, void* acc_out);
@@ -409,17 +429,18 @@ extern const MsmLaunch kMsmG2;
     }                                                                                                                          \
     static int NAME##_accumulate(cudaStream_t s, const void* bases, const uint32_t* sorted, const uint32_t* start,             \
                                  const uint32_t* count, const OvfTask* tasks, const uint32_t* ovf_count, const uint32_t* order, \
-                                 uint32_t nbt, uint32_t log_nb, size_t n, uint32_t ovf_cap, void* buckets, void* ovf_partial) { \
+                                 uint32_t nbt, uint32_t log_nb, size_t n, uint32_t seg_len, uint32_t ovf_cap, void* buckets,     \
+                                 void* ovf_partial) {                                                                          \
         size_t total = (size_t)nbt + ovf_cap;                                                                                  \
         unsigned grid = (unsigned)((total + 127) / 128);                                                                       \
-        msm_accumulate<F><<<grid, 128, 0, s>>>((const uint4*)bases, sorted, start, count, tasks, ovf_count, order, nbt, log_nb, n, \
+        msm_accumulate<F><<<grid, 128, 0, s>>>((const uint4*)bases, sorted, start, count, tasks, ovf_count, order, nbt, log_nb, n, seg_len, \
                                                (uint4*)buckets, (uint4*)ovf_partial);                                          \
         return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                                     \
     }                                                                                                                          \
     static int NAME##_merge(cudaStream_t s, const OvfBucket* ob, const uint32_t* ob_count, uint32_t ob_cap,                    \
                             const void* ovf_partial, void* buckets) {                                                          \
         if (ob_cap == 0) return 0;                                                                                             \
-        unsigned grid = (unsigned)(((size_t)ob_cap * 32 + 127) / 128);                                                         \
+        unsigned grid = (unsigned)(((size_t)ob_cap + 127) / 128);      /* one warp per 32 overflow buckets */                  \
         msm_merge_overflow<F><<<grid, 128, 0, s>>>(ob, ob_count, (const uint4*)ovf_partial, (uint4*)buckets);                  \
         return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                                     \
     }                                                                                                                          \
