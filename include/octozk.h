@@ -71,6 +71,11 @@ OZK_API int ozk_fr_scale_dev(ozk_ctx* ctx, const void* d_a, void* d_out, size_t 
 OZK_API int ozk_fr_scale_powers_dev(ozk_ctx* ctx, const void* d_a, void* d_out, size_t n, const uint8_t* scale, const uint8_t* coset,
                             uint64_t first_index);
 
+/* out[i] = a[i] * b[i] - c[i] mod r (d_c may be NULL: plain product; d_out may alias an input): the pointwise step between
+ * the transforms of R1CStoQAP.R1CStoQAPWitness (src/main/java/reductions/r1cs_to_qap/R1CStoQAP.java:180-182,211-214), so
+ * that A, B, C and H stay on the device from the first inverse FFT to the H MSM. */
+OZK_API int ozk_fr_mul_sub_dev(ozk_ctx* ctx, const void* d_a, const void* d_b, const void* d_c, void* d_out, size_t n);
+
 /* ---- radix-2 NTT over Fr ---------------------------------------------------------------------------------
  * out[k] = sum_j in[j] * omega^(j k), natural order in and out, n a power of two <= 2^28, omega a primitive n-th
  * root of unity.  Replaces FFTAuxiliary.serialRadix2FFT (src/main/java/algebra/fft/FFTAuxiliary.java:60-124) and the

@@ -135,6 +135,114 @@ struct alignas(16) Fp {
     }
     OZK_HD static Fp sqr(const Fp& a) { return mul(a, a); }
 
+    // ---- lazy reduction: full 512-bit products, 512-bit add / sub, one Montgomery reduction for a sum of products --------
+    // mul_wide is the multiplication above without the m*p half of every round (64 multiply-adds); redc is the other half
+    // on its own (72): together the same 136, but a*b - c*d costs 2 x 64 + 72 instead of 2 x 136.
+    struct Wide {
+        uint32_t v[16];
+    };
+    // a, b: any 256-bit values
+    OZK_HD static Wide mul_wide(const Fp& a, const Fp& b) {
+        uint32_t x[8], y[8];
+        Wide t;
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            uint64_t pe = (uint64_t)a.v[j] * b.v[0];
+            uint64_t po = (uint64_t)a.v[j + 1] * b.v[0];
+            x[j] = (uint32_t)pe;
+            x[j + 1] = (uint32_t)(pe >> 32);
+            y[j] = (uint32_t)po;
+            y[j + 1] = (uint32_t)(po >> 32);
+        }
+        // invariant before round i: the limb-0 accumulator's low limb is limb i-1 of the product, final
+        t.v[0] = x[0];
+        chain::mont_round_ab(y, x, a.v, b.v[1]);
+        t.v[1] = y[0];
+        chain::mont_round_ab(x, y, a.v, b.v[2]);
+        t.v[2] = x[0];
+        chain::mont_round_ab(y, x, a.v, b.v[3]);
+        t.v[3] = y[0];
+        chain::mont_round_ab(x, y, a.v, b.v[4]);
+        t.v[4] = x[0];
+        chain::mont_round_ab(y, x, a.v, b.v[5]);
+        t.v[5] = y[0];
+        chain::mont_round_ab(x, y, a.v, b.v[6]);
+        t.v[6] = x[0];
+        chain::mont_round_ab(y, x, a.v, b.v[7]);
+        // y: limb-0 accumulator at limb 7, x: limb-1 accumulator at limb 8
+        t.v[7] = y[0];
+        uint32_t sh[8];
+#pragma unroll
+        for (int i = 0; i < 7; i++) sh[i] = y[i + 1];
+        sh[7] = 0;
+        chain::add8(t.v + 8, x, sh);
+        return t;
+    }
+    // t / 2^256 mod m for t < m * 2^256, result in [0, m)
+    OZK_HD static Fp redc(const Wide& t) {
+        uint32_t x[8], y[8], m[8];
+        load_mod(m);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            x[i] = t.v[i];
+            y[i] = 0;
+        }
+        chain::mont_round_mp(x, y, m, P::NP0);
+        chain::redc_shift(y, x, t.v[8]);
+        chain::mont_round_mp(y, x, m, P::NP0);
+        chain::redc_shift(x, y, t.v[9]);
+        chain::mont_round_mp(x, y, m, P::NP0);
+        chain::redc_shift(y, x, t.v[10]);
+        chain::mont_round_mp(y, x, m, P::NP0);
+        chain::redc_shift(x, y, t.v[11]);
+        chain::mont_round_mp(x, y, m, P::NP0);
+        chain::redc_shift(y, x, t.v[12]);
+        chain::mont_round_mp(y, x, m, P::NP0);
+        chain::redc_shift(x, y, t.v[13]);
+        chain::mont_round_mp(x, y, m, P::NP0);
+        chain::redc_shift(y, x, t.v[14]);
+        chain::mont_round_mp(y, x, m, P::NP0);
+        // y: limb-0 accumulator (y[0] == 0), x: limb-1 accumulator; the top input limb joins at limb 7 of the result
+        uint32_t sh[8], s[8];
+#pragma unroll
+        for (int i = 0; i < 7; i++) sh[i] = y[i + 1];
+        sh[7] = t.v[15];
+        chain::add8(s, x, sh);
+        return reduce_once(s);
+    }
+    OZK_HD static Wide wide_add(const Wide& a, const Wide& b) {
+        Wide r;
+        uint32_t c, x;
+        chain::add8c(r.v, c, x, a.v, b.v, 0u, 0xffffffffu);
+        chain::add8c(r.v + 8, c, x, a.v + 8, b.v + 8, c, 0xffffffffu);
+        return r;
+    }
+    // a - b, requires a >= b
+    OZK_HD static Wide wide_sub(const Wide& a, const Wide& b) {
+        Wide r;
+        uint32_t bw, x;
+        chain::sub8b(r.v, bw, x, a.v, b.v, 0u);
+        chain::sub8b(r.v + 8, bw, x, a.v + 8, b.v + 8, bw & 1u);
+        return r;
+    }
+    // a + b without the final reduction (a, b < m < 2^254, so the sum fits): an operand for mul_wide
+    OZK_HD static Fp add_raw(const Fp& a, const Fp& b) {
+        Fp r;
+        chain::add8(r.v, a.v, b.v);
+        return r;
+    }
+    // a*b - c*d with a single Montgomery reduction
+    OZK_HD static Fp mul_sub(const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
+        return redc(wide_sub_lazy(mul_wide(a, b), mul_wide(c, d)));
+    }
+    // a + m^2 - b: the non-negative representative of a - b for a, b < m^2 (result < 2 m^2 < m 2^256, fit for redc)
+    OZK_HD static Wide wide_sub_lazy(const Wide& a, const Wide& b) {
+        Wide k;
+#pragma unroll
+        for (int i = 0; i < 16; i++) k.v[i] = P::msq(i);
+        return wide_sub(wide_add(a, k), b);
+    }
+
     // ---- conversions ---------------------------------------------------------------------------------------
     OZK_HD static Fp to_mont(const Fp& a) { return mul(a, rr()); }     // a * R
     OZK_HD static Fp from_mont(const Fp& a) {                           // a / R

@@ -289,7 +289,7 @@ static int msm_buckets(ozk_ctx* ctx, const MsmLaunch& L, const void* d_bases, si
     if (L.merge(st, (const OvfBucket*)ctx->msm[B_OVFBUCKET].p, misc + 2, std::min<uint32_t>(sh.ovf_bucket_cap, (uint32_t)nbt),
                 ctx->msm[B_OVFPART].p, ctx->msm[B_BUCKETS].p)) { set_error("msm: merge launch failed"); return OZK_ERR_CUDA; }
     OZK_CUDA(cudaEventRecord(ctx->evs[4], st));
-    ctx->launches += 3;
+    ctx->launches += preconverted ? 3 : 4;
 
     // hierarchical reduction.  scratch layout (in XYZZ elements per window): level arrays A_1.., acc arrays, sum temporaries
     uint32_t m[8], nlev = 0;

@@ -113,7 +113,7 @@ __device__ __forceinline__ void xyzz_madd_hot(XYZZ<F>& acc, const Affine<F>& q) 
     F PPP = F::mul(Pp, PP);
     F Q = F::mul(acc.x, PP);
     F X3 = F::sub(F::sub(F::sqr(Rr), PPP), F::dbl(Q));
-    acc.y = F::sub(F::mul(Rr, F::sub(Q, X3)), F::mul(acc.y, PPP));
+    acc.y = F::mul_sub(Rr, F::sub(Q, X3), acc.y, PPP);       // one reduction for both products (lazy)
     acc.x = X3;
     acc.zz = F::mul(acc.zz, PP);
     acc.zzz = F::mul(acc.zzz, PPP);
@@ -238,36 +238,33 @@ __global__ void __launch_bounds__(128) msm_accumulate(const uint4* __restrict__ 
     else store_xyzz<F>(ovf_partial, t - nbuckets_total, acc);
 }
 
-// buckets[b] += sum of the overflow partials of bucket b.  One warp per 32 overflow buckets: buckets with at most 32 partials
-// are summed by a single lane each (cheap, all lanes busy); denser buckets are then reduced cooperatively, one after the
-// other, with lane-strided sums and a shuffle butterfly.
-template <class F>
+// buckets[b] += sum of the overflow partials of bucket b.  Two launches over the overflow-bucket list:
+//   DENSE == false: one thread per overflow bucket with at most 32 partials (serial sum; the common case for short task lengths)
+//   DENSE == true : one warp per overflow bucket with more than 32 partials (lane-strided sums + shuffle butterfly)
+template <class F, bool DENSE>
 __global__ void __launch_bounds__(128) msm_merge_overflow(const OvfBucket* __restrict__ ovf_buckets, const uint32_t* __restrict__ ovf_bucket_count,
                                                           const uint4* __restrict__ ovf_partial, uint4* __restrict__ buckets) {
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t lane = threadIdx.x & 31;
     const uint32_t total = *ovf_bucket_count;
-    if (warp * 32 >= total) return;
-    const uint32_t idx = warp * 32 + lane;
-    OvfBucket ob = {0, 0, 0};
-    if (idx < total) ob = ovf_buckets[idx];
-    if (ob.ntasks > 0 && ob.ntasks <= 32) {
+    if (!DENSE) {
+        const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+        if (idx >= total) return;
+        const OvfBucket ob = ovf_buckets[idx];
+        if (ob.ntasks > 32) return;
         XYZZ<F> acc = load_xyzz<F>(buckets, ob.bucket);
         for (uint32_t k = 0; k < ob.ntasks; k++) {
             XYZZ<F> q = load_xyzz<F>(ovf_partial, ob.first_task + k);
             xyzz_add_ni(acc, q);
         }
         store_xyzz<F>(buckets, ob.bucket, acc);
-    }
-    const uint32_t dense = __ballot_sync(0xffffffffu, ob.ntasks > 32);
-    for (uint32_t m = dense; m; m &= m - 1) {
-        const int src = __ffs(m) - 1;
-        const uint32_t nt = __shfl_sync(0xffffffffu, ob.ntasks, src);
-        const uint32_t ft = __shfl_sync(0xffffffffu, ob.first_task, src);
-        const uint32_t bk = __shfl_sync(0xffffffffu, ob.bucket, src);
+    } else {
+        const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        const uint32_t lane = threadIdx.x & 31;
+        if (warp >= total) return;
+        const OvfBucket ob = ovf_buckets[warp];
+        if (ob.ntasks <= 32) return;
         XYZZ<F> acc = XYZZ<F>::inf();
-        for (uint32_t k = lane; k < nt; k += 32) {
-            XYZZ<F> q = load_xyzz<F>(ovf_partial, ft + k);
+        for (uint32_t k = lane; k < ob.ntasks; k += 32) {
+            XYZZ<F> q = load_xyzz<F>(ovf_partial, ob.first_task + k);
             xyzz_add_ni(acc, q);
         }
         constexpr int W = sizeof(XYZZ<F>) / 4;
@@ -281,9 +278,9 @@ __global__ void __launch_bounds__(128) msm_merge_overflow(const OvfBucket* __res
             xyzz_add_ni(acc, other);
         }
         if (lane == 0) {
-            XYZZ<F> bsum = load_xyzz<F>(buckets, bk);
+            XYZZ<F> bsum = load_xyzz<F>(buckets, ob.bucket);
             xyzz_add_ni(bsum, acc);
-            store_xyzz<F>(buckets, bk, bsum);
+            store_xyzz<F>(buckets, ob.bucket, bsum);
         }
     }
 }
@@ -440,8 +437,10 @@ extern const MsmLaunch kMsmG2;
     static int NAME##_merge(cudaStream_t s, const OvfBucket* ob, const uint32_t* ob_count, uint32_t ob_cap,                    \
                             const void* ovf_partial, void* buckets) {                                                          \
         if (ob_cap == 0) return 0;                                                                                             \
-        unsigned grid = (unsigned)(((size_t)ob_cap + 127) / 128);      /* one warp per 32 overflow buckets */                  \
-        msm_merge_overflow<F><<<grid, 128, 0, s>>>(ob, ob_count, (const uint4*)ovf_partial, (uint4*)buckets);                  \
+        unsigned grid1 = (unsigned)(((size_t)ob_cap + 127) / 128);          /* thread per overflow bucket */                  \
+        unsigned grid32 = (unsigned)(((size_t)ob_cap * 32 + 127) / 128);    /* warp per overflow bucket */                    \
+        msm_merge_overflow<F, false><<<grid1, 128, 0, s>>>(ob, ob_count, (const uint4*)ovf_partial, (uint4*)buckets);          \
+        msm_merge_overflow<F, true><<<grid32, 128, 0, s>>>(ob, ob_count, (const uint4*)ovf_partial, (uint4*)buckets);          \
         return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                                     \
     }                                                                                                                          \
     static int NAME##_wsum(cudaStream_t s, const void* in, uint32_t m_in, uint32_t nwin, void* run_out, void* acc_out) {       \

@@ -347,6 +347,19 @@ __global__ void __launch_bounds__(256) fr_scale_powers_kernel(const uint4* in, u
     }
 }
 
+// out[i] = a[i] * b[i] - c[i] (c may be null): the pointwise step between the transforms of the QAP witness map
+// (R1CStoQAP.java:180-182,211-214).  All values canonical: to_mont(a) * b = a*b in canonical form.
+__global__ void __launch_bounds__(256) fr_mul_sub_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, const uint4* __restrict__ c,
+                                                         uint4* __restrict__ out, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        Fr x = Fr::to_mont(load_fr(a + i * 2));
+        Fr v = Fr::mul(x, load_fr(b + i * 2));
+        if (c) v = Fr::sub(v, load_fr(c + i * 2));
+        store_fr(out + i * 2, v);
+    }
+}
+
 // ---- small cross-shard DFT (the second step of the multi-GPU transform) ---------------------------------------------------
 // out[k1 * len + j] = sum_{i1 < G} in[i1 * len + j] * omega_G^(i1 k1), G = 2^Q <= 8: one thread per j, all G values in registers.
 template <int Q>
@@ -632,6 +645,19 @@ int ozk_fr_scale_dev(ozk_ctx* ctx, const void* d_a, void* d_out, size_t n, const
     OZK_ARG(d_a && d_out && b, "ozk_fr_scale_dev: null pointer");
     if (n == 0) return OZK_OK;
     return scale_powers(ctx, d_a, d_out, n, b, nullptr);
+}
+
+int ozk_fr_mul_sub_dev(ozk_ctx* ctx, const void* d_a, const void* d_b, const void* d_c, void* d_out, size_t n) {
+    OZK_TRY(ctx_enter(ctx));
+    OZK_ARG(n == 0 || (d_a && d_b && d_out), "ozk_fr_mul_sub_dev: null pointer");
+    if (n == 0) return OZK_OK;
+    size_t blocks = (n + 255) / 256;
+    const size_t cap = (size_t)ctx->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    fr_mul_sub_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>((const uint4*)d_a, (const uint4*)d_b, (const uint4*)d_c, (uint4*)d_out, n);
+    ctx->launches += 1;
+    OZK_CUDA(cudaGetLastError());
+    return OZK_OK;
 }
 
 int ozk_fr_dft_small_dev(ozk_ctx* ctx, const void* d_in, void* d_out, size_t groups, size_t len, const uint8_t omega_g[32]) {

@@ -179,12 +179,9 @@ class Groth16:
         for d in (dA, dB, dC):
             ctx.ntt_ex_dev(d, d, n, winv, None, ninv, None)                 # radix2InverseFFT
             ctx.ntt_ex_dev(d, d, n, w, _le32(g), None, None)                # radix2CosetFFT
-        ctx.sync()
-        # pointwise (A*B - C) on the host, as the Java loops do (R1CStoQAP.java:180-214)
-        hA, hB, hC = (d.cpu().numpy().tobytes() for d in (dA, dB, dC))
-        H = [(int.from_bytes(hA[32 * i:32 * i + 32], "little") * int.from_bytes(hB[32 * i:32 * i + 32], "little")
-              - int.from_bytes(hC[32 * i:32 * i + 32], "little")) % R for i in range(n)]
-        dH = up(H)
+        # pointwise A*B - C on the device (R1CStoQAP.java:180-214); nothing returns to the host between the transforms
+        dH = dA
+        ctx.fr_mul_sub_dev(dA, dB, dC, dH, n)
         inv_z = pow(dom.computeZ(g), -1, R)                                 # divideByZOnCoset folded into the post-scale
         scale = pow(n, -1, R) * inv_z % R
         ctx.ntt_ex_dev(dH, dH, n, winv, None, _le32(scale), _le32(pow(g, -1, R)))   # (divide by Z) + radix2CosetInverseFFT

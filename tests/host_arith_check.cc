@@ -50,6 +50,14 @@ static void field_cmd(const std::string& op, std::istringstream& in) {
         in >> sb;
         F b = F::to_mont(parse<F>(sb));
         if (op == "mul") r = F::mul(a, b);
+        else if (op == "lazymul") r = F::redc(F::mul_wide(a, b));
+        else if (op == "lazydiff") {
+            // a*b - b*b via one reduction
+            r = F::redc(F::wide_sub_lazy(F::mul_wide(a, b), F::mul_wide(b, b)));
+        } else if (op == "lazysum") {
+            // redc of (a*b + a*a - a*b) exercising wide_add / wide_sub
+            r = F::redc(F::wide_sub(F::wide_add(F::mul_wide(a, b), F::mul_wide(a, a)), F::mul_wide(a, b)));
+        }
         else if (op == "add") r = F::add(a, b);
         else if (op == "sub") r = F::sub(a, b);
         else { std::cout << "bad\n"; return; }

@@ -38,6 +38,9 @@ def test_field_ops(checker):
             a, b = rng.choice(vals), rng.choice(vals)
             cmds += [f"{name} mul {h(a)} {h(b)}", f"{name} add {h(a)} {h(b)}", f"{name} sub {h(a)} {h(b)}"]
             exp += ["%064x" % (a * b % m), "%064x" % ((a + b) % m), "%064x" % ((a - b) % m)]
+            # lazy reduction: wide products, 512-bit add/sub, a single Montgomery reduction
+            cmds += [f"{name} lazymul {h(a)} {h(b)}", f"{name} lazydiff {h(a)} {h(b)}", f"{name} lazysum {h(a)} {h(b)}"]
+            exp += ["%064x" % (a * b % m), "%064x" % ((a * b - b * b) % m), "%064x" % (a * a % m)]
         for a in vals[:40]:
             cmds += [f"{name} neg {h(a)}", f"{name} inv {h(a)}", f"{name} sqr {h(a)}"]
             exp += ["%064x" % ((-a) % m), "%064x" % (pow(a, -1, m) if a else 0), "%064x" % (a * a % m)]

@@ -127,6 +127,29 @@ ins.append(('addc.u32', 'o7', ('o7', '0')))
 block('mont_round_mp', [('e', 'io', 8), ('o', 'io', 8), ('p', 'in', 8), ('np', 'in', 1)], ins,
       'm = e[0] * np mod 2^32; T += m * p.  Afterwards e[0] == 0 (T is divisible by 2^32).')
 
+# Montgomery reduction of a 16-limb value, shift step between rounds: drop the (zero) low limb of the limb-0 accumulator `o`,
+# fold its limb 1 into e[0], move the rest down by two limbs and bring the next input limb t in at the top.
+ins = [('add.cc.u32', 'e0', ('e0', 'o1'))]
+for j in range(6):
+    ins.append(('addc.cc.u32', 'o%d' % j, ('o%d' % (j + 2), '0')))
+ins.append(('addc.cc.u32', 'o6', ('t', '0')))
+ins.append(('addc.u32', 'o7', ('0', '0')))
+block('redc_shift', [('e', 'io', 8), ('o', 'io', 8), ('t', 'in', 1)], ins,
+      "Shift between two rounds of a stand-alone Montgomery reduction: e[0] += o[1]; o = (o >> 64) + carry, with the next input\n"
+      "// limb t entering at o[6].  Afterwards e is the limb-0 and o the limb-1 accumulator.")
+
+# 8-limb add / sub with carry (borrow) in and out, for 16-limb values handled as two halves
+ins = [('add.cc.u32', 'x', ('cin', 'ones'))]          # CC = cin
+ins += [('addc.cc.u32', 'r%d' % i, ('a%d' % i, 'b%d' % i)) for i in range(8)]
+ins += [('addc.u32', 'cout', ('0', '0'))]
+block('add8c', [('r', 'out', 8), ('cout', 'out', 1), ('x', 'out', 1), ('a', 'in', 8), ('b', 'in', 8), ('cin', 'in', 1), ('ones', 'in', 1)], ins,
+      'r = a + b + cin over 8 limbs, cout = carry out (cin, cout in {0,1}; ones must be 0xffffffff; x is scratch)')
+ins = [('sub.cc.u32', 'x', ('0', 'bin'))]             # borrow flag = bin
+ins += [('subc.cc.u32', 'r%d' % i, ('a%d' % i, 'b%d' % i)) for i in range(8)]
+ins += [('subc.u32', 'bout', ('0', '0'))]
+block('sub8b', [('r', 'out', 8), ('bout', 'out', 1), ('x', 'out', 1), ('a', 'in', 8), ('b', 'in', 8), ('bin', 'in', 1)], ins,
+      'r = a - b - bin over 8 limbs, bout = 0xffffffff when a borrow leaves limb 7 else 0 (bin in {0,1}; x is scratch)')
+
 HDR = '''// GENERATED by tools/gen_chains.py -- do not edit.
 // Carry-chain blocks of the 256-bit field arithmetic.  Each block is ONE non-volatile inline-asm statement (so the
 // carry flag never crosses a statement the compiler could reorder, and NVVM sees a handful of pure asm calls per
