@@ -68,7 +68,9 @@ __global__ void __launch_bounds__(256) msm_digits(const uint4* __restrict__ scal
 }
 
 // One CTA per window: exclusive scan of the bucket counts -> window-local start offsets (also copied to `cursor`),
-// and the overflow work list for buckets with more than seg_len entries.
+// and the overflow work list for buckets with more than seg_len entries.  Each thread scans kScanPer consecutive buckets
+// per step, so a window of 2^19 buckets takes 64 block-wide steps.
+static constexpr int kScanPer = 8;
 __global__ void __launch_bounds__(1024) msm_scan(const uint32_t* __restrict__ count, uint32_t nb, uint32_t* __restrict__ start,
                                                  uint32_t* __restrict__ cursor, OvfTask* __restrict__ ovf_tasks,
                                                  uint32_t* __restrict__ ovf_task_count, OvfBucket* __restrict__ ovf_buckets,
@@ -79,11 +81,17 @@ __global__ void __launch_bounds__(1024) msm_scan(const uint32_t* __restrict__ co
     const uint32_t* cnt = count + (size_t)w * nb;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
-    for (uint32_t base = 0; base < nb; base += 1024) {
-        const uint32_t b = base + threadIdx.x;
-        const uint32_t v = b < nb ? cnt[b] : 0;
-        // block-wide exclusive scan of v
-        uint32_t x = v;
+    for (uint32_t base = 0; base < nb; base += 1024 * kScanPer) {
+        const uint32_t b0 = base + threadIdx.x * kScanPer;
+        uint32_t v[kScanPer];
+        uint32_t tsum = 0;
+#pragma unroll
+        for (int k = 0; k < kScanPer; k++) {
+            v[k] = (b0 + k) < nb ? cnt[b0 + k] : 0;
+            tsum += v[k];
+        }
+        // block-wide exclusive scan of the per-thread sums
+        uint32_t x = tsum;
         const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
         for (int off = 1; off < 32; off <<= 1) {
             uint32_t y = __shfl_up_sync(0xffffffffu, x, off);
@@ -100,22 +108,27 @@ __global__ void __launch_bounds__(1024) msm_scan(const uint32_t* __restrict__ co
             warp_sums[lane] = ws;
         }
         __syncthreads();
-        const uint32_t excl = carry_s + (wid ? warp_sums[wid - 1] : 0) + x - v;
-        if (b < nb) {
-            start[(size_t)w * nb + b] = excl;
-            cursor[(size_t)w * nb + b] = excl;
-            if (v > seg_len) {
-                const uint32_t extra = (v - 1) / seg_len;
-                const uint32_t t0 = atomicAdd(ovf_task_count, extra);
-                const uint32_t k = atomicAdd(ovf_bucket_count, 1u);
-                if (k < ovf_bucket_cap && t0 + extra <= ovf_task_cap) {
-                    ovf_buckets[k] = {w * nb + b, t0, extra};
-                    for (uint32_t t = 0; t < extra; t++) ovf_tasks[t0 + t] = {w * nb + b, t + 1};
+        uint32_t excl = carry_s + (wid ? warp_sums[wid - 1] : 0) + x - tsum;
+#pragma unroll
+        for (int k = 0; k < kScanPer; k++) {
+            const uint32_t b = b0 + k;
+            if (b < nb) {
+                start[(size_t)w * nb + b] = excl;
+                cursor[(size_t)w * nb + b] = excl;
+                if (v[k] > seg_len) {
+                    const uint32_t extra = (v[k] - 1) / seg_len;
+                    const uint32_t t0 = atomicAdd(ovf_task_count, extra);
+                    const uint32_t kk = atomicAdd(ovf_bucket_count, 1u);
+                    if (kk < ovf_bucket_cap && t0 + extra <= ovf_task_cap) {
+                        ovf_buckets[kk] = {w * nb + b, t0, extra};
+                        for (uint32_t t = 0; t < extra; t++) ovf_tasks[t0 + t] = {w * nb + b, t + 1};
+                    }
                 }
             }
+            excl += v[k];
         }
         __syncthreads();
-        if (threadIdx.x == 1023) carry_s = excl + v;
+        if (threadIdx.x == 1023) carry_s = excl;
         __syncthreads();
     }
 }
@@ -189,17 +202,23 @@ __global__ void __launch_bounds__(256) msm_order_scatter(const uint32_t* __restr
 }
 
 // ---- window choice ---------------------------------------------------------------------------------------------
-// Cost model: nwin(c) * (n mixed adds + 2 * 2^(c-1) full adds at ~1.5x the cost of a mixed add), and short runs waste
-// lanes (one thread per bucket), so prefer c with at least ~64 points per bucket when n allows.
+// Cost model in units of one mixed addition: nwin(c) * (n * (1 + lane imbalance) + ~3 per bucket for the bucket reduce +
+// a fixed per-window tail).  Buckets are visited in order of run length, so the imbalance term is small; what limits c
+// is the bucket-reduce work (2^(c-1) buckets per window, two full additions each).  2^24 -> c = 20 (13 windows).
+static constexpr uint32_t kMaxWindowBits = 20;
 static uint32_t choose_window(size_t n) {
+    if (const char* e = getenv("OZK_MSM_WINDOW")) {
+        int c = atoi(e);
+        if (c >= 2 && c <= (int)kMaxWindowBits) return (uint32_t)c;
+    }
     uint32_t best = 2;
     double best_cost = 1e300;
-    for (uint32_t c = 2; c <= 16; c++) {
+    for (uint32_t c = 2; c <= kMaxWindowBits; c++) {
         const double nwin = (255 + c - 1) / c;
         const double nb = (double)(1u << (c - 1));
         const double per_bucket = (double)n / nb;
-        const double imbalance = per_bucket >= 1 ? 1.0 + 2.5 / std::sqrt(per_bucket) : 4.0;
-        const double cost = nwin * ((double)n * imbalance + 3.0 * nb + 2000.0);
+        const double imbalance = per_bucket >= 1 ? 0.5 / std::sqrt(per_bucket) : 2.0;
+        const double cost = nwin * ((double)n * (1.0 + imbalance) + 3.0 * nb + 2000.0);
         if (cost < best_cost) {
             best_cost = cost;
             best = c;
