@@ -177,6 +177,53 @@ OZK_HD void xyzz_add(XYZZ<F>& acc, const XYZZ<F>& q) {
     acc.zzz = F::mul(F::mul(acc.zzz, q.zzz), PPP);
 }
 
+// ---- one XYZZ doubling spread over four lanes --------------------------------------------------------------------------
+// The window-combining Horner chain of an MSM is ~255 dependent doublings on ONE value: pure latency.  A doubling has 9
+// products but only 3 dependent levels, so four lanes sharing the value through shared memory finish it in 3 product
+// latencies instead of 9.  All lanes run the same instruction stream (same F::mul, operands picked by lane from a slot
+// table), so there is no divergence; the additions between levels are done by lane 0.  Infinity is all zeros and stays
+// all zeros through the formulas.  (Tested on the CPU by running the lanes one after the other: tests/host_arith_check.cc.)
+template <class F>
+struct CoopDbl {
+    enum { sX, sY, sZZ, sZZZ, sU, sV, sXX, sM, sW, sS, sMM, sVZ, sD, sT1, sT2, sWZ, sX3, sDummy0, sDummy1, sDummy2, sDummy3, kSlots };
+    F s[kSlots];
+    OZK_HD void load(const XYZZ<F>& p) { s[sX] = p.x; s[sY] = p.y; s[sZZ] = p.zz; s[sZZZ] = p.zzz; }
+    OZK_HD XYZZ<F> value() const { return {s[sX], s[sY], s[sZZ], s[sZZZ]}; }
+    // level 0..2: the product lane `lane` (0..3) computes
+    OZK_HD void mul_level(int level, int lane) {
+        int a, b, d;
+        if (level == 0) {
+            a = lane == 0 ? sU : sX; b = a; d = lane == 0 ? sV : lane == 1 ? sXX : sDummy0 + lane;
+        } else if (level == 1) {
+            a = lane == 0 ? sU : lane == 1 ? sM : lane == 2 ? sX : sV;
+            b = lane == 0 ? sV : lane == 1 ? sM : lane == 2 ? sV : sZZ;
+            d = lane == 0 ? sW : lane == 1 ? sMM : lane == 2 ? sS : sVZ;
+        } else {
+            a = lane == 0 ? sM : lane == 1 ? sW : lane == 2 ? sW : sX;
+            b = lane == 0 ? sD : lane == 1 ? sY : lane == 2 ? sZZZ : sX;
+            d = lane == 0 ? sT1 : lane == 1 ? sT2 : lane == 2 ? sWZ : sDummy3;
+        }
+        F r = F::mul(s[a], s[b]);
+        s[d] = r;
+    }
+    // the additions before level `level` (0..2) and after the last one (3); executed by one lane
+    OZK_HD void fix(int level) {
+        if (level == 0) {
+            s[sU] = F::dbl(s[sY]);
+        } else if (level == 1) {
+            s[sM] = F::add(F::dbl(s[sXX]), s[sXX]);
+        } else if (level == 2) {
+            s[sX3] = F::sub(s[sMM], F::dbl(s[sS]));
+            s[sD] = F::sub(s[sS], s[sX3]);
+        } else {
+            s[sY] = F::sub(s[sT1], s[sT2]);
+            s[sX] = s[sX3];
+            s[sZZ] = s[sVZ];
+            s[sZZZ] = s[sWZ];
+        }
+    }
+};
+
 template <class F>
 OZK_HD Affine<F> affine_neg(const Affine<F>& p) {
     return {p.x, F::neg(p.y)};

@@ -202,9 +202,13 @@ __global__ void __launch_bounds__(256) msm_order_scatter(const uint32_t* __restr
 }
 
 // ---- window choice ---------------------------------------------------------------------------------------------
-// Cost model in units of one mixed addition: nwin(c) * (n * (1 + lane imbalance) + ~3 per bucket for the bucket reduce +
-// a fixed per-window tail).  Buckets are visited in order of run length, so the imbalance term is small; what limits c
-// is the bucket-reduce work (2^(c-1) buckets per window, two full additions each).  2^24 -> c = 20 (13 windows).
+// Cost model in units of one mixed addition per (point, window), calibrated on B200 at n = 2^24 (profiles/r1_window_sweep.txt):
+//   accumulate : n * (1 + lane imbalance) + ~12 per bucket (bucket store, per-task set-up, two full additions in the reduce)
+//   sort       : 0.12 n while the live write sectors of the counting sort (one 32-byte sector per bucket cursor, all
+//                windows) stay well inside L2; 0.42 n once they do not (c >= 18 at 13-15 windows: the 4-byte scattered
+//                stores then go to DRAM sector by sector: measured 4.9 ms at c = 16, 6.7 at 17, 15.8 at 18, 10.9 at 20)
+//   tail       : a fixed per-window cost
+// 2^24 and 2^26 -> c = 17 (15 windows); a sort that writes coalesced runs would move the optimum to c = 19-20.
 static constexpr uint32_t kMaxWindowBits = 20;
 static uint32_t choose_window(size_t n) {
     if (const char* e = getenv("OZK_MSM_WINDOW")) {
@@ -218,7 +222,9 @@ static uint32_t choose_window(size_t n) {
         const double nb = (double)(1u << (c - 1));
         const double per_bucket = (double)n / nb;
         const double imbalance = per_bucket >= 1 ? 0.5 / std::sqrt(per_bucket) : 2.0;
-        const double cost = nwin * ((double)n * (1.0 + imbalance) + 3.0 * nb + 2000.0);
+        const double live_sector_bytes = nwin * nb * 32.0;
+        const double sort_pen = live_sector_bytes <= 40e6 ? 0.12 : 0.42;
+        const double cost = nwin * ((double)n * (1.0 + imbalance + sort_pen) + 12.0 * nb + 2000.0);
         if (cost < best_cost) {
             best_cost = cost;
             best = c;
@@ -310,24 +316,16 @@ static int msm_buckets(ozk_ctx* ctx, const MsmLaunch& L, const void* d_bases, si
     OZK_CUDA(cudaEventRecord(ctx->evs[4], st));
     ctx->launches += preconverted ? 3 : 4;
 
-    // hierarchical reduction.  scratch layout (in XYZZ elements per window): level arrays A_1.., acc arrays, sum temporaries
-    uint32_t m[8], nlev = 0;
+    // hierarchical reduction: one launch per level (msm_reduce_level).  Level l turns A_l (m[l] per window) into run = A_{l+1}
+    // and acc_l (m[l+1] per window each) and carries acc_0 .. acc_{l-1} one summation step further.
+    uint32_t m[9], nlev = 0;
     m[0] = sh.nb;
     while (m[nlev] > 1) {
         m[nlev + 1] = (m[nlev] + kWsumS - 1) / kWsumS;
         nlev++;
     }
-    // total elements needed: for each level l: run (m[l+1]) + acc (m[l+1]) + acc-sum chain (m[l+1]/S + ... + 1)
     size_t per_win = 4;
-    for (uint32_t l = 0; l < nlev; l++) {
-        per_win += 2 * (size_t)m[l + 1];
-        uint32_t k = m[l + 1];
-        while (k > 1) {
-            k = (k + kWsumS - 1) / kWsumS;
-            per_win += k;
-        }
-        per_win += 1;
-    }
+    for (uint32_t l = 0; l < nlev; l++) per_win += (size_t)(l + 2) * m[l + 1];
     OZK_TRY(ctx->msm[B_SCRATCH].reserve((per_win * sh.nwin + 512) * L.xyzz_bytes, st));
     char* sp = (char*)ctx->msm[B_SCRATCH].p;
     auto take = [&](size_t elems_per_win) {
@@ -338,25 +336,27 @@ static int msm_buckets(ozk_ctx* ctx, const MsmLaunch& L, const void* d_bases, si
     FinalArgs fa;
     memset(&fa, 0, sizeof fa);
     const void* level_in = ctx->msm[B_BUCKETS].p;
+    const void* partial[8] = {};          // partial[k]: current (partially summed) acc array of level k
     for (uint32_t l = 0; l < nlev; l++) {
+        ReduceArgs ra;
+        memset(&ra, 0, sizeof ra);
+        ra.m_in = m[l];
+        ra.nwin = sh.nwin;
         void* run = take(m[l + 1]);
         void* acc = take(m[l + 1]);
-        if (L.wsum(st, level_in, m[l], sh.nwin, run, acc)) { set_error("msm: wsum launch failed"); return OZK_ERR_CUDA; }
-        ctx->launches += 1;
-        // sum acc over its m[l+1] groups
-        const void* cur = acc;
-        uint32_t k = m[l + 1];
-        while (k > 1) {
-            uint32_t k2 = (k + kWsumS - 1) / kWsumS;
-            void* nxt = take(k2);
-            if (L.sum(st, cur, k, sh.nwin, nxt)) { set_error("msm: sum launch failed"); return OZK_ERR_CUDA; }
-            ctx->launches += 1;
-            cur = nxt;
-            k = k2;
+        ra.job[0] = {(const uint4*)level_in, (uint4*)run, (uint4*)acc};
+        ra.njobs = 1;
+        for (uint32_t k = 0; k < l; k++) {
+            void* nxt = take(m[l + 1]);
+            ra.job[ra.njobs++] = {(const uint4*)partial[k], (uint4*)nxt, nullptr};
+            partial[k] = nxt;
         }
-        fa.sum_acc[l] = (const uint4*)cur;
+        partial[l] = acc;
+        if (L.reduce_level(st, ra)) { set_error("msm: reduce launch failed"); return OZK_ERR_CUDA; }
+        ctx->launches += 1;
         level_in = run;
     }
+    for (uint32_t l = 0; l < nlev; l++) fa.sum_acc[l] = (const uint4*)partial[l];
     fa.total = (const uint4*)level_in;     // one element per window: the plain sum of all buckets (nb == 1: the bucket itself)
     fa.nlevels = nlev;
     fa.nwin = sh.nwin;

@@ -286,45 +286,42 @@ __global__ void __launch_bounds__(128) msm_merge_overflow(const OvfBucket* __res
 }
 
 // ---- hierarchical bucket reduction ---------------------------------------------------------------------------------
-// For every window and every group g of S consecutive inputs: run[g] = sum_j in[gS+j], acc[g] = sum_j j * in[gS+j].
-template <class F>
-__global__ void __launch_bounds__(128) msm_wsum_level(const uint4* __restrict__ in, uint32_t m_in, uint32_t nwin,
-                                                      uint4* __restrict__ run_out, uint4* __restrict__ acc_out) {
-    const uint32_t groups = (m_in + kWsumS - 1) / kWsumS;
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= groups * nwin) return;
-    const uint32_t w = t / groups, g = t % groups;
-    const size_t base = (size_t)w * m_in + (size_t)g * kWsumS;
-    const uint32_t len = min((uint32_t)kWsumS, m_in - g * kWsumS);
-    XYZZ<F> run = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
-    for (int j = (int)len - 1; j >= 1; j--) {
-        XYZZ<F> q = load_xyzz<F>(in, base + j);
-        xyzz_add(run, q);
-        xyzz_add(acc, run);
-    }
-    {
-        XYZZ<F> q = load_xyzz<F>(in, base);
-        xyzz_add(run, q);
-    }
-    store_xyzz<F>(run_out, (size_t)w * groups + g, run);
-    store_xyzz<F>(acc_out, (size_t)w * groups + g, acc);
-}
+// One launch per level handles several arrays at once (blockIdx.y = job): job 0 reduces the level's input with index
+// weights -- for every window and every group g of S consecutive inputs run[g] = sum_j in[gS+j], acc[g] = sum_j j * in[gS+j] --
+// and the other jobs carry the acc arrays of the earlier levels one step further towards their plain sums (same shapes), so
+// the whole reduction is `levels` launches with a serial chain of 2S-1 additions each.  Inputs are prefetched one ahead.
+struct ReduceJob {
+    const uint4* in;
+    uint4* out_run;      // plain sums of the groups
+    uint4* out_acc;      // weighted sums of the groups, or null for a plain-sum job
+};
+struct ReduceArgs {
+    ReduceJob job[8];
+    uint32_t njobs;
+    uint32_t m_in;       // elements per window in every input of this level
+    uint32_t nwin;
+};
 
-// out[w][g] = sum of the g-th group of S inputs of window w
 template <class F>
-__global__ void __launch_bounds__(128) msm_sum_level(const uint4* __restrict__ in, uint32_t m_in, uint32_t nwin, uint4* __restrict__ out) {
-    const uint32_t groups = (m_in + kWsumS - 1) / kWsumS;
+__global__ void __launch_bounds__(128) msm_reduce_level(ReduceArgs a) {
+    const ReduceJob jb = a.job[blockIdx.y];
+    const uint32_t groups = (a.m_in + kWsumS - 1) / kWsumS;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= groups * nwin) return;
+    if (t >= groups * a.nwin) return;
     const uint32_t w = t / groups, g = t % groups;
-    const size_t base = (size_t)w * m_in + (size_t)g * kWsumS;
-    const uint32_t len = min((uint32_t)kWsumS, m_in - g * kWsumS);
-    XYZZ<F> s = XYZZ<F>::inf();
-    for (uint32_t j = 0; j < len; j++) {
-        XYZZ<F> q = load_xyzz<F>(in, base + j);
-        xyzz_add(s, q);
+    const size_t base = (size_t)w * a.m_in + (size_t)g * kWsumS;
+    const uint32_t len = min((uint32_t)kWsumS, a.m_in - g * kWsumS);
+    XYZZ<F> run = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
+    XYZZ<F> q = load_xyzz<F>(jb.in, base + len - 1);
+    for (int j = (int)len - 1; j >= 1; j--) {
+        XYZZ<F> qn = load_xyzz<F>(jb.in, base + j - 1);
+        xyzz_add(run, q);
+        if (jb.out_acc) xyzz_add(acc, run);
+        q = qn;
     }
-    store_xyzz<F>(out, (size_t)w * groups + g, s);
+    xyzz_add(run, q);
+    store_xyzz<F>(jb.out_run, (size_t)w * groups + g, run);
+    if (jb.out_acc) store_xyzz<F>(jb.out_acc, (size_t)w * groups + g, acc);
 }
 
 // ---- final ------------------------------------------------------------------------------------------------------------
@@ -356,17 +353,40 @@ __global__ void msm_final(FinalArgs a, uint4* __restrict__ window_vals, uint4* _
         store_xyzz<F>(window_vals, w, T);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        XYZZ<F> res = XYZZ<F>::inf();
+    // Horner over the windows: ~nwin * c dependent doublings.  Lanes 0..3 of warp 0 share each doubling (CoopDbl: three
+    // product latencies instead of nine); lane 0 does the nwin additions and the output conversion.
+    __shared__ CoopDbl<F> st;
+    if (threadIdx.x < 4) {
+        const int lane = threadIdx.x;
+        const unsigned mask = 0xfu;
+        if (lane == 0) st.load(XYZZ<F>::inf());
+        __syncwarp(mask);
         for (int ww = (int)a.nwin - 1; ww >= 0; ww--) {
-            for (uint32_t d = 0; d < a.c; d++) res = xyzz_dbl(res);
-            XYZZ<F> q = load_xyzz<F>(window_vals, ww);
-            xyzz_add(res, q);
+            for (uint32_t d = 0; d < a.c; d++) {
+#pragma unroll 1
+                for (int level = 0; level < 3; level++) {
+                    if (lane == 0) st.fix(level);
+                    __syncwarp(mask);
+                    st.mul_level(level, lane);
+                    __syncwarp(mask);
+                }
+                if (lane == 0) st.fix(3);
+                __syncwarp(mask);
+            }
+            if (lane == 0) {
+                XYZZ<F> res = st.value();
+                XYZZ<F> q = load_xyzz<F>(window_vals, ww);
+                xyzz_add(res, q);
+                st.load(res);
+            }
+            __syncwarp(mask);
         }
-        Jacobian<F> j = xyzz_to_jacobian(res);
-        FieldIO<F>::store(out, F::from_mont(j.x));
-        FieldIO<F>::store(out + U, F::from_mont(j.y));
-        FieldIO<F>::store(out + 2 * U, F::from_mont(j.z));
+        if (lane == 0) {
+            Jacobian<F> j = xyzz_to_jacobian(st.value());
+            FieldIO<F>::store(out, F::from_mont(j.x));
+            FieldIO<F>::store(out + U, F::from_mont(j.y));
+            FieldIO<F>::store(out + 2 * U, F::from_mont(j.z));
+        }
     }
 }
 
@@ -402,8 +422,7 @@ struct MsmLaunch {
                       uint32_t seg_len,
                       uint32_t ovf_cap, void* buckets, void* ovf_partial);
     int (*merge)(cudaStream_t, const OvfBucket* ob, const uint32_t* ob_count, uint32_t ob_cap, const void* ovf_partial, void* buckets);
-    int (*wsum)(cudaStream_t, const void* in, uint32_t m_in, uint32_t nwin, void* run_out, void* acc_out);
-    int (*sum)(cudaStream_t, const void* in, uint32_t m_in, uint32_t nwin, void* out);
+    int (*reduce_level)(cudaStream_t, const ReduceArgs& a);
     int (*final)(cudaStream_t, const FinalArgs& a, void* window_vals, void* out);
     int (*sum_wire)(cudaStream_t, const void* in, uint32_t k, void* out);
     size_t affine_bytes;     // per point
@@ -443,16 +462,10 @@ extern const MsmLaunch kMsmG2;
         msm_merge_overflow<F, true><<<grid32, 128, 0, s>>>(ob, ob_count, (const uint4*)ovf_partial, (uint4*)buckets);          \
         return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                                     \
     }                                                                                                                          \
-    static int NAME##_wsum(cudaStream_t s, const void* in, uint32_t m_in, uint32_t nwin, void* run_out, void* acc_out) {       \
-        uint32_t groups = (m_in + kWsumS - 1) / kWsumS;                                                                        \
-        unsigned grid = (groups * nwin + 127) / 128;                                                                           \
-        msm_wsum_level<F><<<grid, 128, 0, s>>>((const uint4*)in, m_in, nwin, (uint4*)run_out, (uint4*)acc_out);                \
-        return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                                     \
-    }                                                                                                                          \
-    static int NAME##_sum(cudaStream_t s, const void* in, uint32_t m_in, uint32_t nwin, void* out) {                           \
-        uint32_t groups = (m_in + kWsumS - 1) / kWsumS;                                                                        \
-        unsigned grid = (groups * nwin + 127) / 128;                                                                           \
-        msm_sum_level<F><<<grid, 128, 0, s>>>((const uint4*)in, m_in, nwin, (uint4*)out);                                      \
+    static int NAME##_reduce_level(cudaStream_t s, const ReduceArgs& a) {                                                      \
+        uint32_t groups = (a.m_in + kWsumS - 1) / kWsumS;                                                                      \
+        dim3 grid((groups * a.nwin + 127) / 128, a.njobs);                                                                     \
+        msm_reduce_level<F><<<grid, 128, 0, s>>>(a);                                                                           \
         return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                                     \
     }                                                                                                                          \
     static int NAME##_final(cudaStream_t s, const FinalArgs& a, void* window_vals, void* out) {                                \
@@ -463,7 +476,7 @@ extern const MsmLaunch kMsmG2;
         msm_sum_wire_points<F><<<1, 32, 0, s>>>((const uint4*)in, k, (uint4*)out);                                             \
         return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                                     \
     }                                                                                                                          \
-    const MsmLaunch NAME = {NAME##_convert, NAME##_accumulate, NAME##_merge, NAME##_wsum, NAME##_sum, NAME##_final, NAME##_sum_wire, \
+    const MsmLaunch NAME = {NAME##_convert, NAME##_accumulate, NAME##_merge, NAME##_reduce_level, NAME##_final, NAME##_sum_wire, \
                             sizeof(Affine<F>), sizeof(Jacobian<F>), sizeof(XYZZ<F>)};
 
 }  // namespace ozk

@@ -137,6 +137,22 @@ int main() {
                 G1Affine a = g1_parse(in), b = g1_parse(in);
                 xyzz_madd(u, a); xyzz_madd(u, b);
                 g1_print(xyzz_dbl(u));
+            } else if (op == "coopdbl") {
+                // k doublings with the four-lane cooperative schedule, lanes emulated one after the other
+                int k; in >> k;
+                G1XYZZ u = G1XYZZ::inf();
+                G1Affine a = g1_parse(in), b = g1_parse(in);
+                xyzz_madd(u, a); xyzz_madd(u, b);
+                CoopDbl<Fq> st;
+                st.load(u);
+                for (int i = 0; i < k; i++) {
+                    for (int level = 0; level < 3; level++) {
+                        st.fix(level);
+                        for (int lane = 0; lane < 4; lane++) st.mul_level(level, lane);
+                    }
+                    st.fix(3);
+                }
+                g1_print(st.value());
             }
         } else if (fld == "g2") {
             if (op == "chain") {
@@ -155,6 +171,21 @@ int main() {
                 G2Affine a = g2_parse(in), b = g2_parse(in);
                 xyzz_madd(u, a); xyzz_madd(u, b);
                 g2_print(xyzz_dbl(u));
+            } else if (op == "coopdbl") {
+                int k; in >> k;
+                G2XYZZ u = G2XYZZ::inf();
+                G2Affine a = g2_parse(in), b = g2_parse(in);
+                xyzz_madd(u, a); xyzz_madd(u, b);
+                CoopDbl<Fq2> st;
+                st.load(u);
+                for (int i = 0; i < k; i++) {
+                    for (int level = 0; level < 3; level++) {
+                        st.fix(level);
+                        for (int lane = 0; lane < 4; lane++) st.mul_level(level, lane);
+                    }
+                    st.fix(3);
+                }
+                g2_print(st.value());
             }
         } else {
             std::cout << "bad\n";

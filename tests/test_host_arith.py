@@ -123,4 +123,11 @@ def test_curve_ops(checker, gname):
     for a, b in ((pts[5], pts[6]), (pts[7], inf), (inf, inf)):
         cmds.append(f"{gname} dbl " + " ".join(_fmt(G, _aff(G, p)) for p in (a, b)))
         exp.append(_out(G, _aff(G, G.twice(G.add(a, b)))))
+    # the four-lane cooperative doubling schedule used by the MSM's window-combining Horner chain
+    for k, (a, b) in ((1, (pts[5], pts[6])), (5, (pts[7], pts[8])), (3, (inf, inf)), (2, (pts[9], inf))):
+        cmds.append(f"{gname} coopdbl {k} " + " ".join(_fmt(G, _aff(G, p)) for p in (a, b)))
+        e = G.add(a, b)
+        for _ in range(k):
+            e = G.twice(e)
+        exp.append(_out(G, _aff(G, e)))
     assert checker(cmds) == exp
