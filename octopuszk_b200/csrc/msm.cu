@@ -35,19 +35,24 @@ __device__ __forceinline__ bool scalar_lt_r(const uint32_t (&s)[8]) {
 }
 
 // MODE 0: histogram (count[w * nb + b] += 1).  MODE 1: scatter (sorted[w * n + cursor++] = i | sign << 31).
+// Only windows [win_lo, win_hi) are emitted by one launch (the carries of the lower windows are still computed): the
+// scatter is launched per group of windows small enough that the live 32-byte store sectors (one per bucket cursor) stay
+// in L2, so the 4-byte scattered stores combine there instead of going to DRAM one sector at a time.
 template <int MODE>
 __global__ void __launch_bounds__(256) msm_digits(const uint4* __restrict__ scalars, size_t n, uint32_t c, uint32_t nwin,
+                                                  uint32_t win_lo, uint32_t win_hi,
                                                   uint32_t* __restrict__ count_or_cursor, uint32_t* __restrict__ sorted,
                                                   uint32_t* flag) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint4 a = scalars[2 * i], b = scalars[2 * i + 1];
     uint32_t s[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    if (MODE == 0 && !scalar_lt_r(s)) atomicOr(flag, 2u);
+    if (MODE == 0 && win_lo == 0 && !scalar_lt_r(s)) atomicOr(flag, 2u);
     const uint32_t half = 1u << (c - 1);
     const uint32_t log_nb = c - 1;
     uint32_t carry = 0;
-    for (uint32_t w = 0; w < nwin; w++) {
+    (void)nwin;
+    for (uint32_t w = 0; w < win_hi; w++) {
         uint32_t d = scalar_bits(s, w * c, c) + carry;
         uint32_t neg = 0;
         carry = 0;
@@ -56,7 +61,7 @@ __global__ void __launch_bounds__(256) msm_digits(const uint4* __restrict__ scal
             neg = 1;
             carry = 1;
         }
-        if (d == 0) continue;
+        if (d == 0 || w < win_lo) continue;
         const uint32_t slot = (w << log_nb) + (d - 1);
         if (MODE == 0) {
             atomicAdd(&count_or_cursor[slot], 1u);
@@ -276,12 +281,19 @@ static int msm_sort(ozk_ctx* ctx, const void* d_scalars, size_t n, const MsmShap
     OZK_CUDA(cudaMemsetAsync(misc + 1, 0, (kMiscWords - 1) * 4, st));
     OZK_CUDA(cudaMemsetAsync(ctx->msm[B_COUNT].p, 0, nbt * 4, st));
     const unsigned grid = (unsigned)((n + 255) / 256);
-    msm_digits<0><<<grid, 256, 0, st>>>((const uint4*)d_scalars, n, sh.c, sh.nwin, (uint32_t*)ctx->msm[B_COUNT].p, nullptr, misc);
+    // windows per launch: keep (buckets x 32-byte sectors) of one launch within ~24 MB of L2
+    uint32_t wpl = (uint32_t)std::max<size_t>(1, ((size_t)24 << 20) / ((size_t)sh.nb * 32));
+    if (const char* e = getenv("OZK_MSM_WPL")) wpl = (uint32_t)std::max(1, atoi(e));
+    uint32_t nlaunch = 0;
+    for (uint32_t w0 = 0; w0 < sh.nwin; w0 += wpl, nlaunch++)
+        msm_digits<0><<<grid, 256, 0, st>>>((const uint4*)d_scalars, n, sh.c, sh.nwin, w0, std::min(sh.nwin, w0 + wpl),
+                                            (uint32_t*)ctx->msm[B_COUNT].p, nullptr, misc);
     msm_scan<<<sh.nwin, 1024, 0, st>>>((const uint32_t*)ctx->msm[B_COUNT].p, sh.nb, (uint32_t*)ctx->msm[B_START].p,
                                        (uint32_t*)ctx->msm[B_CURSOR].p, (OvfTask*)ctx->msm[B_OVFTASK].p, misc + 1,
                                        (OvfBucket*)ctx->msm[B_OVFBUCKET].p, misc + 2, sh.ovf_task_cap, sh.ovf_bucket_cap, sh.seg);
-    msm_digits<1><<<grid, 256, 0, st>>>((const uint4*)d_scalars, n, sh.c, sh.nwin, (uint32_t*)ctx->msm[B_CURSOR].p,
-                                        (uint32_t*)ctx->msm[B_SORTED].p, misc);
+    for (uint32_t w0 = 0; w0 < sh.nwin; w0 += wpl, nlaunch++)
+        msm_digits<1><<<grid, 256, 0, st>>>((const uint4*)d_scalars, n, sh.c, sh.nwin, w0, std::min(sh.nwin, w0 + wpl),
+                                            (uint32_t*)ctx->msm[B_CURSOR].p, (uint32_t*)ctx->msm[B_SORTED].p, misc);
     {
         const unsigned og = (unsigned)((nbt + 255) / 256);
         msm_order_hist<<<og, 256, 0, st>>>((const uint32_t*)ctx->msm[B_COUNT].p, (uint32_t)nbt, misc + kMiscOhist, sh.seg);
@@ -289,7 +301,7 @@ static int msm_sort(ozk_ctx* ctx, const void* d_scalars, size_t n, const MsmShap
         msm_order_scatter<<<og, 256, 0, st>>>((const uint32_t*)ctx->msm[B_COUNT].p, (uint32_t)nbt, misc + kMiscOcursor,
                                               (uint32_t*)ctx->msm[B_ORDER].p, sh.seg);
     }
-    ctx->launches += 6;
+    ctx->launches += 4 + nlaunch;
     OZK_CUDA(cudaGetLastError());
     return OZK_OK;
 }
