@@ -113,6 +113,32 @@ OZK_API int ozk_msm_g2(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* base
 OZK_API int ozk_msm_g2_dev(ozk_ctx* ctx, const void* d_scalars, const void* d_bases, size_t n, uint8_t out[192]);
 OZK_API int ozk_msm_g1g2(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* bases1, const uint8_t* bases2, size_t n, uint8_t out[288]);
 OZK_API int ozk_msm_g1g2_dev(ozk_ctx* ctx, const void* d_scalars, const void* d_bases1, const void* d_bases2, size_t n, uint8_t out[288]);
+/* ---- persistent bases (device-resident proving key) ---------------------------------------------------------
+ * The query vectors of a Groth16 proving key (src/main/java/zk_proof_systems/zkSNARK/objects/ProvingKey.java:16-47:
+ * queryA, queryB, deltaABCG1, queryH) are the same for every proof, but the reference re-marshals and re-uploads them on
+ * every MSM (VariableBaseMSM.java:217-237; SerialProver.java:70-106 passes them to serialMSM / doubleMSM each time).
+ * ozk_bases_upload_* copies n wire-format points (host memory, or device memory for _dev) once and keeps them on the
+ * context's device in the affine Montgomery form the bucket kernels read; the _keyed MSMs then take only scalars:
+ *   out = sum_{i < n} scalars[i] * key[first + i]
+ * (`first` covers both the Java chunk loop and the subList calls of the prover.)  Results are identical to the plain
+ * entry points on the same points.  A handle belongs to the device of the context that made it; free it with
+ * ozk_bases_free before destroying that context.  SURVEY.md section 8f, row 3. */
+typedef struct ozk_bases ozk_bases;
+OZK_API int ozk_bases_upload_g1(ozk_ctx* ctx, const uint8_t* bases, size_t n, ozk_bases** out);
+OZK_API int ozk_bases_upload_g1_dev(ozk_ctx* ctx, const void* d_bases, size_t n, ozk_bases** out);
+OZK_API int ozk_bases_upload_g2(ozk_ctx* ctx, const uint8_t* bases, size_t n, ozk_bases** out);
+OZK_API int ozk_bases_upload_g2_dev(ozk_ctx* ctx, const void* d_bases, size_t n, ozk_bases** out);
+OZK_API size_t ozk_bases_len(const ozk_bases* key);
+OZK_API void ozk_bases_free(ozk_ctx* ctx, ozk_bases* key);
+OZK_API int ozk_msm_g1_keyed(ozk_ctx* ctx, const uint8_t* scalars, const ozk_bases* key, size_t first, size_t n, uint8_t out[96]);
+OZK_API int ozk_msm_g1_keyed_dev(ozk_ctx* ctx, const void* d_scalars, const ozk_bases* key, size_t first, size_t n, uint8_t out[96]);
+OZK_API int ozk_msm_g2_keyed(ozk_ctx* ctx, const uint8_t* scalars, const ozk_bases* key, size_t first, size_t n, uint8_t out[192]);
+OZK_API int ozk_msm_g2_keyed_dev(ozk_ctx* ctx, const void* d_scalars, const ozk_bases* key, size_t first, size_t n, uint8_t out[192]);
+OZK_API int ozk_msm_g1g2_keyed(ozk_ctx* ctx, const uint8_t* scalars, const ozk_bases* key1, const ozk_bases* key2, size_t first, size_t n,
+                               uint8_t out[288]);
+OZK_API int ozk_msm_g1g2_keyed_dev(ozk_ctx* ctx, const void* d_scalars, const ozk_bases* key1, const ozk_bases* key2, size_t first, size_t n,
+                                   uint8_t out[288]);
+
 /* last MSM on this context: {window bits, windows, buckets per window, overflow tasks, overflow buckets,
  * ms sort, ms convert, ms accumulate, ms merge, ms reduce+final} (device times from events on the context's stream;
  * for the paired call the per-group phases are those of the G2 half) */
@@ -135,6 +161,10 @@ OZK_API int ozk_fixed_g2_dev(ozk_ctx* ctx, const uint8_t base[192], const void* 
 /* Integer-pipe microbenchmark: independent 32x32+64 multiply-add chains on every SM; reports billions of
  * multiply-adds per second.  bench.py uses it as the measured integer roofline (MEASURED_PEAKS.json has none). */
 OZK_API int ozk_imad_peak(ozk_ctx* ctx, double* gimad_per_s);
+/* Issue-rate probes of the other pipes (billions of operations per second over all SMs): which = 1 DFMA chains,
+ * 2 DFMA chains with IMAD.WIDE chains interleaved (reports the DFMA rate; 32 wide multiply-adds ride along per 64 DFMA),
+ * 3 IADD3 carry chains, 4 32-bit IMAD chains.  Planning data for DESIGN.md section 4. */
+OZK_API int ozk_pipe_probe(ozk_ctx* ctx, int which, double* gops_per_s);
 /* Fr Montgomery multiplications per second with all operands in registers (upper bound for the field kernels). */
 OZK_API int ozk_modmul_peak(ozk_ctx* ctx, double* gmodmul_per_s);
 

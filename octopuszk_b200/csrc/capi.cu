@@ -70,6 +70,75 @@ __global__ void __launch_bounds__(256) modmul_peak_kernel(uint32_t* out, uint32_
     if (z.v[0] == 0x12345678u && x.v[3] == 7) out[0] = z.v[1];
 }
 
+// Issue-rate probes for the other pipes a 256-bit multiplier could use (planning data for mixed-pipe arithmetic):
+//   which 1: DFMA chains (fp64 pipe)   2: DFMA and IMAD.WIDE chains interleaved in the same thread
+//   which 3: IADD3 carry chains (alu)  4: 32-bit IMAD (low half only) chains
+__global__ void __launch_bounds__(256) pipe_probe_kernel(uint32_t* out, uint32_t seed, int iters, int which) {
+    using namespace ptx;
+    double d[8];
+    uint32_t lo[8], hi[8];
+    const double m = 1.0 + 1e-9 * (seed & 7);
+    uint32_t b = seed * 3 + blockIdx.x + 0x9e3779b9u;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        d[k] = 1.0 + threadIdx.x * 1e-3 + k;
+        lo[k] = threadIdx.x * 8 + k + 1;
+        hi[k] = seed + k;
+    }
+    if (which == 1) {
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+#pragma unroll
+                for (int k = 0; k < 8; k++) d[k] = fma(d[k], m, 0.5);
+        }
+    } else if (which == 2) {
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) d[k] = fma(d[k], m, 0.5);
+#pragma unroll
+                for (int k = 0; k < 8; k += 2) {
+                    uint32_t m0 = lo[k], m1 = lo[k + 1];
+                    lo[k] = mad_lo_cc(m0, b, lo[k]);
+                    hi[k] = madc_hi_cc(m0, b, hi[k]);
+                    lo[k + 1] = madc_lo_cc(m1, b, lo[k + 1]);
+                    hi[k + 1] = madc_hi(m1, b, hi[k + 1]);
+                }
+            }
+        }
+    } else if (which == 3) {
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+#pragma unroll
+                for (int k = 0; k < 8; k += 2) {
+                    lo[k] = add_cc(lo[k], hi[k + 1]);
+                    hi[k] = addc_cc(hi[k], lo[k + 1]);
+                    lo[k + 1] = addc_cc(lo[k + 1], hi[k]);
+                    hi[k + 1] = addc(hi[k + 1], lo[k]);
+                }
+            }
+        }
+    } else {
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+#pragma unroll
+                for (int k = 0; k < 8; k++) lo[k] = lo[k] * b + hi[k];
+        }
+    }
+    uint32_t s = 0;
+    double ds = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        s ^= lo[k] ^ hi[k];
+        ds += d[k];
+    }
+    if (s == 0x12345678u && ds == 3.25) out[0] = s;
+}
+
 }  // namespace ozk
 
 using namespace ozk;
@@ -176,6 +245,29 @@ int ozk_imad_peak(ozk_ctx* c, double* out) {
     OZK_TRY(time_kernel(c, imad_peak_kernel, iters, &ms));
     double ops = (double)c->sm_count * 8 * 256 * (double)iters * 64.0;
     *out = ops / (ms * 1e-3) / 1e9;
+    return OZK_OK;
+}
+
+int ozk_pipe_probe(ozk_ctx* c, int which, double* out) {
+    OZK_TRY(ctx_enter(c));
+    OZK_ARG(out != nullptr && which >= 1 && which <= 4, "ozk_pipe_probe: which must be 1..4");
+    OZK_TRY(c->io_out.reserve(256, c->stream));
+    const int iters = 2048, grid = c->sm_count * 8;
+    pipe_probe_kernel<<<grid, 256, 0, c->stream>>>((uint32_t*)c->io_out.p, 1u, 16, which);
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; rep++) {
+        OZK_CUDA(cudaEventRecord(c->ev0, c->stream));
+        pipe_probe_kernel<<<grid, 256, 0, c->stream>>>((uint32_t*)c->io_out.p, 7u + rep, iters, which);
+        OZK_CUDA(cudaEventRecord(c->ev1, c->stream));
+        OZK_CUDA(cudaEventSynchronize(c->ev1));
+        float t;
+        OZK_CUDA(cudaEventElapsedTime(&t, c->ev0, c->ev1));
+        if (t < best) best = t;
+    }
+    c->launches += 4;
+    OZK_CUDA(cudaGetLastError());
+    // operations of the probed kind per iteration and thread: 64 (which 2 counts the 64 DFMA; the 32 IMAD.WIDE pairs ride along)
+    *out = (double)c->sm_count * 8 * 256 * (double)iters * 64.0 / (best * 1e-3) / 1e9;
     return OZK_OK;
 }
 

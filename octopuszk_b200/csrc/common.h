@@ -91,6 +91,14 @@ struct ozk_ctx {
     std::map<std::string, ozk::FixedTable*> fixed_tables;
 };
 
+// Persistent device-resident bases (ozk_bases_upload_*): affine Montgomery coordinates, (0,0) for infinity.
+struct ozk_bases {
+    int group = 0;            // 1 = G1, 2 = G2
+    int device = 0;
+    size_t n = 0;
+    void* d_affine = nullptr;
+};
+
 namespace ozk {
 static constexpr int kCopyChunks = 8;      // chunks per uploaded base array (<= 2 arrays x 8 + 1 events)
 // activates ctx->device for the calling thread

@@ -15,6 +15,7 @@
 // The "...Direct" natives take java.nio direct ByteBuffers of 32-byte elements in and out (no per-element BigInteger
 // marshalling, no 64-byte padding): the Java edits that call them are in INTEGRATION.md.
 // No JVM exists in this image: the shims are exercised through a fake JNIEnv (tests/fake_jni.cc).
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -166,6 +167,56 @@ JNIEXPORT jint JNICALL Java_algebra_msm_VariableBaseMSM_variableBaseMSMDirect(
     if (!ctx) { fail(env, "variableBaseMSMDirect"); return -1; }
     int rc = type == 1 ? ozk_msm_g1(ctx, s, b1, n, o) : type == 2 ? ozk_msm_g2(ctx, s, b2, n, o) : ozk_msm_g1g2(ctx, s, b1, b2, n, o);
     if (rc != OZK_OK) { fail(env, "variableBaseMSMDirect"); return -1; }
+    return 0;
+}
+// Persistent proving-key vectors: upload a query vector once, then pass its handle.
+// type 1 = G1 (96-byte points), 2 = G2 (192-byte points).  Returns the handle (never 0), or throws and returns 0.
+// The handle lives on device taskID % deviceCount; later calls must use a taskID that maps to the same device.
+JNIEXPORT jlong JNICALL Java_algebra_msm_VariableBaseMSM_uploadBasesDirect(
+    JNIEnv* env, jclass, jobject bases, jint count, jint type, jint taskID) {
+    const size_t n = count < 0 ? 0 : (size_t)count;
+    const uint8_t* b = bases ? (const uint8_t*)env->GetDirectBufferAddress(bases) : nullptr;
+    const size_t pt = type == 1 ? 96 : 192;
+    if (count <= 0 || (type != 1 && type != 2) || !b || (size_t)env->GetDirectBufferCapacity(bases) < n * pt) {
+        fail_msg(env, "uploadBasesDirect: bases must be a direct buffer of count > 0 points, type 1 (G1) or 2 (G2)");
+        return 0;
+    }
+    ozk_ctx* ctx = context_for_task(taskID);
+    if (!ctx) { fail(env, "uploadBasesDirect"); return 0; }
+    ozk_bases* key = nullptr;
+    int rc = type == 1 ? ozk_bases_upload_g1(ctx, b, n, &key) : ozk_bases_upload_g2(ctx, b, n, &key);
+    if (rc != OZK_OK) { fail(env, "uploadBasesDirect"); return 0; }
+    return (jlong)(intptr_t)key;
+}
+
+JNIEXPORT void JNICALL Java_algebra_msm_VariableBaseMSM_freeBases(JNIEnv* env, jclass, jlong key, jint taskID) {
+    if (!key) return;
+    ozk_ctx* ctx = context_for_task(taskID);
+    if (!ctx) { fail(env, "freeBases"); return; }
+    ozk_bases_free(ctx, (ozk_bases*)(intptr_t)key);
+}
+
+// out = sum_{i < batch_size} scalars[i] * key[first + i]; type 1: key1 is a G1 handle, 2: key2 is a G2 handle, 3: both
+// (paired, out = G1 || G2).  Only the scalars cross PCIe.  Returns 0, or throws RuntimeException and returns -1.
+JNIEXPORT jint JNICALL Java_algebra_msm_VariableBaseMSM_variableBaseMSMKeyedDirect(
+    JNIEnv* env, jclass, jlong key1, jlong key2, jobject scalars, jint first, jint batch_size, jint type, jint taskID, jobject out) {
+    const size_t n = batch_size < 0 ? 0 : (size_t)batch_size;
+    const uint8_t* s = scalars ? (const uint8_t*)env->GetDirectBufferAddress(scalars) : nullptr;
+    uint8_t* o = out ? (uint8_t*)env->GetDirectBufferAddress(out) : nullptr;
+    const size_t out_need = type == 1 ? 96 : type == 2 ? 192 : 288;
+    if (batch_size < 0 || first < 0 || type < 1 || type > 3 || !o || (size_t)env->GetDirectBufferCapacity(out) < out_need ||
+        (n && (!s || (size_t)env->GetDirectBufferCapacity(scalars) < n * 32))) {
+        fail_msg(env, "variableBaseMSMKeyedDirect: buffers must be direct and hold batch_size elements");
+        return -1;
+    }
+    ozk_ctx* ctx = context_for_task(taskID);
+    if (!ctx) { fail(env, "variableBaseMSMKeyedDirect"); return -1; }
+    const ozk_bases* k1 = (const ozk_bases*)(intptr_t)key1;
+    const ozk_bases* k2 = (const ozk_bases*)(intptr_t)key2;
+    int rc = type == 1 ? ozk_msm_g1_keyed(ctx, s, k1, (size_t)first, n, o)
+           : type == 2 ? ozk_msm_g2_keyed(ctx, s, k2, (size_t)first, n, o)
+                       : ozk_msm_g1g2_keyed(ctx, s, k1, k2, (size_t)first, n, o);
+    if (rc != OZK_OK) { fail(env, "variableBaseMSMKeyedDirect"); return -1; }
     return 0;
 }
 #endif  // OZK_SHIM_VARMSM

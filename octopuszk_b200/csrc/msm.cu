@@ -244,25 +244,28 @@ struct MsmShape {
     uint32_t ovf_task_cap, ovf_bucket_cap;
 };
 
-static MsmShape msm_shape(size_t n) {
+// n_total fixes the window shape (slices of one MSM share their buckets); len is the number of pairs sorted and
+// accumulated at a time and fixes the task length and the overflow capacities.
+static MsmShape msm_shape(size_t n_total, size_t len) {
     MsmShape s;
-    s.c = choose_window(n);
+    s.c = choose_window(n_total);
     s.nwin = (255 + s.c - 1) / s.c;
     s.log_nb = s.c - 1;
     s.nb = 1u << s.log_nb;
     // task length: long enough to amortise a task, short enough that the serial chain of one task (about 2.3 us per
     // addition) does not dominate small inputs: aim for ~2^17 tasks
-    size_t want = ((size_t)s.nwin * n) >> 17;
+    size_t want = ((size_t)s.nwin * len) >> 17;
     s.seg = 32;
     while (s.seg < (uint32_t)kSegMax && s.seg * 2 <= want) s.seg *= 2;
-    size_t cap = ((size_t)s.nwin * n) / s.seg + 1;
+    size_t cap = ((size_t)s.nwin * len) / s.seg + 1;
     s.ovf_task_cap = (uint32_t)std::min<size_t>(cap, 0x7fffffffu);
     s.ovf_bucket_cap = s.ovf_task_cap;
     return s;
 }
+static MsmShape msm_shape(size_t n) { return msm_shape(n, n); }
 
 // buffers in ctx->msm[]
-enum { B_AFF1 = 0, B_AFF2, B_COUNT, B_START, B_CURSOR, B_SORTED, B_BUCKETS, B_OVFTASK, B_OVFBUCKET, B_OVFPART, B_SCRATCH, B_MISC, B_ORDER };
+enum { B_AFF1 = 0, B_AFF2, B_COUNT, B_START, B_CURSOR, B_SORTED, B_BUCKETS, B_OVFTASK, B_OVFBUCKET, B_OVFPART, B_SCRATCH, B_MISC, B_ORDER, B_BUCKETS2 };
 static constexpr int kMiscOhist = 64, kMiscOcursor = 2048, kMiscWords = 4096;   // word offsets inside B_MISC
 
 // sort phase shared by G1 / G2 / paired calls: fills start/count/sorted and the overflow lists
@@ -306,27 +309,48 @@ static int msm_sort(ozk_ctx* ctx, const void* d_scalars, size_t n, const MsmShap
     return OZK_OK;
 }
 
-// bucket phase for one group: convert bases, accumulate, reduce, final -> d_out (jac_bytes, canonical)
-static int msm_buckets(ozk_ctx* ctx, const MsmLaunch& L, const void* d_bases, size_t n, const MsmShape& sh, int aff_slot, void* d_out,
-                       bool preconverted = false) {
+// Where the bases of one group come from: the wire format (device pointer; converted to affine Montgomery form into
+// ctx->msm[aff_slot] first) or an already converted persistent array (ozk_bases_*, below).
+struct BaseSrc {
+    const void* wire = nullptr;
+    const void* affine = nullptr;
+    bool any() const { return wire || affine; }
+};
+
+// bucket phase, part 1: convert `n` bases and add them into the buckets of their digits.  resume == false starts from empty
+// buckets; resume == true adds to what earlier slices of the same MSM left there (same shape c / nwin / nb).
+static int msm_accumulate_phase(ozk_ctx* ctx, const MsmLaunch& L, const BaseSrc& src, size_t n, const MsmShape& sh, int aff_slot, int bkt_slot,
+                                bool resume) {
     cudaStream_t st = ctx->stream;
     const size_t nbt = (size_t)sh.nwin * sh.nb;
     uint32_t* misc = (uint32_t*)ctx->msm[B_MISC].p;
-    OZK_TRY(ctx->msm[aff_slot].reserve(n * L.affine_bytes, st));
-    OZK_TRY(ctx->msm[B_BUCKETS].reserve(nbt * L.xyzz_bytes, st));
+    OZK_TRY(ctx->msm[bkt_slot].reserve(nbt * L.xyzz_bytes, st));
     OZK_TRY(ctx->msm[B_OVFPART].reserve((size_t)sh.ovf_task_cap * L.xyzz_bytes, st));
     OZK_CUDA(cudaEventRecord(ctx->evs[1], st));
-    if (!preconverted && L.convert(st, d_bases, ctx->msm[aff_slot].p, n, misc, ctx->sm_count)) { set_error("msm: convert launch failed"); return OZK_ERR_CUDA; }
+    const void* aff = src.affine;
+    if (!aff) {
+        OZK_TRY(ctx->msm[aff_slot].reserve(n * L.affine_bytes, st));
+        if (L.convert(st, src.wire, ctx->msm[aff_slot].p, n, misc, ctx->sm_count)) { set_error("msm: convert launch failed"); return OZK_ERR_CUDA; }
+        aff = ctx->msm[aff_slot].p;
+        ctx->launches += 1;
+    }
     OZK_CUDA(cudaEventRecord(ctx->evs[2], st));
-    if (L.accumulate(st, ctx->msm[aff_slot].p, (const uint32_t*)ctx->msm[B_SORTED].p, (const uint32_t*)ctx->msm[B_START].p,
+    if (L.accumulate(st, aff, (const uint32_t*)ctx->msm[B_SORTED].p, (const uint32_t*)ctx->msm[B_START].p,
                      (const uint32_t*)ctx->msm[B_COUNT].p, (const OvfTask*)ctx->msm[B_OVFTASK].p, misc + 1, (const uint32_t*)ctx->msm[B_ORDER].p,
-                     (uint32_t)nbt, sh.log_nb, n, sh.seg,
-                     sh.ovf_task_cap, ctx->msm[B_BUCKETS].p, ctx->msm[B_OVFPART].p)) { set_error("msm: accumulate launch failed"); return OZK_ERR_CUDA; }
+                     (uint32_t)nbt, sh.log_nb, n, sh.seg, resume ? 1u : 0u,
+                     sh.ovf_task_cap, ctx->msm[bkt_slot].p, ctx->msm[B_OVFPART].p)) { set_error("msm: accumulate launch failed"); return OZK_ERR_CUDA; }
     OZK_CUDA(cudaEventRecord(ctx->evs[3], st));
     if (L.merge(st, (const OvfBucket*)ctx->msm[B_OVFBUCKET].p, misc + 2, std::min<uint32_t>(sh.ovf_bucket_cap, (uint32_t)nbt),
-                ctx->msm[B_OVFPART].p, ctx->msm[B_BUCKETS].p)) { set_error("msm: merge launch failed"); return OZK_ERR_CUDA; }
+                ctx->msm[B_OVFPART].p, ctx->msm[bkt_slot].p)) { set_error("msm: merge launch failed"); return OZK_ERR_CUDA; }
     OZK_CUDA(cudaEventRecord(ctx->evs[4], st));
-    ctx->launches += preconverted ? 3 : 4;
+    ctx->launches += 3;
+    OZK_CUDA(cudaGetLastError());
+    return OZK_OK;
+}
+
+// bucket phase, part 2: buckets -> window sums -> result in d_out (jac_bytes, canonical wire format)
+static int msm_reduce_phase(ozk_ctx* ctx, const MsmLaunch& L, const MsmShape& sh, int bkt_slot, void* d_out) {
+    cudaStream_t st = ctx->stream;
 
     // hierarchical reduction: one launch per level (msm_reduce_level).  Level l turns A_l (m[l] per window) into run = A_{l+1}
     // and acc_l (m[l+1] per window each) and carries acc_0 .. acc_{l-1} one summation step further.
@@ -347,7 +371,7 @@ static int msm_buckets(ozk_ctx* ctx, const MsmLaunch& L, const void* d_bases, si
     };
     FinalArgs fa;
     memset(&fa, 0, sizeof fa);
-    const void* level_in = ctx->msm[B_BUCKETS].p;
+    const void* level_in = ctx->msm[bkt_slot].p;
     const void* partial[8] = {};          // partial[k]: current (partially summed) acc array of level k
     for (uint32_t l = 0; l < nlev; l++) {
         ReduceArgs ra;
@@ -407,47 +431,66 @@ static void write_inf(uint8_t* out, size_t coord_bytes) {
     out[coord_bytes] = 1;      // (0, 1, 0)
 }
 
-static int msm_run(ozk_ctx* ctx, const void* d_scalars, const void* d_b1, const void* d_b2, size_t n, uint8_t* out) {
+// Device-resident scalars.  Large inputs are still cut into slices of kSliceLen pairs that share one set of buckets (and
+// one reduction): the sort scratch (nwin x len x 4 B) stays bounded.
+static constexpr size_t kDevSliceLen = (size_t)1 << 26;
+
+static int msm_run(ozk_ctx* ctx, const void* d_scalars, BaseSrc s1, BaseSrc s2, size_t n, uint8_t* out) {
     OZK_ARG(n > 0 && n < ((size_t)1 << 31), "msm: between 1 and 2^31 - 1 points per call");
-    const MsmShape sh = msm_shape(n);
     OZK_TRY(ctx->msm[B_MISC].reserve(kMiscWords * 4, ctx->stream));
     OZK_CUDA(cudaMemsetAsync(ctx->msm[B_MISC].p, 0, 4, ctx->stream));
     OZK_CUDA(cudaEventRecord(ctx->evs[0], ctx->stream));
+    OZK_TRY(ctx->io_out.reserve(512, ctx->stream));
+    char* d_res = (char*)ctx->io_out.p;
+    MsmShape sh = msm_shape(n, std::min(n, kDevSliceLen));
     ctx->msm_stats[0] = sh.c;
     ctx->msm_stats[1] = sh.nwin;
     ctx->msm_stats[2] = sh.nb;
-    OZK_TRY(msm_sort(ctx, d_scalars, n, sh));
-    OZK_TRY(ctx->io_out.reserve(512, ctx->stream));
-    char* d_res = (char*)ctx->io_out.p;
+    for (size_t lo = 0; lo < n; lo += kDevSliceLen) {
+        const size_t len = std::min(kDevSliceLen, n - lo);
+        sh = msm_shape(n, len);
+        OZK_TRY(msm_sort(ctx, (const char*)d_scalars + lo * 32, len, sh));
+        if (s1.any()) {
+            BaseSrc b = {s1.wire ? (const char*)s1.wire + lo * kMsmG1.jac_bytes : nullptr, s1.affine ? (const char*)s1.affine + lo * kMsmG1.affine_bytes : nullptr};
+            OZK_TRY(msm_accumulate_phase(ctx, kMsmG1, b, len, sh, B_AFF1, B_BUCKETS, lo != 0));
+        }
+        if (s2.any()) {
+            BaseSrc b = {s2.wire ? (const char*)s2.wire + lo * kMsmG2.jac_bytes : nullptr, s2.affine ? (const char*)s2.affine + lo * kMsmG2.affine_bytes : nullptr};
+            OZK_TRY(msm_accumulate_phase(ctx, kMsmG2, b, len, sh, B_AFF2, B_BUCKETS2, lo != 0));
+        }
+    }
     size_t bytes = 0;
-    if (d_b1) {
-        OZK_TRY(msm_buckets(ctx, kMsmG1, d_b1, n, sh, B_AFF1, d_res));
+    if (s1.any()) {
+        OZK_TRY(msm_reduce_phase(ctx, kMsmG1, sh, B_BUCKETS, d_res));
         bytes += 96;
     }
-    if (d_b2) {
-        OZK_TRY(msm_buckets(ctx, kMsmG2, d_b2, n, sh, B_AFF2, d_res + bytes));
+    if (s2.any()) {
+        OZK_TRY(msm_reduce_phase(ctx, kMsmG2, sh, B_BUCKETS2, d_res + bytes));
         bytes += 192;
     }
     return msm_finish(ctx, d_res, bytes, out);
 }
 
 // Host-pointer entry.  Large inputs are cut into up to kCopyChunks slices: slice k+1 crosses PCIe on a second stream
-// while slice k is sorted, normalised and accumulated, and the partial sums are added at the end.  (An MSM is a sum over
-// points, so slices are independent; this is the same partition-then-add the Java does with its 2^23-element chunks,
-// VariableBaseMSM.java:211-265, except that here it only exists to overlap the copies.)
-static int msm_run_host(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* b1, const uint8_t* b2, size_t n, uint8_t* out) {
+// while slice k is sorted, normalised and accumulated.  All slices add into the same buckets (an MSM is a sum over
+// points, so a bucket may receive its points in any grouping), so the window shape is that of the whole input and the
+// bucket reduction and the Horner tail run once.  This is the partition the Java does with its 2^23-element chunks
+// (VariableBaseMSM.java:211-265), except that here it only exists to overlap the copies.
+// Host arrays may be null when the matching BaseSrc already points at device memory (persistent bases).
+static int msm_run_host(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* b1, const uint8_t* b2, BaseSrc s1, BaseSrc s2, size_t n, uint8_t* out) {
     OZK_ARG(n > 0 && n < ((size_t)1 << 31), "msm: between 1 and 2^31 - 1 points per call");
     cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
     int nslices = 1;
-    if (n >= ((size_t)1 << 22)) nslices = 4;
-    else if (n >= ((size_t)1 << 20)) nslices = 2;
+    if (n >= ((size_t)1 << 22)) nslices = 8;
+    else if (n >= ((size_t)1 << 20)) nslices = 4;
+    else if (n >= ((size_t)1 << 18)) nslices = 2;
     if (const char* e = getenv("OZK_HOST_SLICES")) nslices = std::max(1, std::min(kCopyChunks, atoi(e)));
     const size_t slice = (n + nslices - 1) / nslices;
     OZK_TRY(ctx->io_a.reserve(n * 32, st));
     if (b1) OZK_TRY(ctx->io_b.reserve(n * 96, st));
     if (b2) OZK_TRY(ctx->io_c.reserve(n * 192, st));
     OZK_TRY(ctx->msm[B_MISC].reserve(kMiscWords * 4, st));
-    OZK_TRY(ctx->io_out.reserve(512 + (size_t)kCopyChunks * 2 * 288, st));
+    OZK_TRY(ctx->io_out.reserve(512, st));
     OZK_CUDA(cudaMemsetAsync(ctx->msm[B_MISC].p, 0, 4, st));
     OZK_CUDA(cudaEventRecord(ctx->evs[0], st));
     // the copy stream must not overtake earlier work on the main stream that still uses the staging buffers
@@ -461,36 +504,93 @@ static int msm_run_host(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* b1,
         if (b2) OZK_CUDA(cudaMemcpyAsync((char*)ctx->io_c.p + lo * 192, b2 + lo * 192, len * 192, cudaMemcpyHostToDevice, cs));
         OZK_CUDA(cudaEventRecord(ctx->copy_ev[k], cs));
     }
-    nslices = k;
-    char* d_res = (char*)ctx->io_out.p;                 // final result
-    char* d_parts1 = d_res + 512;                        // per-slice partial sums, G1 then G2
-    char* d_parts2 = d_parts1 + (size_t)kCopyChunks * 96;
+    if (b1) s1 = {ctx->io_b.p, nullptr};
+    if (b2) s2 = {ctx->io_c.p, nullptr};
+    char* d_res = (char*)ctx->io_out.p;
+    MsmShape sh = msm_shape(n, slice);
+    ctx->msm_stats[0] = sh.c;
+    ctx->msm_stats[1] = sh.nwin;
+    ctx->msm_stats[2] = sh.nb;
     k = 0;
     for (size_t lo = 0; lo < n; lo += slice, k++) {
         const size_t len = std::min(slice, n - lo);
-        const MsmShape sh = msm_shape(len);
-        if (k == 0) {
-            ctx->msm_stats[0] = sh.c;
-            ctx->msm_stats[1] = sh.nwin;
-            ctx->msm_stats[2] = sh.nb;
-        }
+        sh = msm_shape(n, len);
         OZK_CUDA(cudaStreamWaitEvent(st, ctx->copy_ev[k], 0));
         OZK_TRY(msm_sort(ctx, (char*)ctx->io_a.p + lo * 32, len, sh));
-        if (b1) OZK_TRY(msm_buckets(ctx, kMsmG1, (char*)ctx->io_b.p + lo * 96, len, sh, B_AFF1, nslices == 1 ? d_res : d_parts1 + (size_t)k * 96));
-        if (b2) OZK_TRY(msm_buckets(ctx, kMsmG2, (char*)ctx->io_c.p + lo * 192, len, sh, B_AFF2,
-                                    nslices == 1 ? d_res + (b1 ? 96 : 0) : d_parts2 + (size_t)k * 192));
+        if (s1.any()) {
+            BaseSrc b = {s1.wire ? (const char*)s1.wire + lo * kMsmG1.jac_bytes : nullptr, s1.affine ? (const char*)s1.affine + lo * kMsmG1.affine_bytes : nullptr};
+            OZK_TRY(msm_accumulate_phase(ctx, kMsmG1, b, len, sh, B_AFF1, B_BUCKETS, k != 0));
+        }
+        if (s2.any()) {
+            BaseSrc b = {s2.wire ? (const char*)s2.wire + lo * kMsmG2.jac_bytes : nullptr, s2.affine ? (const char*)s2.affine + lo * kMsmG2.affine_bytes : nullptr};
+            OZK_TRY(msm_accumulate_phase(ctx, kMsmG2, b, len, sh, B_AFF2, B_BUCKETS2, k != 0));
+        }
     }
     size_t bytes = 0;
-    if (b1) {
-        if (nslices > 1 && kMsmG1.sum_wire(st, d_parts1, (uint32_t)nslices, d_res)) { set_error("msm: sum launch failed"); return OZK_ERR_CUDA; }
+    if (s1.any()) {
+        OZK_TRY(msm_reduce_phase(ctx, kMsmG1, sh, B_BUCKETS, d_res));
         bytes += 96;
     }
-    if (b2) {
-        if (nslices > 1 && kMsmG2.sum_wire(st, d_parts2, (uint32_t)nslices, d_res + bytes)) { set_error("msm: sum launch failed"); return OZK_ERR_CUDA; }
+    if (s2.any()) {
+        OZK_TRY(msm_reduce_phase(ctx, kMsmG2, sh, B_BUCKETS2, d_res + bytes));
         bytes += 192;
     }
-    if (nslices > 1) ctx->launches += (b1 ? 1 : 0) + (b2 ? 1 : 0);
     return msm_finish(ctx, d_res, bytes, out);
+}
+
+// ---- persistent bases -------------------------------------------------------------------------------------------
+// A proving key's query vectors are the same for every proof (ProvingKey.java:16-47; SerialProver.prove reads
+// queryA/queryB/deltaABCG1/queryH, SerialProver.java:70-106), so they can be uploaded and normalised to affine
+// Montgomery form once; later MSMs then move only the scalars.
+static int bases_upload(ozk_ctx* ctx, const MsmLaunch& L, int group, const uint8_t* host, const void* dev, size_t n, ozk_bases** out) {
+    OZK_ARG(out != nullptr && n > 0 && n < ((size_t)1 << 31) && (host || dev), "ozk_bases_upload: bad argument");
+    cudaStream_t st = ctx->stream;
+    ozk_bases* kb = new ozk_bases();
+    kb->group = group;
+    kb->n = n;
+    kb->device = ctx->device;
+    if (cudaMalloc(&kb->d_affine, n * L.affine_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        delete kb;
+        set_error("ozk_bases_upload: out of device memory for %zu points", n);
+        return OZK_ERR_CUDA;
+    }
+    auto fail = [&](int rc) {
+        cudaFree(kb->d_affine);
+        delete kb;
+        return rc;
+    };
+    if (ctx->msm[B_MISC].reserve(kMiscWords * 4, st) != OZK_OK) return fail(OZK_ERR_CUDA);
+    uint32_t* misc = (uint32_t*)ctx->msm[B_MISC].p;
+    if (cudaMemsetAsync(misc, 0, 4, st) != cudaSuccess) return fail(OZK_ERR_CUDA);
+    const size_t chunk = (size_t)1 << 22;
+    if (host && ctx->io_b.reserve(std::min(n, chunk) * L.jac_bytes, st) != OZK_OK) return fail(OZK_ERR_CUDA);
+    for (size_t lo = 0; lo < n; lo += chunk) {
+        const size_t len = std::min(chunk, n - lo);
+        const void* src = dev ? (const void*)((const char*)dev + lo * L.jac_bytes) : ctx->io_b.p;
+        if (host && cudaMemcpyAsync(ctx->io_b.p, host + lo * L.jac_bytes, len * L.jac_bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) return fail(OZK_ERR_CUDA);
+        if (L.convert(st, src, (char*)kb->d_affine + lo * L.affine_bytes, len, misc, ctx->sm_count)) return fail(OZK_ERR_CUDA);
+        ctx->launches += 1;
+    }
+    uint32_t* pin = (uint32_t*)ctx->pinned;
+    if (cudaMemcpyAsync(pin, misc, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+        set_error("ozk_bases_upload: %s", cudaGetErrorString(cudaGetLastError()));
+        return fail(OZK_ERR_CUDA);
+    }
+    if (pin[0] & 1u) {
+        set_error("ozk_bases_upload: a base coordinate is not reduced mod p");
+        return fail(OZK_ERR_DOMAIN);
+    }
+    *out = kb;
+    return OZK_OK;
+}
+
+static int keyed_check(ozk_ctx* ctx, const ozk_bases* kb, int group, size_t first, size_t n) {
+    OZK_ARG(kb != nullptr, "keyed msm: null bases handle");
+    OZK_ARG(kb->group == group, "keyed msm: bases handle belongs to the other group");
+    OZK_ARG(kb->device == ctx->device, "keyed msm: bases handle lives on another device");
+    OZK_ARG(first <= kb->n && n <= kb->n - first, "keyed msm: [first, first + n) exceeds the uploaded bases");
+    return OZK_OK;
 }
 
 }  // namespace ozk
@@ -503,13 +603,13 @@ int ozk_msm_g1_dev(ozk_ctx* ctx, const void* d_scalars, const void* d_bases, siz
     OZK_TRY(ctx_enter(ctx));
     OZK_ARG(out && (n == 0 || (d_scalars && d_bases)), "ozk_msm_g1_dev: null pointer");
     if (n == 0) { write_inf(out, 32); return OZK_OK; }
-    return msm_run(ctx, d_scalars, d_bases, nullptr, n, out);
+    return msm_run(ctx, d_scalars, BaseSrc{d_bases, nullptr}, BaseSrc{}, n, out);
 }
 int ozk_msm_g2_dev(ozk_ctx* ctx, const void* d_scalars, const void* d_bases, size_t n, uint8_t out[192]) {
     OZK_TRY(ctx_enter(ctx));
     OZK_ARG(out && (n == 0 || (d_scalars && d_bases)), "ozk_msm_g2_dev: null pointer");
     if (n == 0) { write_inf(out, 64); return OZK_OK; }
-    return msm_run(ctx, d_scalars, nullptr, d_bases, n, out);
+    return msm_run(ctx, d_scalars, BaseSrc{}, BaseSrc{d_bases, nullptr}, n, out);
 }
 int ozk_msm_g1g2_dev(ozk_ctx* ctx, const void* d_scalars, const void* d_bases1, const void* d_bases2, size_t n, uint8_t out[288]) {
     OZK_TRY(ctx_enter(ctx));
@@ -519,19 +619,19 @@ int ozk_msm_g1g2_dev(ozk_ctx* ctx, const void* d_scalars, const void* d_bases1, 
         write_inf(out + 96, 64);
         return OZK_OK;
     }
-    return msm_run(ctx, d_scalars, d_bases1, d_bases2, n, out);
+    return msm_run(ctx, d_scalars, BaseSrc{d_bases1, nullptr}, BaseSrc{d_bases2, nullptr}, n, out);
 }
 int ozk_msm_g1(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* bases, size_t n, uint8_t out[96]) {
     OZK_TRY(ctx_enter(ctx));
     OZK_ARG(out && (n == 0 || (scalars && bases)), "ozk_msm_g1: null pointer");
     if (n == 0) { write_inf(out, 32); return OZK_OK; }
-    return msm_run_host(ctx, scalars, bases, nullptr, n, out);
+    return msm_run_host(ctx, scalars, bases, nullptr, BaseSrc{}, BaseSrc{}, n, out);
 }
 int ozk_msm_g2(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* bases, size_t n, uint8_t out[192]) {
     OZK_TRY(ctx_enter(ctx));
     OZK_ARG(out && (n == 0 || (scalars && bases)), "ozk_msm_g2: null pointer");
     if (n == 0) { write_inf(out, 64); return OZK_OK; }
-    return msm_run_host(ctx, scalars, nullptr, bases, n, out);
+    return msm_run_host(ctx, scalars, nullptr, bases, BaseSrc{}, BaseSrc{}, n, out);
 }
 int ozk_msm_g1g2(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* bases1, const uint8_t* bases2, size_t n, uint8_t out[288]) {
     OZK_TRY(ctx_enter(ctx));
@@ -541,7 +641,89 @@ int ozk_msm_g1g2(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* bases1, co
         write_inf(out + 96, 64);
         return OZK_OK;
     }
-    return msm_run_host(ctx, scalars, bases1, bases2, n, out);
+    return msm_run_host(ctx, scalars, bases1, bases2, BaseSrc{}, BaseSrc{}, n, out);
+}
+
+int ozk_bases_upload_g1(ozk_ctx* ctx, const uint8_t* bases, size_t n, ozk_bases** out) {
+    OZK_TRY(ctx_enter(ctx));
+    return bases_upload(ctx, kMsmG1, 1, bases, nullptr, n, out);
+}
+int ozk_bases_upload_g2(ozk_ctx* ctx, const uint8_t* bases, size_t n, ozk_bases** out) {
+    OZK_TRY(ctx_enter(ctx));
+    return bases_upload(ctx, kMsmG2, 2, bases, nullptr, n, out);
+}
+int ozk_bases_upload_g1_dev(ozk_ctx* ctx, const void* d_bases, size_t n, ozk_bases** out) {
+    OZK_TRY(ctx_enter(ctx));
+    return bases_upload(ctx, kMsmG1, 1, nullptr, d_bases, n, out);
+}
+int ozk_bases_upload_g2_dev(ozk_ctx* ctx, const void* d_bases, size_t n, ozk_bases** out) {
+    OZK_TRY(ctx_enter(ctx));
+    return bases_upload(ctx, kMsmG2, 2, nullptr, d_bases, n, out);
+}
+size_t ozk_bases_len(const ozk_bases* kb) { return kb ? kb->n : 0; }
+void ozk_bases_free(ozk_ctx* ctx, ozk_bases* kb) {
+    if (!kb) return;
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    cudaFree(kb->d_affine);
+    delete kb;
+}
+
+int ozk_msm_g1_keyed(ozk_ctx* ctx, const uint8_t* scalars, const ozk_bases* key, size_t first, size_t n, uint8_t out[96]) {
+    OZK_TRY(ctx_enter(ctx));
+    OZK_ARG(out && (n == 0 || scalars), "ozk_msm_g1_keyed: null pointer");
+    OZK_TRY(keyed_check(ctx, key, 1, first, n));
+    if (n == 0) { write_inf(out, 32); return OZK_OK; }
+    return msm_run_host(ctx, scalars, nullptr, nullptr, BaseSrc{nullptr, (const char*)key->d_affine + first * kMsmG1.affine_bytes}, BaseSrc{}, n, out);
+}
+int ozk_msm_g1_keyed_dev(ozk_ctx* ctx, const void* d_scalars, const ozk_bases* key, size_t first, size_t n, uint8_t out[96]) {
+    OZK_TRY(ctx_enter(ctx));
+    OZK_ARG(out && (n == 0 || d_scalars), "ozk_msm_g1_keyed_dev: null pointer");
+    OZK_TRY(keyed_check(ctx, key, 1, first, n));
+    if (n == 0) { write_inf(out, 32); return OZK_OK; }
+    return msm_run(ctx, d_scalars, BaseSrc{nullptr, (const char*)key->d_affine + first * kMsmG1.affine_bytes}, BaseSrc{}, n, out);
+}
+int ozk_msm_g2_keyed(ozk_ctx* ctx, const uint8_t* scalars, const ozk_bases* key, size_t first, size_t n, uint8_t out[192]) {
+    OZK_TRY(ctx_enter(ctx));
+    OZK_ARG(out && (n == 0 || scalars), "ozk_msm_g2_keyed: null pointer");
+    OZK_TRY(keyed_check(ctx, key, 2, first, n));
+    if (n == 0) { write_inf(out, 64); return OZK_OK; }
+    return msm_run_host(ctx, scalars, nullptr, nullptr, BaseSrc{}, BaseSrc{nullptr, (const char*)key->d_affine + first * kMsmG2.affine_bytes}, n, out);
+}
+int ozk_msm_g2_keyed_dev(ozk_ctx* ctx, const void* d_scalars, const ozk_bases* key, size_t first, size_t n, uint8_t out[192]) {
+    OZK_TRY(ctx_enter(ctx));
+    OZK_ARG(out && (n == 0 || d_scalars), "ozk_msm_g2_keyed_dev: null pointer");
+    OZK_TRY(keyed_check(ctx, key, 2, first, n));
+    if (n == 0) { write_inf(out, 64); return OZK_OK; }
+    return msm_run(ctx, d_scalars, BaseSrc{}, BaseSrc{nullptr, (const char*)key->d_affine + first * kMsmG2.affine_bytes}, n, out);
+}
+int ozk_msm_g1g2_keyed(ozk_ctx* ctx, const uint8_t* scalars, const ozk_bases* key1, const ozk_bases* key2, size_t first, size_t n, uint8_t out[288]) {
+    OZK_TRY(ctx_enter(ctx));
+    OZK_ARG(out && (n == 0 || scalars), "ozk_msm_g1g2_keyed: null pointer");
+    OZK_TRY(keyed_check(ctx, key1, 1, first, n));
+    OZK_TRY(keyed_check(ctx, key2, 2, first, n));
+    if (n == 0) {
+        write_inf(out, 32);
+        write_inf(out + 96, 64);
+        return OZK_OK;
+    }
+    return msm_run_host(ctx, scalars, nullptr, nullptr, BaseSrc{nullptr, (const char*)key1->d_affine + first * kMsmG1.affine_bytes},
+                        BaseSrc{nullptr, (const char*)key2->d_affine + first * kMsmG2.affine_bytes}, n, out);
+}
+int ozk_msm_g1g2_keyed_dev(ozk_ctx* ctx, const void* d_scalars, const ozk_bases* key1, const ozk_bases* key2, size_t first, size_t n, uint8_t out[288]) {
+    OZK_TRY(ctx_enter(ctx));
+    OZK_ARG(out && (n == 0 || d_scalars), "ozk_msm_g1g2_keyed_dev: null pointer");
+    OZK_TRY(keyed_check(ctx, key1, 1, first, n));
+    OZK_TRY(keyed_check(ctx, key2, 2, first, n));
+    if (n == 0) {
+        write_inf(out, 32);
+        write_inf(out + 96, 64);
+        return OZK_OK;
+    }
+    return msm_run(ctx, d_scalars, BaseSrc{nullptr, (const char*)key1->d_affine + first * kMsmG1.affine_bytes},
+                   BaseSrc{nullptr, (const char*)key2->d_affine + first * kMsmG2.affine_bytes}, n, out);
 }
 
 int ozk_msm_last_stats(ozk_ctx* ctx, double* out, int cap) {

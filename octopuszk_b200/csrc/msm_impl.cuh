@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(128) msm_accumulate(const uint4* __restrict__ 
                                                       const OvfTask* __restrict__ ovf_tasks, const uint32_t* __restrict__ ovf_count,
                                                       const uint32_t* __restrict__ order,
                                                       uint32_t nbuckets_total, uint32_t log_nb, size_t n, uint32_t seg_len,
-                                                      uint4* __restrict__ buckets, uint4* __restrict__ ovf_partial) {
+                                                      uint32_t resume, uint4* __restrict__ buckets, uint4* __restrict__ ovf_partial) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t bucket, seg;
     if (t < nbuckets_total) {
@@ -216,7 +216,8 @@ __global__ void __launch_bounds__(128) msm_accumulate(const uint4* __restrict__ 
     uint32_t lo = seg * seg_len;
     uint32_t hi = min(cnt, lo + seg_len);
     const uint32_t* run = sorted + (size_t)w * n + start[bucket];
-    XYZZ<F> acc = XYZZ<F>::inf();
+    // resume != 0: the buckets already hold the sums of earlier slices of the same MSM (host-pointer entry, msm.cu)
+    XYZZ<F> acc = (resume && t < nbuckets_total) ? load_xyzz<F>(buckets, bucket) : XYZZ<F>::inf();
     if (lo < hi) {
         uint32_t e = run[lo];
         Affine<F> p = load_affine<F>(bases, e & 0x7fffffffu);
@@ -419,7 +420,7 @@ struct MsmLaunch {
     int (*convert)(cudaStream_t, const void* in, void* out, size_t n, uint32_t* flag, int sm_count);
     int (*accumulate)(cudaStream_t, const void* bases, const uint32_t* sorted, const uint32_t* start, const uint32_t* count,
                       const OvfTask* tasks, const uint32_t* ovf_count, const uint32_t* order, uint32_t nbuckets_total, uint32_t log_nb, size_t n,
-                      uint32_t seg_len,
+                      uint32_t seg_len, uint32_t resume,
                       uint32_t ovf_cap, void* buckets, void* ovf_partial);
     int (*merge)(cudaStream_t, const OvfBucket* ob, const uint32_t* ob_count, uint32_t ob_cap, const void* ovf_partial, void* buckets);
     int (*reduce_level)(cudaStream_t, const ReduceArgs& a);
@@ -445,12 +446,12 @@ extern const MsmLaunch kMsmG2;
     }                                                                                                                          \
     static int NAME##_accumulate(cudaStream_t s, const void* bases, const uint32_t* sorted, const uint32_t* start,             \
                                  const uint32_t* count, const OvfTask* tasks, const uint32_t* ovf_count, const uint32_t* order, \
-                                 uint32_t nbt, uint32_t log_nb, size_t n, uint32_t seg_len, uint32_t ovf_cap, void* buckets,     \
-                                 void* ovf_partial) {                                                                          \
+                                 uint32_t nbt, uint32_t log_nb, size_t n, uint32_t seg_len, uint32_t resume, uint32_t ovf_cap,   \
+                                 void* buckets, void* ovf_partial) {                                                           \
         size_t total = (size_t)nbt + ovf_cap;                                                                                  \
         unsigned grid = (unsigned)((total + 127) / 128);                                                                       \
         msm_accumulate<F><<<grid, 128, 0, s>>>((const uint4*)bases, sorted, start, count, tasks, ovf_count, order, nbt, log_nb, n, seg_len, \
-                                               (uint4*)buckets, (uint4*)ovf_partial);                                          \
+                                               resume, (uint4*)buckets, (uint4*)ovf_partial);                                          \
         return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                                     \
     }                                                                                                                          \
     static int NAME##_merge(cudaStream_t s, const OvfBucket* ob, const uint32_t* ob_count, uint32_t ob_cap,                    \

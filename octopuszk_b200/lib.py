@@ -49,6 +49,7 @@ SIGNATURES = {
     "ozk_ntt_fr_ex_dev": (_int, [_vp, _vp, _vp, _sz, _c_u8p, _c_u8p, _c_u8p, _c_u8p]),
     "ozk_imad_peak": (_int, [_vp, ctypes.POINTER(ctypes.c_double)]),
     "ozk_modmul_peak": (_int, [_vp, ctypes.POINTER(ctypes.c_double)]),
+    "ozk_pipe_probe": (_int, [_vp, _int, ctypes.POINTER(ctypes.c_double)]),
     # MSM_BEGIN
     "ozk_msm_g1": (_int, [_vp, _vp, _vp, _sz, _vp]),
     "ozk_msm_g1_dev": (_int, [_vp, _vp, _vp, _sz, _vp]),
@@ -61,6 +62,18 @@ SIGNATURES = {
     "ozk_fixed_g2": (_int, [_vp, _c_u8p, _vp, _sz, _int, _int, _vp]),
     "ozk_fixed_g2_dev": (_int, [_vp, _c_u8p, _vp, _sz, _int, _int, _vp]),
     "ozk_msm_last_stats": (_int, [_vp, ctypes.POINTER(ctypes.c_double), _int]),
+    "ozk_bases_upload_g1": (_int, [_vp, _vp, _sz, ctypes.POINTER(_vp)]),
+    "ozk_bases_upload_g1_dev": (_int, [_vp, _vp, _sz, ctypes.POINTER(_vp)]),
+    "ozk_bases_upload_g2": (_int, [_vp, _vp, _sz, ctypes.POINTER(_vp)]),
+    "ozk_bases_upload_g2_dev": (_int, [_vp, _vp, _sz, ctypes.POINTER(_vp)]),
+    "ozk_bases_len": (_sz, [_vp]),
+    "ozk_bases_free": (None, [_vp, _vp]),
+    "ozk_msm_g1_keyed": (_int, [_vp, _vp, _vp, _sz, _sz, _vp]),
+    "ozk_msm_g1_keyed_dev": (_int, [_vp, _vp, _vp, _sz, _sz, _vp]),
+    "ozk_msm_g2_keyed": (_int, [_vp, _vp, _vp, _sz, _sz, _vp]),
+    "ozk_msm_g2_keyed_dev": (_int, [_vp, _vp, _vp, _sz, _sz, _vp]),
+    "ozk_msm_g1g2_keyed": (_int, [_vp, _vp, _vp, _vp, _sz, _sz, _vp]),
+    "ozk_msm_g1g2_keyed_dev": (_int, [_vp, _vp, _vp, _vp, _sz, _sz, _vp]),
     # MSM_END
 }
 
@@ -99,6 +112,27 @@ def _ptr(x):
     if isinstance(x, ctypes.Array):
         return x
     raise TypeError(type(x))
+
+
+class Bases:
+    """Persistent device-resident bases (a proving-key query vector), see ozk_bases_upload_* in include/octozk.h."""
+
+    def __init__(self, ctx: "Context", handle, group: int):
+        self.ctx, self._h, self.group = ctx, handle, group
+
+    def __len__(self) -> int:
+        return int(self.ctx.lib.ozk_bases_len(self._h)) if self._h is not None else 0
+
+    def free(self):
+        if self._h is not None and self.ctx._h is not None:
+            self.ctx.lib.ozk_bases_free(self.ctx._h, self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 class Context:
@@ -142,6 +176,11 @@ class Context:
     def imad_peak(self) -> float:
         v = ctypes.c_double()
         self._check(self.lib.ozk_imad_peak(self._h, ctypes.byref(v)))
+        return v.value
+
+    def pipe_probe(self, which: int) -> float:
+        v = ctypes.c_double()
+        self._check(self.lib.ozk_pipe_probe(self._h, which, ctypes.byref(v)))
         return v.value
 
     def modmul_peak(self) -> float:
@@ -213,6 +252,25 @@ class Context:
     def msm_g1g2_dev(self, d_scalars, d_bases1, d_bases2, n: int) -> bytes:
         out = ctypes.create_string_buffer(288)
         self._check(self.lib.ozk_msm_g1g2_dev(self._h, _ptr(d_scalars), _ptr(d_bases1), _ptr(d_bases2), n, out))
+        return out.raw
+
+    # ---- persistent bases + keyed MSM (scalars only per call)
+    def upload_bases(self, group: int, bases, n: int, device: bool = False) -> Bases:
+        fn = getattr(self.lib, f"ozk_bases_upload_g{group}" + ("_dev" if device else ""))
+        h = ctypes.c_void_p()
+        self._check(fn(self._h, _ptr(bases), n, ctypes.byref(h)))
+        return Bases(self, h, group)
+
+    def msm_keyed(self, scalars, key: Bases, n: int, first: int = 0, device: bool = False) -> bytes:
+        out = ctypes.create_string_buffer(96 if key.group == 1 else 192)
+        fn = getattr(self.lib, f"ozk_msm_g{key.group}_keyed" + ("_dev" if device else ""))
+        self._check(fn(self._h, _ptr(scalars), key._h, first, n, out))
+        return out.raw
+
+    def msm_g1g2_keyed(self, scalars, key1: Bases, key2: Bases, n: int, first: int = 0, device: bool = False) -> bytes:
+        out = ctypes.create_string_buffer(288)
+        fn = getattr(self.lib, "ozk_msm_g1g2_keyed" + ("_dev" if device else ""))
+        self._check(fn(self._h, _ptr(scalars), key1._h, key2._h, first, n, out))
         return out.raw
 
     def msm_last_stats(self):

@@ -11,7 +11,10 @@ vp, sz, i32 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int32
 SHIMS = {
     "libAlgebraMSMVariableBaseMSM.so": ["Java_algebra_msm_VariableBaseMSM_variableBaseSerialMSMNativeHelper",
                                         "Java_algebra_msm_VariableBaseMSM_variableBaseDoubleMSMNativeHelper",
-                                        "Java_algebra_msm_VariableBaseMSM_variableBaseMSMDirect"],
+                                        "Java_algebra_msm_VariableBaseMSM_variableBaseMSMDirect",
+                                        "Java_algebra_msm_VariableBaseMSM_uploadBasesDirect",
+                                        "Java_algebra_msm_VariableBaseMSM_freeBases",
+                                        "Java_algebra_msm_VariableBaseMSM_variableBaseMSMKeyedDirect"],
     "libAlgebraMSMFixedBaseMSM.so": ["Java_algebra_msm_FixedBaseMSM_batchMSMNativeHelper",
                                      "Java_algebra_msm_FixedBaseMSM_doubleBatchMSMNativeHelper",
                                      "Java_algebra_msm_FixedBaseMSM_fieldBatchMSMNativeHelper",

@@ -2,7 +2,8 @@
 (SerialzkSNARKTest.java:69-93 with R1CSConstruction.serialConstruct), every MSM and FFT on the GPU through
 octopuszk_b200/groth16.py, compared with the oracle: the witness polynomial H bit for bit, sampled proving-key elements
 and the three proof points as group elements; the proof also satisfies the Groth16 equation (checked in the exponent
-by the oracle, the toxic waste being the known seed-10 value)."""
+by the oracle, the toxic waste being the known seed-10 value) and is accepted by the oracle's pairing verifier
+(oracle/pairing_oracle.py, Verifier.java:25-59 restated)."""
 import random
 
 import pytest
@@ -58,7 +59,13 @@ def test_serial_groth16_matches_oracle(ctx, num_constraints, num_inputs):
     assert O.G1.equals(A, O.G1.mul(g1, a))
     assert O.G2.equals(B, O.G2.mul(g2, b))
     assert O.G1.equals(C, O.G1.mul(g1, c))
+    # the reference's own end-to-end assertion, Verifier.verify == true (SerialzkSNARKTest.java:63-78), by the oracle's
+    # restatement of the pairing verifier, on the proof and the keys the GPU path produced
+    from oracle import pairing_oracle as PO
+    assert PO.verify(pk["alphaG1"], pk["betaG2"], vk["gammaG2"], vk["deltaG2"], vk["gammaABCG1"], prim, (A, B, C))
     if num_constraints <= 64:
+        assert not PO.verify(pk["alphaG1"], pk["betaG2"], vk["gammaG2"], vk["deltaG2"], vk["gammaABCG1"], prim,
+                             (A, B, O.G1.add(C, g1)))
         # literal restatement of SerialSetup + SerialProver: identical proof
         _, o_pk, _ = G.setup_literal(o_cons, ni, nv)
         (oA, oB, oC), _ = G.prove_literal(o_pk, o_cons, ni, o_prim, o_aux)

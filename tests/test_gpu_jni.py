@@ -55,6 +55,27 @@ def test_variable_base_serial_and_double(jvm):
     assert rc == 0
     out = jvm.read(ob)
     assert O.G1.equals(O.unpack_g1(out[:96])[0], e1) and O.G2.equals(O.unpack_g2(out[96:])[0], e2)
+    # persistent proving-key handles: upload once, then only the scalars are passed
+    i64 = ctypes.c_int64
+    up = jvm.fn("libAlgebraMSMVariableBaseMSM.so", "Java_algebra_msm_VariableBaseMSM_uploadBasesDirect", [vp, i32, i32, i32], i64)
+    keyed = jvm.fn("libAlgebraMSMVariableBaseMSM.so", "Java_algebra_msm_VariableBaseMSM_variableBaseMSMKeyedDirect",
+                   [i64, i64, vp, i32, i32, i32, i32, vp], i32)
+    free = jvm.fn("libAlgebraMSMVariableBaseMSM.so", "Java_algebra_msm_VariableBaseMSM_freeBases", [i64, i32], None)
+    k1 = up(jvm.env, None, jvm.direct(O.pack_g1(b1)), n, 1, 0)
+    k2 = up(jvm.env, None, jvm.direct(O.pack_g2(b2)), n, 2, 0)
+    assert k1 and k2
+    ob = jvm.direct(size=288)
+    assert keyed(jvm.env, None, k1, k2, jvm.direct(O.pack_scalars(sc)), 0, n, 3, 0, ob) == 0
+    out = jvm.read(ob)
+    assert O.G1.equals(O.unpack_g1(out[:96])[0], e1) and O.G2.equals(O.unpack_g2(out[96:])[0], e2)
+    ob = jvm.direct(size=96)
+    assert keyed(jvm.env, None, k1, 0, jvm.direct(O.pack_scalars(sc[:5])), 3, 5, 1, 0, ob) == 0
+    assert O.G1.equals(O.unpack_g1(jvm.read(ob))[0], O.pippenger_msm(O.G1, sc[:5], b1[3:8]))
+    assert keyed(jvm.env, None, k1, 0, jvm.direct(O.pack_scalars(sc)), 1, n, 1, 0, ob) == -1       # range exceeds the key
+    assert "RuntimeException" in jvm.exception()
+    jvm.clear()
+    free(jvm.env, None, k1, 0)
+    free(jvm.env, None, k2, 0)
 
 
 def test_errors_become_runtime_exceptions(jvm):

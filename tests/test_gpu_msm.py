@@ -151,3 +151,97 @@ def test_device_resident_entry_point(ctx):
     out = ctx.msm_g1_dev(d_s, d_b, n)
     exp = util.expected_from_dlogs(O.G1, ks, util.column_sums(raw, 16))
     assert O.G1.equals(O.unpack_g1(out)[0], exp)
+
+
+# ---- sliced host-pointer path: all slices add into one set of buckets (msm_run_host, csrc/msm.cu) -----------------------
+@pytest.mark.parametrize("slices", [2, 3, 8])
+def test_host_slices_share_buckets(ctx, slices, monkeypatch):
+    monkeypatch.setenv("OZK_HOST_SLICES", str(slices))
+    n = 100003                                   # ragged last slice
+    ks, pool = util.known_dlog_points(O.G1, 64, seed=31, random_z=True)
+    raw = util.rand_scalars_bytes(n, seed=31)
+    bases = util.tiled_bases_bytes(O.G1, pool, n)
+    out = ctx.msm_g1(raw.tobytes(), bases.tobytes(), n)
+    exp = util.expected_from_dlogs(O.G1, ks, util.column_sums(raw, 64))
+    assert O.G1.equals(O.unpack_g1(out)[0], exp)
+
+
+def test_host_slices_paired_and_dense_buckets(ctx, monkeypatch):
+    monkeypatch.setenv("OZK_HOST_SLICES", "4")
+    # paired G1 + G2 (each group keeps its own buckets across the slices)
+    n = 1 << 15
+    k1, p1 = util.known_dlog_points(O.G1, 64, seed=32)
+    k2, p2 = util.known_dlog_points(O.G2, 64, seed=33)
+    raw = util.rand_scalars_bytes(n, seed=34)
+    out = ctx.msm_g1g2(raw.tobytes(), util.tiled_bases_bytes(O.G1, p1, n).tobytes(), util.tiled_bases_bytes(O.G2, p2, n).tobytes(), n)
+    sums = util.column_sums(raw, 64)
+    assert O.G1.equals(O.unpack_g1(out[:96])[0], util.expected_from_dlogs(O.G1, k1, sums))
+    assert O.G2.equals(O.unpack_g2(out[96:])[0], util.expected_from_dlogs(O.G2, k2, sums))
+    # the profiler's distribution through four slices: overflow tasks are merged into resumed buckets
+    n = 1 << 16
+    rng = O.JavaRandom(10)
+    g = O.G1.random(10)
+    scalars = [rng.next_long() % O.R for _ in range(n)]
+    out = ctx.msm_g1(O.pack_scalars(scalars), O.pack_g1([g]) * n, n)
+    assert O.G1.equals(O.unpack_g1(out)[0], O.G1.mul(g, sum(scalars) % O.R))
+
+
+# ---- persistent bases (ProvingKey.java query vectors stay on the device) --------------------
+def test_keyed_msm_matches_plain_and_oracle(ctx):
+    import torch
+    rng = random.Random(41)
+    n = 3000
+    ks, pool = util.known_dlog_points(O.G1, 16, seed=41, random_z=True)
+    bases = [pool[rng.randrange(16)] for _ in range(n)]
+    bases[0] = O.G1.zero()
+    bases[7] = (pool[0][0], pool[0][1], 0)
+    bases[9] = O.G1.to_affine(pool[3])
+    scalars = [rng.randrange(O.R) for _ in range(n)]
+    packed = O.pack_g1(bases)
+    key = ctx.upload_bases(1, packed, n)
+    assert len(key) == n
+    sb = O.pack_scalars(scalars)
+    plain = O.unpack_g1(ctx.msm_g1(sb, packed, n))[0]
+    got = O.unpack_g1(ctx.msm_keyed(sb, key, n))[0]
+    assert O.G1.equals(got, plain)
+    # a sub-range, as the prover's subList calls and the Java chunk loop need (VariableBaseMSM.java:211-265)
+    first, m = 1000, 777
+    got = O.unpack_g1(ctx.msm_keyed(O.pack_scalars(scalars[:m]), key, m, first=first))[0]
+    assert O.G1.equals(got, O.pippenger_msm(O.G1, scalars[:m], bases[first:first + m]))
+    # device-resident scalars, and a key built from device-resident wire-format points
+    d_s = torch.frombuffer(bytearray(sb), dtype=torch.uint8).cuda()
+    d_b = torch.frombuffer(bytearray(packed), dtype=torch.uint8).cuda()
+    key_d = ctx.upload_bases(1, d_b, n, device=True)
+    got = O.unpack_g1(ctx.msm_keyed(d_s, key_d, n, device=True))[0]
+    assert O.G1.equals(got, plain)
+    assert O.G1.is_zero(O.unpack_g1(ctx.msm_keyed(b"", key, 0))[0])
+    key.free()
+    key_d.free()
+
+
+def test_keyed_paired_and_errors(ctx):
+    from octopuszk_b200 import OzkError
+    rng = random.Random(43)
+    n = 500
+    k1, p1 = util.known_dlog_points(O.G1, 8, seed=43)
+    k2, p2 = util.known_dlog_points(O.G2, 8, seed=44)
+    b1 = [p1[i % 8] for i in range(n)]
+    b2 = [p2[i % 8] for i in range(n)]
+    scalars = [rng.randrange(O.R) for _ in range(n)]
+    key1 = ctx.upload_bases(1, O.pack_g1(b1), n)
+    key2 = ctx.upload_bases(2, O.pack_g2(b2), n)
+    sb = O.pack_scalars(scalars)
+    out = ctx.msm_g1g2_keyed(sb, key1, key2, n)
+    e1, e2 = O.double_msm(scalars, b1, b2)
+    assert O.G1.equals(O.unpack_g1(out[:96])[0], e1)
+    assert O.G2.equals(O.unpack_g2(out[96:])[0], e2)
+    assert O.G2.equals(O.unpack_g2(ctx.msm_keyed(sb, key2, n))[0], e2)
+    with pytest.raises(OzkError):
+        ctx.msm_keyed(sb, key1, n, first=1)                     # range exceeds the key
+    with pytest.raises(OzkError):
+        ctx.msm_g1g2_keyed(sb, key2, key1, n)                   # groups swapped
+    bad = [(O.P, p1[0][1], p1[0][2])]
+    with pytest.raises(OzkError):
+        ctx.upload_bases(1, b"".join(O.le32(v) for p in bad for v in p), 1)
+    key1.free()
+    key2.free()
