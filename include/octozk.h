@@ -76,6 +76,12 @@ OZK_API int ozk_fr_scale_powers_dev(ozk_ctx* ctx, const void* d_a, void* d_out, 
  * that A, B, C and H stay on the device from the first inverse FFT to the H MSM. */
 OZK_API int ozk_fr_mul_sub_dev(ozk_ctx* ctx, const void* d_a, const void* d_b, const void* d_c, void* d_out, size_t n);
 
+/* out[i] = L_i(t), the m Lagrange coefficients of the domain S = {omega^0 .. omega^(m-1)} at t (the unit vector e_i when
+ * t == omega^i): FFTAuxiliary.serialRadix2LagrangeCoefficients (src/main/java/algebra/fft/FFTAuxiliary.java:249-302), the
+ * m field inversions of R1CStoQAP.R1CStoQAPRelation (src/main/java/reductions/r1cs_to_qap/R1CStoQAP.java:54-56) in the
+ * setup.  m a power of two <= 2^28, omega a primitive m-th root of unity.  SURVEY.md section 8f row 4. */
+OZK_API int ozk_fr_lagrange_dev(ozk_ctx* ctx, void* d_out, size_t m, const uint8_t t[32], const uint8_t omega[32]);
+
 /* ---- radix-2 NTT over Fr ---------------------------------------------------------------------------------
  * out[k] = sum_j in[j] * omega^(j k), natural order in and out, n a power of two <= 2^28, omega a primitive n-th
  * root of unity.  Replaces FFTAuxiliary.serialRadix2FFT (src/main/java/algebra/fft/FFTAuxiliary.java:60-124) and the

@@ -200,6 +200,16 @@ class SerialFFT:
         self._run(input, omega=_le32(pow(self.omega, -1, FR_MODULUS)), post_scale=_le32(pow(self.domainSize, -1, FR_MODULUS)),
                   post_coset=_le32(pow(g, -1, FR_MODULUS)))
 
+    def lagrangeCoefficients(self, t: int) -> List[int]:                   # :126-128 -> FFTAuxiliary.java:249-302
+        """All Lagrange polynomials of the domain at t, on the GPU (one shared inversion per 32 coefficients in place of
+        the Java's inversion per coefficient)."""
+        import torch
+        n = self.domainSize
+        d = torch.empty(n * 32, dtype=torch.uint8, device=torch.device("cuda", self.ctx.device))
+        self.ctx.fr_lagrange_dev(d, n, _le32(t % FR_MODULUS), _le32(self.omega))
+        out = d.cpu().numpy().tobytes()
+        return [int.from_bytes(out[32 * i:32 * i + 32], "little") for i in range(n)]
+
     def computeZ(self, t: int) -> int:                                     # :139-141
         return (pow(t, self.domainSize, FR_MODULUS) - 1) % FR_MODULUS
 
@@ -214,3 +224,4 @@ class SerialFFT:
     radix2_coset_fft = radix2CosetFFT
     radix2_coset_inverse_fft = radix2CosetInverseFFT
     divide_by_z_on_coset = divideByZOnCoset
+    lagrange_coefficients = lagrangeCoefficients

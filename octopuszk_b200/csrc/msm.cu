@@ -38,16 +38,27 @@ __device__ __forceinline__ bool scalar_lt_r(const uint32_t (&s)[8]) {
 // Only windows [win_lo, win_hi) are emitted by one launch (the carries of the lower windows are still computed): the
 // scatter is launched per group of windows small enough that the live 32-byte store sectors (one per bucket cursor) stay
 // in L2, so the 4-byte scattered stores combine there instead of going to DRAM one sector at a time.
+// The atomic of the warp's first emitting lane is aggregated: every lane that hits the same (window, bucket) as that lane
+// is served by one atomicAdd of the group's size and takes consecutive positions (two ballots and a shuffle; a full
+// match.any cost 1 ms per 2^24 pairs).  With uniform scalars the group is the one lane; with skewed scalars -- the reference
+// profiler's input (VariableBaseMSMProfiling.java:27-31: half of all scalars share every high digit), 0/1-heavy witnesses,
+// a top window with one or two significant bits -- the dominant bucket of a window is in nearly every warp's first lane
+// group, which turns up to 32 same-address atomics into one and the group's stores into one coalesced run.
 template <int MODE>
 __global__ void __launch_bounds__(256) msm_digits(const uint4* __restrict__ scalars, size_t n, uint32_t c, uint32_t nwin,
                                                   uint32_t win_lo, uint32_t win_hi,
                                                   uint32_t* __restrict__ count_or_cursor, uint32_t* __restrict__ sorted,
                                                   uint32_t* flag) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint4 a = scalars[2 * i], b = scalars[2 * i + 1];
-    uint32_t s[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    if (MODE == 0 && win_lo == 0 && !scalar_lt_r(s)) atomicOr(flag, 2u);
+    const bool valid = i < n;                      // no early return: every lane takes part in the warp votes below
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (valid) {
+        uint4 a = scalars[2 * i], b = scalars[2 * i + 1];
+        s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w;
+        s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
+        if (MODE == 0 && win_lo == 0 && !scalar_lt_r(s)) atomicOr(flag, 2u);
+    }
     const uint32_t half = 1u << (c - 1);
     const uint32_t log_nb = c - 1;
     uint32_t carry = 0;
@@ -61,12 +72,24 @@ __global__ void __launch_bounds__(256) msm_digits(const uint4* __restrict__ scal
             neg = 1;
             carry = 1;
         }
-        if (d == 0 || w < win_lo) continue;
+        if (w < win_lo) continue;                  // uniform across the warp
+        const bool emit = valid && d != 0;
+        const unsigned act = __ballot_sync(0xffffffffu, emit);
+        if (act == 0) continue;
         const uint32_t slot = (w << log_nb) + (d - 1);
+        // the first emitting lane's slot is the candidate hot bucket of this warp
+        const uint32_t first = __ffs(act) - 1;
+        const uint32_t slot0 = __shfl_sync(0xffffffffu, slot, first);
+        const bool in_group = emit && slot == slot0;
+        const unsigned group = __ballot_sync(0xffffffffu, in_group);
+        uint32_t base = 0;
+        if (lane == first) base = atomicAdd(&count_or_cursor[slot0], (uint32_t)__popc(group));
+        if (MODE == 1) base = __shfl_sync(0xffffffffu, base, first);
+        if (!emit) continue;
         if (MODE == 0) {
-            atomicAdd(&count_or_cursor[slot], 1u);
+            if (!in_group) atomicAdd(&count_or_cursor[slot], 1u);
         } else {
-            const uint32_t pos = atomicAdd(&count_or_cursor[slot], 1u);
+            const uint32_t pos = in_group ? base + __popc(group & ((1u << lane) - 1u)) : atomicAdd(&count_or_cursor[slot], 1u);
             sorted[(size_t)w * n + pos] = (uint32_t)i | (neg << 31);
         }
     }
@@ -207,13 +230,15 @@ __global__ void __launch_bounds__(256) msm_order_scatter(const uint32_t* __restr
 }
 
 // ---- window choice ---------------------------------------------------------------------------------------------
-// Cost model in units of one mixed addition per (point, window), calibrated on B200 at n = 2^24 (profiles/r1_window_sweep.txt):
-//   accumulate : n * (1 + lane imbalance) + ~12 per bucket (bucket store, per-task set-up, two full additions in the reduce)
-//   sort       : 0.12 n while the live write sectors of the counting sort (one 32-byte sector per bucket cursor, all
-//                windows) stay well inside L2; 0.42 n once they do not (c >= 18 at 13-15 windows: the 4-byte scattered
-//                stores then go to DRAM sector by sector: measured 4.9 ms at c = 16, 6.7 at 17, 15.8 at 18, 10.9 at 20)
+// Cost model in units of one mixed addition per (point, window), calibrated on B200 at n = 2^24 and 2^26
+// (profiles/r1_window_sweep.txt):
+//   accumulate : n * (1 + lane imbalance) + ~11.5 per bucket (task set-up, bucket store, two full additions in the reduce)
+//   sort       : 0.13 n (measured 5.8-8.5 ms per 2^24 x 13-15 windows for c = 16..20)
 //   tail       : a fixed per-window cost
-// 2^24 and 2^26 -> c = 17 (15 windows); a sort that writes coalesced runs would move the optimum to c = 19-20.
+//   hot top    : when the top window holds only t < c - 1 significant bits of the 254-bit scalars, its 2^t buckets each
+//                receive n / 2^t points (same-address atomics in the sort, overflow tasks in accumulate); penalised
+//                when that is more than 2^15 points per bucket (c = 18, 19 at 2^24: +5 .. +7 ms measured)
+// 2^23 .. 2^25 -> c = 17 (15 windows); >= 2^26 -> c = 20 (13 windows: 170 ms against 191 ms at 2^26).
 static constexpr uint32_t kMaxWindowBits = 20;
 static uint32_t choose_window(size_t n) {
     if (const char* e = getenv("OZK_MSM_WINDOW")) {
@@ -223,13 +248,14 @@ static uint32_t choose_window(size_t n) {
     uint32_t best = 2;
     double best_cost = 1e300;
     for (uint32_t c = 2; c <= kMaxWindowBits; c++) {
-        const double nwin = (255 + c - 1) / c;
+        const uint32_t nwin_i = (255 + c - 1) / c;
+        const double nwin = nwin_i;
         const double nb = (double)(1u << (c - 1));
         const double per_bucket = (double)n / nb;
         const double imbalance = per_bucket >= 1 ? 0.5 / std::sqrt(per_bucket) : 2.0;
-        const double live_sector_bytes = nwin * nb * 32.0;
-        const double sort_pen = live_sector_bytes <= 40e6 ? 0.12 : 0.42;
-        const double cost = nwin * ((double)n * (1.0 + imbalance + sort_pen) + 12.0 * nb + 2000.0);
+        double cost = nwin * ((double)n * (1.0 + imbalance + 0.13) + 11.5 * nb + 2000.0);
+        const int top_bits = 254 - (int)((nwin_i - 1) * c);
+        if (top_bits > 0 && top_bits < (int)c - 1 && ((double)n / (double)(1u << top_bits)) > 32768.0) cost += 0.35 * (double)n;
         if (cost < best_cost) {
             best_cost = cost;
             best = c;

@@ -192,8 +192,9 @@ __global__ void __launch_bounds__(128) msm_convert_bases(const uint4* __restrict
 // task t < nbuckets_total : bucket order[t], entries [0, min(cnt, seg_len)) of its run  -> buckets[bucket]
 // task t >= nbuckets_total: overflow task (bucket, seg), entries [seg*seg_len, ...)     -> ovf_partial[t - nbuckets_total]
 // sorted[w * n + pos] = point index | sign << 31 ; start/count are per (window, bucket), start is window-local.
+// G1: four 128-thread CTAs per SM (<= 128 registers per thread); G2 needs ~240 registers and runs two.
 template <class F>
-__global__ void __launch_bounds__(128) msm_accumulate(const uint4* __restrict__ bases, const uint32_t* __restrict__ sorted,
+__global__ void __launch_bounds__(128, sizeof(F) == 32 ? 4 : 1) msm_accumulate(const uint4* __restrict__ bases, const uint32_t* __restrict__ sorted,
                                                       const uint32_t* __restrict__ start, const uint32_t* __restrict__ count,
                                                       const OvfTask* __restrict__ ovf_tasks, const uint32_t* __restrict__ ovf_count,
                                                       const uint32_t* __restrict__ order,

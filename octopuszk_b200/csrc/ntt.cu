@@ -18,6 +18,7 @@
 //
 // Inside a CTA the n_j-point transform is decimation-in-frequency, radix-8 per thread in registers (three butterfly
 // stages per shared-memory round trip); outputs are picked up in bit-reversed position by the store phase.
+#include <algorithm>
 #include <cstring>
 
 #include "common.h"
@@ -360,6 +361,67 @@ __global__ void __launch_bounds__(256) fr_mul_sub_kernel(const uint4* __restrict
     }
 }
 
+// ---- Lagrange coefficients ----------------------------------------------------------------------------------------------
+// out[i] = L_i(t) over S = {omega^0 .. omega^(m-1)} = (t^m - 1) / m * omega^i / (t - omega^i), or the unit vector when t is
+// omega^i itself: FFTAuxiliary.serialRadix2LagrangeCoefficients (src/main/java/algebra/fft/FFTAuxiliary.java:249-302),
+// which inverts (t - omega^i) one element at a time.  Here every thread takes kLagBatch consecutive indices and shares one
+// inversion among them (Montgomery's trick); hit[0] = 1, hit[1] = i when some t - omega^i is zero.
+static constexpr int kLagBatch = 32;
+
+// consts[0] = (t^m - 1) / m in Montgomery form
+__global__ void fr_lagrange_setup(Fr* consts, Fr t_canon, uint32_t log_m) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const Fr t = Fr::to_mont(t_canon);
+    Fr tm = t;
+    for (uint32_t k = 0; k < log_m; k++) tm = Fr::sqr(tm);
+    Fr mm = Fr::zero();
+    mm.v[0] = 1u << (log_m & 31);                 // m = 2^log_m <= 2^28, canonical
+    consts[0] = Fr::mul(Fr::sub(tm, Fr::one()), Fr::inv(Fr::to_mont(mm)));
+}
+
+__global__ void __launch_bounds__(128) fr_lagrange_kernel(uint4* __restrict__ out, size_t m, Fr t_canon, Fr omega_canon,
+                                                         const Fr* __restrict__ consts, uint32_t* __restrict__ hit) {
+    const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * kLagBatch;
+    if (i0 >= m) return;
+    const int cnt = (int)((m - i0) < (size_t)kLagBatch ? (m - i0) : (size_t)kLagBatch);
+    const Fr t = Fr::to_mont(t_canon), omega = Fr::to_mont(omega_canon);
+    Fr r = fr_pow(omega, (uint32_t)i0);             // omega^i0
+    Fr num[kLagBatch], prefix[kLagBatch], den[kLagBatch];
+#pragma unroll 1
+    for (int k = 0; k < cnt; k++) {
+        num[k] = r;
+        Fr d = Fr::sub(t, r);
+        if (d.is_zero()) {
+            hit[0] = 1u;
+            hit[1] = (uint32_t)(i0 + k);
+            d = Fr::one();
+        }
+        den[k] = d;
+        prefix[k] = k ? Fr::mul(prefix[k - 1], d) : d;
+        r = Fr::mul(r, omega);
+    }
+    Fr inv = Fr::inv(prefix[cnt - 1]);
+    const Fr l0 = consts[0];
+#pragma unroll 1
+    for (int k = cnt - 1; k >= 0; k--) {
+        const Fr di = k ? Fr::mul(inv, prefix[k - 1]) : inv;       // 1 / den[k]
+        inv = Fr::mul(inv, den[k]);
+        const Fr v = Fr::mul(Fr::mul(l0, num[k]), di);
+        store_fr(out + (i0 + k) * 2, Fr::from_mont(v));
+    }
+}
+
+// t is a point of S: the coefficients are the unit vector e_{hit[1]} (FFTAuxiliary.java:268-279)
+__global__ void __launch_bounds__(256) fr_lagrange_unit(uint4* __restrict__ out, size_t m, const uint32_t* __restrict__ hit) {
+    if (hit[0] == 0) return;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+        Fr v = Fr::zero();
+        if (i == hit[1]) v.v[0] = 1;
+        store_fr(out + i * 2, v);
+    }
+}
+
 // ---- small cross-shard DFT (the second step of the multi-GPU transform) ---------------------------------------------------
 // out[k1 * len + j] = sum_{i1 < G} in[i1 * len + j] * omega_G^(i1 k1), G = 2^Q <= 8: one thread per j, all G values in registers.
 template <int Q>
@@ -687,6 +749,43 @@ int ozk_fr_scale_powers_dev(ozk_ctx* ctx, const void* d_a, void* d_out, size_t n
     OZK_ARG(n == 0 || (d_a && d_out), "ozk_fr_scale_powers_dev: null pointer");
     if (n == 0) return OZK_OK;
     return scale_powers(ctx, d_a, d_out, n, scale, coset, first_index);
+}
+
+int ozk_fr_lagrange_dev(ozk_ctx* ctx, void* d_out, size_t m, const uint8_t t[32], const uint8_t omega[32]) {
+    OZK_TRY(ctx_enter(ctx));
+    OZK_ARG(d_out && t && omega, "ozk_fr_lagrange_dev: null pointer");
+    OZK_ARG(m >= 1 && m <= ((size_t)1 << 28) && (m & (m - 1)) == 0, "ozk_fr_lagrange_dev: m must be a power of two <= 2^28");
+    if (!fr_bytes_canonical(t) || !fr_bytes_canonical(omega)) {
+        set_error("ozk_fr_lagrange_dev: t or omega is not reduced mod r");
+        return OZK_ERR_DOMAIN;
+    }
+    Fr tt, ww;
+    fr_from_bytes(tt, t);
+    fr_from_bytes(ww, omega);
+    uint32_t log_m = 0;
+    while (((size_t)1 << log_m) < m) log_m++;
+    cudaStream_t st = ctx->stream;
+    OZK_TRY(ctx->io_out.reserve(512, st));
+    Fr* consts = (Fr*)ctx->io_out.p;
+    uint32_t* hit = (uint32_t*)((char*)ctx->io_out.p + 256);
+    OZK_CUDA(cudaMemsetAsync(hit, 0, 8, st));
+    // omega must generate S: omega^(m/2) == -1 (m == 1: omega == 1), checked on the device like the NTT's
+    ntt_check_omega<<<1, 32, 0, st>>>(hit + 2, ww, (uint32_t)(m / 2));
+    fr_lagrange_setup<<<1, 32, 0, st>>>(consts, tt, log_m);
+    const size_t threads = (m + kLagBatch - 1) / kLagBatch;
+    fr_lagrange_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>((uint4*)d_out, m, tt, ww, consts, hit);
+    size_t blocks = std::min<size_t>((m + 255) / 256, (size_t)ctx->sm_count * 8);
+    fr_lagrange_unit<<<(unsigned)blocks, 256, 0, st>>>((uint4*)d_out, m, hit);
+    ctx->launches += 4;
+    OZK_CUDA(cudaGetLastError());
+    uint32_t* pin = (uint32_t*)ctx->pinned;
+    OZK_CUDA(cudaMemcpyAsync(pin, hit, 12, cudaMemcpyDeviceToHost, st));
+    OZK_CUDA(cudaStreamSynchronize(st));
+    if (pin[2] != 1u) {
+        set_error("ozk_fr_lagrange_dev: omega is not a primitive m-th root of unity");
+        return OZK_ERR_DOMAIN;
+    }
+    return OZK_OK;
 }
 
 int ozk_fr_scale(ozk_ctx* ctx, const uint8_t* a, size_t n, const uint8_t b[32], uint8_t* out) {

@@ -10,7 +10,8 @@ Mirrors (reference paths under src/main/java/):
   R1CSConstruction.serialConstruct  profiler/generation/R1CSConstruction.java:31-110 (synthetic circuit)
 Every random() is Fp.random(seed 10) as in the reference's Configuration (configuration/Configuration.java:52).
 
-As in the Java, the O(n) field loops (linear-combination evaluation, Lagrange coefficients) run on the host; all group
+As in the Java, the O(n) field loops (linear-combination evaluation) run on the host; the Lagrange coefficients of the
+setup come from the GPU (ozk_fr_lagrange_dev); all group
 arithmetic and all transforms go through liboctozk.  Single scalar multiplications and additions of the Java
 (AbstractGroup.mul / add, SerialProver.java:67,106-114) are issued as tiny MSMs."""
 from __future__ import annotations
@@ -109,34 +110,11 @@ class Groth16:
             acc += val * assignment[idx]
         return acc % R
 
-    @staticmethod
-    def _lagrange(t: int, m: int) -> List[int]:
-        """FFTAuxiliary.serialRadix2LagrangeCoefficients (algebra/fft/FFTAuxiliary.java:249-302)."""
-        if m == 1:
-            return [1]
-        omega = pow(FR_ROOT, R // m, R)
-        out = [0] * m
-        if pow(t, m, R) == 1:
-            w = 1
-            for i in range(m):
-                if w == t:
-                    out[i] = 1
-                    return out
-                w = w * omega % R
-        Z = (pow(t, m, R) - 1) % R
-        l = Z * pow(m, -1, R) % R
-        r = 1
-        for i in range(m):
-            out[i] = l * pow((t - r) % R, -1, R) % R
-            l = l * omega % R
-            r = r * omega % R
-        return out
-
     def r1cs_to_qap_relation(self, cons, num_inputs, num_variables, t):
         num_constraints = len(cons)
         dom = SerialFFT(self.ctx, num_constraints + num_inputs)
         At, Bt, Ct = [0] * num_variables, [0] * num_variables, [0] * num_variables
-        lag = self._lagrange(t, dom.domainSize)
+        lag = dom.lagrangeCoefficients(t)                      # GPU (SerialFFT.lagrangeCoefficients, SerialFFT.java:126-128)
         for i in range(num_inputs):
             At[i] = lag[num_constraints + i]
         for i, (A, B, C) in enumerate(cons):

@@ -127,3 +127,48 @@ def test_ntt_ex_wrappers_match_serialfft(ctx):
     assert run(omega=O.le32(dom.omega), pre_coset=O.le32(g)) == e
     e = list(x); dom.radix2_coset_inverse_fft(e, g)
     assert run(omega=O.le32(pow(dom.omega, -1, O.R)), post_scale=O.le32(ninv), post_coset=O.le32(pow(g, -1, O.R))) == e
+
+
+@pytest.mark.parametrize("m", [1, 2, 8, 32, 64, 1000, 1 << 12])
+def test_lagrange_coefficients_match_oracle(ctx, m):
+    """ozk_fr_lagrange_dev against FFTAuxiliary.serialRadix2LagrangeCoefficients restated (FFTAuxiliary.java:249-302;
+    the reference's own test is DistributedFFTTest/SerialFFTTest "Lagrange" against naive interpolation): ordinary t, the
+    seed-10 value the setup uses, t inside the domain (unit vector), and ragged sizes of the last thread's batch."""
+    import torch
+    from octopuszk_b200 import OzkError
+    if m & (m - 1):
+        with pytest.raises(OzkError):
+            ctx.fr_lagrange_dev(torch.empty(32 * m, dtype=torch.uint8, device="cuda"), m, O.le32(5), O.le32(1))
+        return
+    omega = O.root_of_unity(m) if m > 1 else 1
+    rng = random.Random(m)
+    ts = [rng.randrange(O.R), O.fp_random(10, O.R), 0, 1]
+    if m > 2:
+        ts += [pow(omega, m - 1, O.R), pow(omega, m // 2 + 1, O.R)]
+    for t in ts:
+        d = torch.empty(32 * m, dtype=torch.uint8, device="cuda")
+        ctx.fr_lagrange_dev(d, m, O.le32(t), O.le32(omega))
+        got = d.cpu().numpy().tobytes()
+        got = [O.from_le(got[32 * i:32 * i + 32]) for i in range(m)]
+        assert got == O.serial_radix2_lagrange_coefficients(t, m, O.R, omega), (m, t)
+    if m > 2:
+        with pytest.raises(OzkError):
+            ctx.fr_lagrange_dev(torch.empty(32 * m, dtype=torch.uint8, device="cuda"), m, O.le32(5), O.le32(pow(omega, 2, O.R)))
+
+
+def test_lagrange_large_interpolates(ctx):
+    """2^20 coefficients: sum_i L_i(t) = 1 and sum_i L_i(t) omega^(i k) = t^k (interpolation of x^k), exact in Fr."""
+    import numpy as np
+    import torch
+    m = 1 << 20
+    omega = O.root_of_unity(m)
+    t = O.fp_random(10, O.R)
+    d = torch.empty(32 * m, dtype=torch.uint8, device="cuda")
+    ctx.fr_lagrange_dev(d, m, O.le32(t), O.le32(omega))
+    raw = d.cpu().numpy().reshape(m, 32)
+    from tests import util
+    assert util.column_sums(raw, 1)[0] % O.R == 1
+    # k = m / 4: omega^(i k) cycles through the four 4th roots of unity, so the sum splits into four column sums
+    w4 = pow(omega, m // 4, O.R)
+    cols = util.column_sums(raw, 4)
+    assert sum(c * pow(w4, j, O.R) for j, c in enumerate(cols)) % O.R == pow(t, m // 4, O.R)

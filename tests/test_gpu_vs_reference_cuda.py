@@ -14,10 +14,10 @@ from tests import util
 pytestmark = pytest.mark.gpu
 
 
-def _ref(name, *args):
+def _ref(name, *args, timeout=75.0):
     """The reference's CUDA runs in a child process with a time limit (it leaks, device-synchronises and exit()s)."""
     try:
-        return R.isolated(name, *args, timeout=240.0)
+        return R.isolated(name, *args, timeout=timeout)
     except TimeoutError as e:
         pytest.skip(str(e))
 
@@ -84,7 +84,8 @@ def test_fft_against_reference_cuda(ctx, log_n):
     O.serial_radix2_fft(exp, omega)
     ours = ctx.ntt(O.pack_scalars(x), O.le32(omega))
     assert [O.from_le(ours[32 * i:32 * i + 32]) for i in range(n)] == exp
-    ref = _ref('fft', O.pack_scalars(x), O.le32(omega))
+    # undefined exponents can also make its modular_power loops run for minutes: a short limit, then the run is skipped
+    ref = _ref('fft', O.pack_scalars(x), O.le32(omega), timeout=20.0)
     ref_vals = [int.from_bytes(ref[64 * i:64 * i + 64], "little") for i in range(n)]
     if ref_vals != exp:
         pytest.xfail("the reference's dormant GPU FFT kernel reads uninitialised limbs (algebra_fft_FFTAuxiliary.cu:117-119,129-131)")

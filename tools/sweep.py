@@ -1,7 +1,7 @@
 """Sweep of BASELINE.json configs[1..3] on one GPU, device-resident, CUDA-event timed (median of 5 after 2 warm-ups):
 G1 / G2 variable-base MSM, NTT, fixed-base batch MSM.  Prints one JSON line per point; used for profiles/rNN_sweep.jsonl.
 
-    python tools/sweep.py [msm|msm2|ntt|fixed|fixed2 ...]"""
+    python tools/sweep.py [msm|msm2|skew|ntt|fixed|fixed2 ...]   (OZK_SWEEP_LOGS=24,26 restricts the G1 MSM sizes)"""
 import json
 import os
 import sys
@@ -51,8 +51,45 @@ def msm_sweep(G, logs, name):
         del d_s, d_b
 
 
+def profiler_scalars(n, seed):
+    """The reference profiler's scalar distribution (VariableBaseMSMProfiling.java:27-31: Fr(random long)): a uniform
+    63-bit magnitude x, taken as x or as r - x with equal probability, as an (n, 32) uint8 array."""
+    rng = np.random.default_rng(seed)
+    x = rng.integers(0, 1 << 63, size=n, dtype=np.uint64)
+    negative = rng.integers(0, 2, size=n, dtype=np.uint8).astype(bool)
+    r = [(O.R >> (64 * k)) & ((1 << 64) - 1) for k in range(4)]
+    limbs = np.zeros((n, 4), dtype=np.uint64)
+    limbs[:, 0] = x
+    lo = (np.uint64(r[0]) - x)                                   # mod 2^64
+    borrow = (x > np.uint64(r[0])).astype(np.uint64)
+    limbs[negative, 0] = lo[negative]
+    limbs[negative, 1] = (np.uint64(r[1]) - borrow)[negative]    # r[1] != 0: the borrow stops here
+    limbs[negative, 2] = np.uint64(r[2])
+    limbs[negative, 3] = np.uint64(r[3])
+    return limbs.view(np.uint8).reshape(n, 32)
+
+
+if "skew" in what:
+    # robustness (SURVEY.md section 8d): N copies of one base, the profiler's scalars -- every high window has one bucket
+    # with N/2 points; must be correct and at least half as fast as the uniform case
+    g = O.G1.random(10)
+    for log_n in [20, 22, 24]:
+        n = 1 << log_n
+        raw = np.ascontiguousarray(profiler_scalars(n, seed=log_n))
+        d_s = torch.from_numpy(raw).cuda()
+        d_b = torch.from_numpy(np.frombuffer(O.pack_g1([O.G1.to_affine(g)]), dtype=np.uint8).copy()).cuda().repeat(n, 1).contiguous()
+        out = ctx.msm_g1_dev(d_s, d_b, n)
+        total = util.column_sums(raw, 1)[0] % O.R
+        ok = O.G1.equals(O.unpack_g1(out)[0], O.G1.mul(g, total))
+        ms = timeit(lambda: ctx.msm_g1_dev(d_s, d_b, n))
+        st = ctx.msm_last_stats()
+        print(json.dumps({"op": "varmsm_g1_profiler_distribution", "log_n": log_n, "ok": ok, "ms": ms, "Mpairs_per_s": n / ms / 1e3,
+                          "window_bits": st[0], "overflow_tasks": st[3],
+                          "phases_ms": {"sort": st[5], "convert": st[6], "accumulate": st[7], "merge": st[8], "reduce_final": st[9]}}), flush=True)
+        del d_s, d_b
+
 if "msm" in what:
-    msm_sweep(O.G1, [16, 18, 20, 22, 24, 26], "varmsm_g1")
+    msm_sweep(O.G1, [int(x) for x in os.environ.get("OZK_SWEEP_LOGS", "16,18,20,22,24,26").split(",")], "varmsm_g1")
 if "msm2" in what:
     msm_sweep(O.G2, [16, 18, 20, 22], "varmsm_g2")
 if "ntt" in what:
