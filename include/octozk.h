@@ -104,6 +104,23 @@ OZK_API int ozk_ntt_fr_ex_dev(ozk_ctx* ctx, const void* d_in, void* d_out, size_
  * groups-th root of unity.  d_in != d_out. */
 OZK_API int ozk_fr_dft_small_dev(ozk_ctx* ctx, const void* d_in, void* d_out, size_t groups, size_t len, const uint8_t omega_g[32]);
 
+/* Fused form of step 1 + twiddle + exchange of the same four-step transform: the shard-local n_local-point transform (with
+ * omega_local = omega_n^groups) whose last pass multiplies output element i by twiddle_base^i (twiddle_base = omega_n^rank)
+ * and stores it straight into the buffer of the rank that owns chunk i / (n_local / groups), at element
+ * rank * (n_local / groups) + i mod (n_local / groups).  peer_out[r] is rank r's receive buffer (n_local x 32 B) mapped into
+ * this process (ozk_peer_open; peer_out[rank] is this rank's own), so the all-to-all travels over NVLink as coalesced 128-byte
+ * stores from the epilogue of the transform instead of a separate NCCL collective and two more passes over HBM.  The caller
+ * orders the ranks (a barrier before: receive buffers free; a barrier after: all stores landed) and then runs
+ * ozk_fr_dft_small_dev on its receive buffer.  d_in is not modified. */
+OZK_API int ozk_ntt_fr_scatter_dev(ozk_ctx* ctx, const void* d_in, void* const* peer_out, size_t groups, size_t rank, size_t n_local,
+                                   const uint8_t omega_local[32], const uint8_t twiddle_base[32]);
+/* Receive buffers that other processes on the same node can map: cudaMalloc + CUDA IPC handle (64 bytes, to be sent to the
+ * peers by any means, e.g. torch.distributed.all_gather); ozk_peer_open maps a peer's buffer with peer access enabled. */
+OZK_API int ozk_peer_alloc(ozk_ctx* ctx, size_t bytes, void** d_ptr, uint8_t handle[64]);
+OZK_API int ozk_peer_open(ozk_ctx* ctx, const uint8_t handle[64], void** d_ptr);
+OZK_API int ozk_peer_close(ozk_ctx* ctx, void* d_ptr);
+OZK_API int ozk_peer_free(ozk_ctx* ctx, void* d_ptr);
+
 /* ---- variable-base MSM --------------------------------------------------------------------------------------
  * out = sum_i scalars[i] * bases[i].  Replaces VariableBaseMSM.serialMSM's native leg
  * Java_algebra_msm_VariableBaseMSM_variableBaseSerialMSMNativeHelper (algebra_msm_VariableBaseMSM.cu:1614-1695,

@@ -104,6 +104,16 @@ struct PassArgs {
     uint32_t nmid;         // last pass: number of middle passes (2..k-1) and their radices
     uint32_t logmid0, logmid1;
     uint32_t log_t;        // this pass's transform size
+    // last pass of a shard-local transform inside the multi-GPU four-step (ozk_ntt_fr_scatter_dev): element i of the output
+    // is multiplied by g^i (g = omega_n^rank, two-level table ptlo / pthi) and stored into the buffer of the rank that owns
+    // chunk i >> log_chunk, at [my_rank][i mod chunk] -- the inter-shard twiddle and the all-to-all fused into the epilogue.
+    uint32_t npeers;       // 0: plain store to `out`
+    uint32_t my_rank;
+    uint32_t log_chunk;
+    uint32_t pH;
+    const Fr* ptlo;
+    const Fr* pthi;
+    uint4* peer[8];
 };
 
 template <bool LAST>
@@ -309,7 +319,18 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_kernel(PassArgs a) {
             }
             store_fr(a.out + (out_base + ((size_t)k << a.log_inner) + c) * 2, v);
         } else {
-            store_fr(a.out + (out_base + ((size_t)k << a.log_outer) + c) * 2, v);
+            const size_t idx = out_base + ((size_t)k << a.log_outer) + c;
+            if (a.npeers) {
+                if (idx != 0 && a.my_rank != 0) {
+                    const Fr w = Fr::mul(a.ptlo[idx & ((1u << a.pH) - 1)], a.pthi[idx >> a.pH]);
+                    v = Fr::mul(v, w);
+                }
+                const uint32_t dest = (uint32_t)(idx >> a.log_chunk);
+                const size_t local = ((size_t)a.my_rank << a.log_chunk) + (idx & (((size_t)1 << a.log_chunk) - 1));
+                store_fr(a.peer[dest] + local * 2, v);       // peer memory over NVLink (or this GPU's own buffer)
+            } else {
+                store_fr(a.out + idx * 2, v);
+            }
         }
     }
 }
@@ -557,8 +578,15 @@ static int launch_pass(ozk_ctx* ctx, int log_t, const PassArgs& a, uint32_t grid
     return OZK_OK;
 }
 
-static int ntt_run(ozk_ctx* ctx, const void* d_in, void* d_out, int log_n, const uint8_t omega[32]) {
-    if (log_n == 0) {
+struct ScatterDesc {
+    uint32_t npeers = 0, my_rank = 0, log_chunk = 0, pH = 0;
+    const Fr* ptlo = nullptr;
+    const Fr* pthi = nullptr;
+    uint4* peer[8] = {};
+};
+
+static int ntt_run(ozk_ctx* ctx, const void* d_in, void* d_out, int log_n, const uint8_t omega[32], const ScatterDesc* sc = nullptr) {
+    if (log_n == 0 && !sc) {
         // n == 1: FFTAuxiliary.serialRadix2FFT returns at once whatever omega is (FFTAuxiliary.java:64-66)
         if (d_in != d_out) OZK_CUDA(cudaMemcpyAsync(d_out, d_in, 32, cudaMemcpyDeviceToDevice, ctx->stream));
         return OZK_OK;
@@ -603,6 +631,15 @@ static int ntt_run(ozk_ctx* ctx, const void* d_in, void* d_out, int log_n, const
             int lc = kTileLog - lt;
             if (lc > (int)a.log_n1) lc = a.log_n1;
             a.log_c = lc;
+            if (sc) {
+                a.npeers = sc->npeers;
+                a.my_rank = sc->my_rank;
+                a.log_chunk = sc->log_chunk;
+                a.pH = sc->pH;
+                a.ptlo = sc->ptlo;
+                a.pthi = sc->pthi;
+                for (int r = 0; r < 8; r++) a.peer[r] = sc->peer[r];
+            }
             uint32_t grid = 1u << (log_n - lt - lc);
             OZK_TRY(launch_pass<true>(ctx, lt, a, grid));
         }
@@ -749,6 +786,100 @@ int ozk_fr_scale_powers_dev(ozk_ctx* ctx, const void* d_a, void* d_out, size_t n
     OZK_ARG(n == 0 || (d_a && d_out), "ozk_fr_scale_powers_dev: null pointer");
     if (n == 0) return OZK_OK;
     return scale_powers(ctx, d_a, d_out, n, scale, coset, first_index);
+}
+
+/* ---- multi-GPU four-step, fused exchange ---------------------------------------------------------------------------------- */
+int ozk_peer_alloc(ozk_ctx* ctx, size_t bytes, void** d_ptr, uint8_t handle[64]) {
+    OZK_TRY(ctx_enter(ctx));
+    OZK_ARG(d_ptr && handle && bytes > 0, "ozk_peer_alloc: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void* p = nullptr;
+    OZK_CUDA(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        set_error("ozk_peer_alloc: cudaIpcGetMemHandle -> %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return OZK_ERR_CUDA;
+    }
+    memcpy(handle, &h, 64);
+    *d_ptr = p;
+    return OZK_OK;
+}
+int ozk_peer_open(ozk_ctx* ctx, const uint8_t handle[64], void** d_ptr) {
+    OZK_TRY(ctx_enter(ctx));
+    OZK_ARG(d_ptr && handle, "ozk_peer_open: null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    OZK_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return OZK_OK;
+}
+int ozk_peer_close(ozk_ctx* ctx, void* d_ptr) {
+    OZK_TRY(ctx_enter(ctx));
+    OZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    OZK_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return OZK_OK;
+}
+int ozk_peer_free(ozk_ctx* ctx, void* d_ptr) {
+    OZK_TRY(ctx_enter(ctx));
+    OZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    OZK_CUDA(cudaFree(d_ptr));
+    return OZK_OK;
+}
+
+int ozk_ntt_fr_scatter_dev(ozk_ctx* ctx, const void* d_in, void* const* peer_out, size_t groups, size_t rank, size_t n_local,
+                           const uint8_t omega_local[32], const uint8_t twiddle_base[32]) {
+    OZK_TRY(ctx_enter(ctx));
+    OZK_ARG(d_in && peer_out && omega_local && twiddle_base, "ozk_ntt_fr_scatter_dev: null pointer");
+    OZK_ARG(groups == 2 || groups == 4 || groups == 8, "ozk_ntt_fr_scatter_dev: groups must be 2, 4 or 8");
+    OZK_ARG(rank < groups, "ozk_ntt_fr_scatter_dev: rank out of range");
+    const int log_m = ilog2_exact(n_local);
+    OZK_ARG(log_m >= 3 && log_m <= 28, "ozk_ntt_fr_scatter_dev: n_local must be a power of two in [8, 2^28]");
+    if (!fr_bytes_canonical(twiddle_base)) {
+        set_error("ozk_ntt_fr_scatter_dev: twiddle base is not reduced mod r");
+        return OZK_ERR_DOMAIN;
+    }
+    for (size_t r = 0; r < groups; r++) OZK_ARG(peer_out[r] != nullptr, "ozk_ntt_fr_scatter_dev: null peer buffer");
+    int log_g = 0;
+    while (((size_t)1 << log_g) < groups) log_g++;
+    // two-level table of g^i, i < n_local, cached on the context like an NTT plan (key: 't' + g + log_m)
+    std::string key("t");
+    key.append((const char*)twiddle_base, 32);
+    key.push_back((char)log_m);
+    NttPlan* tw = nullptr;
+    auto it = ctx->ntt_plans.find(key);
+    if (it != ctx->ntt_plans.end()) {
+        tw = it->second;
+    } else {
+        tw = new NttPlan();
+        tw->log_n = log_m;
+        tw->H = (log_m + 1) / 2;
+        const size_t nlo = (size_t)1 << tw->H, nhi = (size_t)1 << (log_m - tw->H);
+        if (cudaMalloc(&tw->block, (nlo + nhi) * sizeof(Fr)) != cudaSuccess) {
+            delete tw;
+            set_error("ozk_ntt_fr_scatter_dev: out of device memory");
+            cudaGetLastError();
+            return OZK_ERR_CUDA;
+        }
+        tw->tlo = (Fr*)tw->block;
+        tw->thi = tw->tlo + nlo;
+        Fr g;
+        fr_from_bytes(g, twiddle_base);
+        ntt_gen_table<<<(unsigned)((nlo + 127) / 128), 128, 0, ctx->stream>>>(tw->tlo, (uint32_t)nlo, 1u, g);
+        ntt_gen_table<<<(unsigned)((nhi + 127) / 128), 128, 0, ctx->stream>>>(tw->thi, (uint32_t)nhi, 1u << tw->H, g);
+        ctx->launches += 2;
+        ctx->ntt_plans[key] = tw;
+    }
+    ScatterDesc sc;
+    sc.npeers = (uint32_t)groups;
+    sc.my_rank = (uint32_t)rank;
+    sc.log_chunk = (uint32_t)(log_m - log_g);
+    sc.pH = (uint32_t)tw->H;
+    sc.ptlo = tw->tlo;
+    sc.pthi = tw->thi;
+    for (size_t r = 0; r < groups; r++) sc.peer[r] = (uint4*)peer_out[r];
+    return ntt_run(ctx, d_in, nullptr, log_m, omega_local, &sc);
 }
 
 int ozk_fr_lagrange_dev(ozk_ctx* ctx, void* d_out, size_t m, const uint8_t t[32], const uint8_t omega[32]) {

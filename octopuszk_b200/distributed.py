@@ -13,6 +13,10 @@ Replaces the reference's Spark distribution:
          step 2 : G-point transform across the received chunks with omega^M
          output : rank d holds X[k1 * M + d * M/G + t] at [k1][t]           (G chunks of M/G, k1-major)
        `ntt_gather_natural` turns the distributed output into the natural-order vector for checks.
+       With a `PeerExchange` (receive buffers of all ranks mapped into every process over CUDA IPC) step 1, the twiddle
+       and the exchange are ONE kernel sequence: the last pass of the local transform multiplies by omega^(d * k2) and
+       stores every element straight into the owning rank's receive buffer over NVLink (ozk_ntt_fr_scatter_dev); the
+       NCCL all_to_all and the separate twiddle pass disappear, only two tiny stream-ordered barriers remain.
 
 The local compute is behind a small `ops` object so the index logic and the collectives can be exercised on CPU with
 the gloo backend (tests/test_distributed_cpu.py plugs the oracle in there); `GpuOps` is the product path."""
@@ -45,6 +49,9 @@ class GpuOps:
 
     def scale_powers(self, x, n, coset):
         self.ctx.fr_scale_powers_dev(x, x, n, None, _le32(coset), 0)
+
+    def ntt_scatter(self, x, peer_ptrs, rank, n_local, omega_local, twiddle_base):
+        self.ctx.ntt_scatter_dev(x, peer_ptrs, rank, n_local, _le32(omega_local), _le32(twiddle_base))
 
     def dft_small(self, x, out, groups, length, omega_g):
         self.ctx.fr_dft_small_dev(x, out, groups, length, _le32(omega_g))
@@ -84,9 +91,43 @@ def msm_distributed(ops, scalars_local, bases_local, n_local: int, g2: bool = Fa
     return fn(ops.to_device(bytes(ones)), gathered, world)
 
 
-def ntt_distributed(ops, x_local, n: int, omega: int, group=None):
+class PeerExchange:
+    """The receive buffers of all ranks of one node, mapped into this process (cudaMalloc + CUDA IPC through
+    ozk_peer_alloc / ozk_peer_open), for the fused exchange of `ntt_distributed`.  One instance serves transforms of up
+    to `nbytes` bytes per rank; the torch current stream must be the context's stream (Context(stream=...)), so that the
+    NCCL barriers below order the kernels of all ranks on the device, without host synchronisation."""
+
+    def __init__(self, ctx, nbytes: int, group=None):
+        self.ctx, self.group, self.nbytes = ctx, group, nbytes
+        self.world, self.rank = _world(group), _rank(group)
+        dev = torch.device("cuda", ctx.device)
+        self.ptr, handle = ctx.peer_alloc(nbytes)
+        mine = torch.frombuffer(bytearray(handle), dtype=torch.uint8).to(dev)
+        allh = torch.empty(self.world * 64, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, mine, group=group)
+        hs = allh.cpu().numpy().tobytes()
+        self.peers = [self.ptr if r == self.rank else ctx.peer_open(hs[64 * r:64 * r + 64]) for r in range(self.world)]
+        self._token = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def barrier(self):
+        """Stream-ordered barrier over the ranks: every kernel enqueued before it, on every rank, completes before any
+        kernel enqueued after it starts (a 4-byte all_reduce on the current stream)."""
+        dist.all_reduce(self._token, group=self.group)
+
+    def close(self):
+        self.barrier()
+        torch.cuda.synchronize()
+        for r, p in enumerate(self.peers):
+            if r != self.rank:
+                self.ctx.peer_close(p)
+        self.ctx.peer_free(self.ptr)
+        self.peers = []
+
+
+def ntt_distributed(ops, x_local, n: int, omega: int, group=None, exchange: Optional[PeerExchange] = None):
     """Forward transform of a length-n vector sharded cyclically over the ranks (see the module docstring for layouts).
-    x_local: uint8 tensor of M * 32 bytes, overwritten.  Returns a uint8 tensor of the same size laid out [k1][t]."""
+    x_local: uint8 tensor of M * 32 bytes (overwritten by the NCCL form, preserved by the fused form).  Returns a uint8
+    tensor of the same size laid out [k1][t]."""
     world = _world(group)
     rank = _rank(group)
     assert n % world == 0 and world in (1, 2, 4, 8)
@@ -96,6 +137,14 @@ def ntt_distributed(ops, x_local, n: int, omega: int, group=None):
         ops.ntt(x_local, n, omega)
         return x_local
     assert m % world == 0
+    if exchange is not None:
+        assert exchange.nbytes >= m * 32 and exchange.world == world
+        exchange.barrier()                                                   # every rank's receive buffer is free again
+        ops.ntt_scatter(x_local, exchange.peers, rank, m, pow(omega, world, FR_MODULUS), pow(omega, rank, FR_MODULUS))
+        exchange.barrier()                                                   # all remote stores have landed
+        out = ops.empty_like(x_local)
+        ops.dft_small(exchange.ptr, out, world, m // world, pow(omega, m, FR_MODULUS))   # step 2
+        return out
     ops.ntt(x_local, m, pow(omega, world, FR_MODULUS))                       # step 1
     ops.scale_powers(x_local, m, pow(omega, rank, FR_MODULUS))               # twiddle omega^(d * k2)
     recv = ops.empty_like(x_local)

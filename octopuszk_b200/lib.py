@@ -44,6 +44,11 @@ SIGNATURES = {
     "ozk_fr_scale_powers_dev": (_int, [_vp, _vp, _vp, _sz, _c_u8p, _c_u8p, ctypes.c_uint64]),
     "ozk_fr_mul_sub_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _sz]),
     "ozk_fr_lagrange_dev": (_int, [_vp, _vp, _sz, _c_u8p, _c_u8p]),
+    "ozk_ntt_fr_scatter_dev": (_int, [_vp, _vp, ctypes.POINTER(_vp), _sz, _sz, _sz, _c_u8p, _c_u8p]),
+    "ozk_peer_alloc": (_int, [_vp, _sz, ctypes.POINTER(_vp), ctypes.c_char_p]),
+    "ozk_peer_open": (_int, [_vp, ctypes.c_char_p, ctypes.POINTER(_vp)]),
+    "ozk_peer_close": (_int, [_vp, _vp]),
+    "ozk_peer_free": (_int, [_vp, _vp]),
     "ozk_fr_dft_small_dev": (_int, [_vp, _vp, _vp, _sz, _sz, _c_u8p]),
     "ozk_ntt_fr": (_int, [_vp, _vp, _sz, _c_u8p]),
     "ozk_ntt_fr_dev": (_int, [_vp, _vp, _vp, _sz, _c_u8p]),
@@ -207,6 +212,28 @@ class Context:
 
     def fr_lagrange_dev(self, d_out, m: int, t: bytes, omega: bytes):
         self._check(self.lib.ozk_fr_lagrange_dev(self._h, _ptr(d_out), m, t, omega))
+
+    def ntt_scatter_dev(self, d_in, peer_ptrs, rank: int, n_local: int, omega_local: bytes, twiddle_base: bytes):
+        arr = (ctypes.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        self._check(self.lib.ozk_ntt_fr_scatter_dev(self._h, _ptr(d_in), arr, len(peer_ptrs), rank, n_local, omega_local, twiddle_base))
+
+    def peer_alloc(self, nbytes: int):
+        """(device pointer, 64-byte IPC handle) of a fresh cudaMalloc block other processes can map."""
+        p = ctypes.c_void_p()
+        h = ctypes.create_string_buffer(64)
+        self._check(self.lib.ozk_peer_alloc(self._h, nbytes, ctypes.byref(p), h))
+        return int(p.value), h.raw
+
+    def peer_open(self, handle: bytes) -> int:
+        p = ctypes.c_void_p()
+        self._check(self.lib.ozk_peer_open(self._h, handle, ctypes.byref(p)))
+        return int(p.value)
+
+    def peer_close(self, ptr: int):
+        self._check(self.lib.ozk_peer_close(self._h, ctypes.c_void_p(ptr)))
+
+    def peer_free(self, ptr: int):
+        self._check(self.lib.ozk_peer_free(self._h, ctypes.c_void_p(ptr)))
 
     def fr_dft_small_dev(self, d_in, d_out, groups: int, length: int, omega_g: bytes):
         self._check(self.lib.ozk_fr_dft_small_dev(self._h, _ptr(d_in), _ptr(d_out), groups, length, omega_g))

@@ -1,6 +1,8 @@
 """Multi-GPU NTT (BASELINE.json configs[2], "four-step all-to-all beyond one GPU"): one length-n transform sharded over
-the ranks of a torchrun job with octopuszk_b200.distributed.ntt_distributed (local M-point transforms, twiddle, ONE
-all_to_all, G-point cross-shard transform).  Device-resident, CUDA events, max over ranks.
+the ranks of a torchrun job with octopuszk_b200.distributed.ntt_distributed, in both forms: "nccl" (local M-point transforms,
+twiddle pass, ONE all_to_all, G-point cross-shard transform) and "fused" (the last pass of the local transform applies the
+twiddle and stores into the peers' receive buffers over NVLink; no collective on the data path).  Device-resident, CUDA
+events, max over ranks.
 
     torchrun --nproc-per-node N tools/ntt_multi_bench.py [log_n ...]"""
 import json
@@ -45,25 +47,35 @@ for log_n in [int(a) for a in sys.argv[1:]] or [26, 28]:
         k = rank * c + 5
         got = O.from_le(out[32 * 5:32 * 6].cpu().numpy().tobytes())
         assert got == pow(omega, j * k, O.R), "distributed NTT delta response mismatch"
-    ts = []
-    for it in range(5):
-        if world > 1:
-            dist.barrier()
+    ex = D.PeerExchange(ctx, m * 32) if world > 1 else None
+    if ex is not None and log_n <= 26:
+        a1 = D.ntt_distributed(ops, x, n, omega, exchange=ex)
+        a2 = D.ntt_distributed(ops, x.clone(), n, omega)
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        out = D.ntt_distributed(ops, x, n, omega)
-        e1.record()
-        torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        if it >= 2:
-            ts.append(float(t.item()))
-    if rank == 0:
-        ms = sorted(ts)[len(ts) // 2]
-        print(json.dumps({"op": "ntt_fr_distributed", "log_n": log_n, "n_gpus": world, "ms": ms,
-                          "exchange_bytes_per_gpu": (m * 32) * (world - 1) // world}), flush=True)
+        assert torch.equal(a1, a2), "fused and NCCL forms disagree"
+        del a1, a2
+    for form in (["nccl", "fused"] if world > 1 else ["single"]):
+        ts = []
+        for it in range(6):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = D.ntt_distributed(ops, x, n, omega, exchange=ex if form == "fused" else None)
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if it >= 2:
+                ts.append(float(t.item()))
+        if rank == 0:
+            ms = sorted(ts)[len(ts) // 2]
+            print(json.dumps({"op": "ntt_fr_distributed", "form": form, "log_n": log_n, "n_gpus": world, "ms": ms,
+                              "exchange_bytes_per_gpu": (m * 32) * (world - 1) // world}), flush=True)
+    if ex is not None:
+        ex.close()
     del x, out
 if world > 1:
     dist.destroy_process_group()
