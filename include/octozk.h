@@ -114,6 +114,14 @@ OZK_API int ozk_fr_dft_small_dev(ozk_ctx* ctx, const void* d_in, void* d_out, si
  * ozk_fr_dft_small_dev on its receive buffer.  d_in is not modified. */
 OZK_API int ozk_ntt_fr_scatter_dev(ozk_ctx* ctx, const void* d_in, void* const* peer_out, size_t groups, size_t rank, size_t n_local,
                                    const uint8_t omega_local[32], const uint8_t twiddle_base[32]);
+/* The mirrored transform, for data that is already in the output layout of the one above (rank d holds x[a * M + d * len + t],
+ * a < groups, t < len = M / groups, as [a][t]): groups-point transforms over a (omega_g = omega_n^M), twiddle
+ * omega_n^((d len + t) k1), and result k1 stored straight into rank k1's buffer at element d * len + t.  After a barrier every
+ * rank runs the plain M-point transform (omega_n^groups) on its receive buffer and holds X[rank + groups * k2]: the cyclic
+ * layout again.  The two forms alternate through the prover's transform chain (inverse, coset forward, ..., R1CStoQAP.java:
+ * 165-227) so no re-layout is ever needed.  The omega_n table is validated only through omega_g = omega_n^M by the caller. */
+OZK_API int ozk_fr_dft_small_scatter_dev(ozk_ctx* ctx, const void* d_in, void* const* peer_out, size_t groups, size_t rank, size_t len,
+                                         const uint8_t omega_g[32], const uint8_t omega_n[32]);
 /* Receive buffers that other processes on the same node can map: cudaMalloc + CUDA IPC handle (64 bytes, to be sent to the
  * peers by any means, e.g. torch.distributed.all_gather); ozk_peer_open maps a peer's buffer with peer access enabled. */
 OZK_API int ozk_peer_alloc(ozk_ctx* ctx, size_t bytes, void** d_ptr, uint8_t handle[64]);

@@ -19,6 +19,7 @@
 // Inside a CTA the n_j-point transform is decimation-in-frequency, radix-8 per thread in registers (three butterfly
 // stages per shared-memory round trip); outputs are picked up in bit-reversed position by the store phase.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.h"
@@ -27,7 +28,20 @@
 namespace ozk {
 
 static constexpr int kMaxLogT = 9;          // largest in-CTA transform: 512 points
-static constexpr int kTileLog = 11;         // 2048 elements (64 KB) per CTA tile
+// Tile of 1024 elements (32 KB) per 128-thread CTA: four CTAs per SM whose load / transform / store phases interleave
+// (measured 2^26: 16.3 ms with 2048-element tiles and two CTAs per SM, 15.9 ms with 1024).
+static constexpr int kTileLogDefault = 10;
+// Largest inter-pass twiddle range that gets a direct table: 2^26 entries = 2 GiB per (n, omega) plan.  HBM is < 10 % busy in
+// these passes, so one more 32-byte read per element is free, and it replaces the product of two table entries (one of the
+// ~13.4 multiplications per element at 2^26: 15.9 -> 15.0 ms).  Larger ranges fall back to the two-level table.
+static constexpr int kDirectLogDefault = 26;
+static int env_int(const char* name, int dflt, int lo, int hi) {
+    if (const char* e = getenv(name)) {
+        int v = atoi(e);
+        if (v >= lo && v <= hi) return v;
+    }
+    return dflt;
+}
 static constexpr int kMaxPasses = 4;
 
 struct NttPlan {
@@ -67,11 +81,20 @@ __device__ Fr fr_pow(Fr base, uint32_t e) {
 
 // ---- twiddle tables ------------------------------------------------------------------------------------------
 // table[i] = omega^(i * step) in Montgomery form; `omega_canon` is the canonical 32-byte value from the caller.
+// A thread fills kGenRun consecutive entries: one exponentiation, then one multiplication per entry (the direct inter-pass
+// tables have up to 2^26 entries).
+static constexpr uint32_t kGenRun = 16;
 __global__ void ntt_gen_table(Fr* table, uint32_t count, uint32_t step, Fr omega_canon) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    Fr w = Fr::to_mont(omega_canon);
-    table[i] = fr_pow(w, i * step);
+    const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * kGenRun;
+    if (i0 >= count) return;
+    const Fr w = Fr::to_mont(omega_canon);
+    const Fr ws = fr_pow(w, step);
+    Fr v = fr_pow(ws, i0);
+    const uint32_t end = min(count, i0 + kGenRun);
+    for (uint32_t i = i0; i < end; i++) {
+        table[i] = v;
+        v = Fr::mul(v, ws);
+    }
 }
 
 // flag[0] = 1 when omega is canonical and omega^(n/2) == -1 (i.e. omega is a primitive n-th root of unity)
@@ -278,7 +301,8 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_kernel(PassArgs a) {
     }
     __syncthreads();
 
-    // ---- DIF stages from half-size T/2 down to 1: (LOGT mod 3) single stages first, then radix-8 steps.
+    // ---- DIF stages from half-size T/2 down to 1: (LOGT mod 3) single stages first, then radix-8 steps.  (Merging two leftover
+    // stages into one radix-4 step was measured slower: 15.7 against 15.0 ms at 2^26.)
     {
         uint32_t log_m = LOGT;
         uint32_t r0 = LOGT % 3;
@@ -461,6 +485,34 @@ __global__ void __launch_bounds__(256) fr_dft_small_kernel(const uint4* __restri
     }
 }
 
+// The mirrored first step of the multi-GPU transform (ozk_fr_dft_small_scatter_dev): this rank holds x[a * M + i2] for all
+// a < G and its own block of i2 (len values starting at rank * len).  One thread per i2: the G-point transform over a, the
+// twiddle omega_n^(i2 * k1) (two-level table), and the store of result k1 straight into rank k1's buffer at position i2,
+// so every rank ends up with a full natural-order M-vector: the exchange is the epilogue of this kernel.
+struct PeerPtrs {
+    uint4* p[8];
+};
+template <int Q>
+__global__ void __launch_bounds__(256) fr_dft_small_scatter_kernel(const uint4* __restrict__ in, size_t len, const Fr* __restrict__ wtab,
+                                                                   const Fr* __restrict__ tlo, const Fr* __restrict__ thi, uint32_t H,
+                                                                   uint32_t rank, PeerPtrs peers) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= len) return;
+    Fr x[1 << Q];
+#pragma unroll
+    for (int u = 0; u < (1 << Q); u++) x[u] = load_fr(in + ((size_t)u * len + j) * 2);
+    dif_step<Q, true>(x, wtab, 0, 0, Q);
+    const size_t i2 = (size_t)rank * len + j;
+#pragma unroll
+    for (int u = 0; u < (1 << Q); u++) {
+        const uint32_t k1 = __brev((uint32_t)u) >> (32 - Q);
+        Fr v = x[u];
+        const uint32_t e = (uint32_t)i2 * k1;            // < n <= 2^28
+        if (e != 0) v = Fr::mul(v, Fr::mul(tlo[e & ((1u << H) - 1)], thi[e >> H]));
+        store_fr(peers.p[k1] + i2 * 2, v);
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------
 static void fr_from_bytes(Fr& f, const uint8_t* b) { memcpy(f.v, b, 32); }
 
@@ -521,7 +573,7 @@ static int ntt_get_plan(ozk_ctx* ctx, int log_n, const uint8_t omega[32], NttPla
         int log_outer = 0;
         for (int j = 0; j + 1 < p->npass; j++) {
             const int range_log = log_n - log_outer;
-            if (range_log <= 20) {
+            if (range_log <= env_int("OZK_NTT_DIRECT_LOG", kDirectLogDefault, 0, 27)) {
                 off_dir[j] = count;
                 dir_log[j] = range_log;
                 count += (size_t)1 << range_log;
@@ -534,15 +586,15 @@ static int ntt_get_plan(ozk_ctx* ctx, int log_n, const uint8_t omega[32], NttPla
     for (int j = 0; j < p->npass; j++) {
         p->wsub[j] = base + off_w[j];
         uint32_t cnt = p->logt[j] ? 1u << (p->logt[j] - 1) : 1u;
-        ntt_gen_table<<<(cnt + 127) / 128, 128, 0, ctx->stream>>>(p->wsub[j], cnt, 1u << (log_n - p->logt[j]), om);
+        ntt_gen_table<<<(cnt / kGenRun + 128) / 128, 128, 0, ctx->stream>>>(p->wsub[j], cnt, 1u << (log_n - p->logt[j]), om);
     }
     p->tlo = base + off_lo;
     p->thi = base + off_hi;
     {
         uint32_t cnt = 1u << p->H;
-        ntt_gen_table<<<(cnt + 127) / 128, 128, 0, ctx->stream>>>(p->tlo, cnt, 1u, om);
+        ntt_gen_table<<<(cnt / kGenRun + 128) / 128, 128, 0, ctx->stream>>>(p->tlo, cnt, 1u, om);
         cnt = 1u << (log_n - p->H);
-        ntt_gen_table<<<(cnt + 127) / 128, 128, 0, ctx->stream>>>(p->thi, cnt, 1u << p->H, om);
+        ntt_gen_table<<<(cnt / kGenRun + 128) / 128, 128, 0, ctx->stream>>>(p->thi, cnt, 1u << p->H, om);
     }
     {
         int log_outer = 0;
@@ -550,7 +602,7 @@ static int ntt_get_plan(ozk_ctx* ctx, int log_n, const uint8_t omega[32], NttPla
             if (dir_log[j]) {
                 p->tdir[j] = base + off_dir[j];
                 uint32_t cnt = 1u << dir_log[j];
-                ntt_gen_table<<<(cnt + 127) / 128, 128, 0, ctx->stream>>>(p->tdir[j], cnt, 1u << log_outer, om);
+                ntt_gen_table<<<(cnt / kGenRun + 128) / 128, 128, 0, ctx->stream>>>(p->tdir[j], cnt, 1u << log_outer, om);
             }
             log_outer += p->logt[j];
         }
@@ -618,7 +670,7 @@ static int ntt_run(ozk_ctx* ctx, const void* d_in, void* d_out, int log_n, const
         a.log_outer = log_n - lt - log_inner;
         a.log_t = lt;
         if (!last) {
-            int lc = kTileLog - lt;
+            int lc = env_int("OZK_NTT_TILE_LOG", kTileLogDefault, 9, 11) - lt;
             if (lc > log_inner) lc = log_inner;
             a.log_c = lc;
             uint32_t grid = 1u << (log_n - lt - lc);
@@ -628,7 +680,7 @@ static int ntt_run(ozk_ctx* ctx, const void* d_in, void* d_out, int log_n, const
             a.nmid = p->npass > 2 ? p->npass - 2 : 0;
             a.logmid0 = a.nmid > 0 ? p->logt[1] : 0;
             a.logmid1 = a.nmid > 1 ? p->logt[2] : 0;
-            int lc = kTileLog - lt;
+            int lc = env_int("OZK_NTT_TILE_LOG", kTileLogDefault, 9, 11) - lt;
             if (lc > (int)a.log_n1) lc = a.log_n1;
             a.log_c = lc;
             if (sc) {
@@ -664,6 +716,42 @@ static bool fr_bytes_canonical(const uint8_t* b) {
         if (v[i] > mod[i]) return false;
     }
     return false;
+}
+
+// two-level table of g^e, e < 2^log_range (tlo[e] = g^e, e < 2^H; thi[e] = g^(e 2^H)), cached on the context like a plan
+static int get_pow_table(ozk_ctx* ctx, const uint8_t base[32], int log_range, NttPlan** out) {
+    if (!fr_bytes_canonical(base)) {
+        set_error("twiddle base is not reduced mod r");
+        return OZK_ERR_DOMAIN;
+    }
+    std::string key("t");
+    key.append((const char*)base, 32);
+    key.push_back((char)log_range);
+    auto it = ctx->ntt_plans.find(key);
+    if (it != ctx->ntt_plans.end()) {
+        *out = it->second;
+        return OZK_OK;
+    }
+    NttPlan* tw = new NttPlan();
+    tw->log_n = log_range;
+    tw->H = (log_range + 1) / 2;
+    const size_t nlo = (size_t)1 << tw->H, nhi = (size_t)1 << (log_range - tw->H);
+    if (cudaMalloc(&tw->block, (nlo + nhi) * sizeof(Fr)) != cudaSuccess) {
+        delete tw;
+        set_error("twiddle table: out of device memory");
+        cudaGetLastError();
+        return OZK_ERR_CUDA;
+    }
+    tw->tlo = (Fr*)tw->block;
+    tw->thi = tw->tlo + nlo;
+    Fr g;
+    fr_from_bytes(g, base);
+    ntt_gen_table<<<(unsigned)((nlo / kGenRun + 128) / 128), 128, 0, ctx->stream>>>(tw->tlo, (uint32_t)nlo, 1u, g);
+    ntt_gen_table<<<(unsigned)((nhi / kGenRun + 128) / 128), 128, 0, ctx->stream>>>(tw->thi, (uint32_t)nhi, 1u << tw->H, g);
+    ctx->launches += 2;
+    ctx->ntt_plans[key] = tw;
+    *out = tw;
+    return OZK_OK;
 }
 
 static int scale_powers(ozk_ctx* ctx, const void* d_in, void* d_out, size_t n, const uint8_t* scale, const uint8_t* coset,
@@ -780,6 +868,32 @@ int ozk_fr_dft_small_dev(ozk_ctx* ctx, const void* d_in, void* d_out, size_t gro
     return OZK_OK;
 }
 
+int ozk_fr_dft_small_scatter_dev(ozk_ctx* ctx, const void* d_in, void* const* peer_out, size_t groups, size_t rank, size_t len,
+                                 const uint8_t omega_g[32], const uint8_t omega_n[32]) {
+    OZK_TRY(ctx_enter(ctx));
+    OZK_ARG(d_in && peer_out && omega_g && omega_n, "ozk_fr_dft_small_scatter_dev: null pointer");
+    const int q = ilog2_exact(groups);
+    OZK_ARG(q >= 1 && q <= 3, "ozk_fr_dft_small_scatter_dev: groups must be 2, 4 or 8");
+    OZK_ARG(rank < groups, "ozk_fr_dft_small_scatter_dev: rank out of range");
+    const int log_len = ilog2_exact(len);
+    OZK_ARG(log_len >= 0 && log_len + 2 * q <= 28, "ozk_fr_dft_small_scatter_dev: len must be a power of two, groups^2 * len <= 2^28");
+    for (size_t r = 0; r < groups; r++) OZK_ARG(peer_out[r] != nullptr, "ozk_fr_dft_small_scatter_dev: null peer buffer");
+    NttPlan* p;
+    OZK_TRY(ntt_get_plan(ctx, q, omega_g, &p));       // validates omega_g and holds omega_g^t, t < groups / 2
+    NttPlan* tw = nullptr;
+    OZK_TRY(get_pow_table(ctx, omega_n, log_len + 2 * q, &tw));
+    PeerPtrs pp;
+    memset(&pp, 0, sizeof pp);
+    for (size_t r = 0; r < groups; r++) pp.p[r] = (uint4*)peer_out[r];
+    const unsigned grid = (unsigned)((len + 255) / 256);
+    if (q == 1) fr_dft_small_scatter_kernel<1><<<grid, 256, 0, ctx->stream>>>((const uint4*)d_in, len, p->wsub[0], tw->tlo, tw->thi, (uint32_t)tw->H, (uint32_t)rank, pp);
+    else if (q == 2) fr_dft_small_scatter_kernel<2><<<grid, 256, 0, ctx->stream>>>((const uint4*)d_in, len, p->wsub[0], tw->tlo, tw->thi, (uint32_t)tw->H, (uint32_t)rank, pp);
+    else fr_dft_small_scatter_kernel<3><<<grid, 256, 0, ctx->stream>>>((const uint4*)d_in, len, p->wsub[0], tw->tlo, tw->thi, (uint32_t)tw->H, (uint32_t)rank, pp);
+    ctx->launches += 1;
+    OZK_CUDA(cudaGetLastError());
+    return OZK_OK;
+}
+
 int ozk_fr_scale_powers_dev(ozk_ctx* ctx, const void* d_a, void* d_out, size_t n, const uint8_t* scale, const uint8_t* coset,
                             uint64_t first_index) {
     OZK_TRY(ctx_enter(ctx));
@@ -836,41 +950,11 @@ int ozk_ntt_fr_scatter_dev(ozk_ctx* ctx, const void* d_in, void* const* peer_out
     OZK_ARG(rank < groups, "ozk_ntt_fr_scatter_dev: rank out of range");
     const int log_m = ilog2_exact(n_local);
     OZK_ARG(log_m >= 3 && log_m <= 28, "ozk_ntt_fr_scatter_dev: n_local must be a power of two in [8, 2^28]");
-    if (!fr_bytes_canonical(twiddle_base)) {
-        set_error("ozk_ntt_fr_scatter_dev: twiddle base is not reduced mod r");
-        return OZK_ERR_DOMAIN;
-    }
     for (size_t r = 0; r < groups; r++) OZK_ARG(peer_out[r] != nullptr, "ozk_ntt_fr_scatter_dev: null peer buffer");
     int log_g = 0;
     while (((size_t)1 << log_g) < groups) log_g++;
-    // two-level table of g^i, i < n_local, cached on the context like an NTT plan (key: 't' + g + log_m)
-    std::string key("t");
-    key.append((const char*)twiddle_base, 32);
-    key.push_back((char)log_m);
     NttPlan* tw = nullptr;
-    auto it = ctx->ntt_plans.find(key);
-    if (it != ctx->ntt_plans.end()) {
-        tw = it->second;
-    } else {
-        tw = new NttPlan();
-        tw->log_n = log_m;
-        tw->H = (log_m + 1) / 2;
-        const size_t nlo = (size_t)1 << tw->H, nhi = (size_t)1 << (log_m - tw->H);
-        if (cudaMalloc(&tw->block, (nlo + nhi) * sizeof(Fr)) != cudaSuccess) {
-            delete tw;
-            set_error("ozk_ntt_fr_scatter_dev: out of device memory");
-            cudaGetLastError();
-            return OZK_ERR_CUDA;
-        }
-        tw->tlo = (Fr*)tw->block;
-        tw->thi = tw->tlo + nlo;
-        Fr g;
-        fr_from_bytes(g, twiddle_base);
-        ntt_gen_table<<<(unsigned)((nlo + 127) / 128), 128, 0, ctx->stream>>>(tw->tlo, (uint32_t)nlo, 1u, g);
-        ntt_gen_table<<<(unsigned)((nhi + 127) / 128), 128, 0, ctx->stream>>>(tw->thi, (uint32_t)nhi, 1u << tw->H, g);
-        ctx->launches += 2;
-        ctx->ntt_plans[key] = tw;
-    }
+    OZK_TRY(get_pow_table(ctx, twiddle_base, log_m, &tw));
     ScatterDesc sc;
     sc.npeers = (uint32_t)groups;
     sc.my_rank = (uint32_t)rank;

@@ -28,6 +28,7 @@ import torch
 import torch.distributed as dist
 
 FR_MODULUS = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+from .algebra import FR_MULTIPLICATIVE_GENERATOR, FR_ROOT  # noqa: E402  (BN254aFrParameters.java:29-34)
 
 
 def _le32(x: int) -> bytes:
@@ -47,8 +48,17 @@ class GpuOps:
     def ntt(self, x, n, omega):
         self.ctx.ntt_dev(x, x, n, _le32(omega))
 
-    def scale_powers(self, x, n, coset):
-        self.ctx.fr_scale_powers_dev(x, x, n, None, _le32(coset), 0)
+    def scale_powers(self, x, n, coset, scale=None, first_index=0):
+        self.ctx.fr_scale_powers_dev(x, x, n, None if scale is None else _le32(scale), None if coset is None else _le32(coset), first_index)
+
+    def ntt_from(self, src, out, n, omega):
+        self.ctx.ntt_dev(src, out, n, _le32(omega))
+
+    def dft_small_scatter(self, x, peer_ptrs, rank, length, omega_g, omega_n):
+        self.ctx.dft_small_scatter_dev(x, peer_ptrs, rank, length, _le32(omega_g), _le32(omega_n))
+
+    def mul_sub(self, a, b, c, out, n):
+        self.ctx.fr_mul_sub_dev(a, b, c, out, n)
 
     def ntt_scatter(self, x, peer_ptrs, rank, n_local, omega_local, twiddle_base):
         self.ctx.ntt_scatter_dev(x, peer_ptrs, rank, n_local, _le32(omega_local), _le32(twiddle_base))
@@ -152,6 +162,91 @@ def ntt_distributed(ops, x_local, n: int, omega: int, group=None, exchange: Opti
     out = ops.empty_like(x_local)
     ops.dft_small(recv, out, world, m // world, pow(omega, m, FR_MODULUS))   # step 2
     return out
+
+
+def ntt_distributed_blocked_in(ops, x_local, n: int, omega: int, group=None, exchange: Optional[PeerExchange] = None):
+    """The mirrored transform: x_local is in the OUTPUT layout of `ntt_distributed` (rank d holds x[a * M + d * c + t] at
+    [a][t], c = M / G); returns the transform in the cyclic layout (rank d holds X[d + G * k2] at k2).
+         step 1 : G-point transform over a (local)           y[k1][t] = sum_a x[a][t] omega_G^(a k1)
+         twiddle: y[k1][t] *= omega^((d c + t) k1)
+         exchange: block y[k1] goes to rank k1, placed at d c  (fused: stored there by the step-1 kernel)
+         step 2 : local M-point transform with omega^G
+    Alternating the two forms chains transforms without ever re-laying data out (sharded R1CStoQAPWitness below)."""
+    world = _world(group)
+    rank = _rank(group)
+    assert n % world == 0 and world in (1, 2, 4, 8)
+    m = n // world
+    assert x_local.numel() == m * 32
+    if world == 1:
+        ops.ntt(x_local, n, omega)
+        return x_local
+    assert m % world == 0
+    c = m // world
+    omega_g = pow(omega, m, FR_MODULUS)
+    if exchange is not None:
+        assert exchange.nbytes >= m * 32 and exchange.world == world
+        exchange.barrier()
+        ops.dft_small_scatter(x_local, exchange.peers, rank, c, omega_g, omega)
+        exchange.barrier()
+        out = ops.empty_like(x_local)
+        ops.ntt_from(exchange.ptr, out, m, pow(omega, world, FR_MODULUS))
+        return out
+    y = ops.empty_like(x_local)
+    ops.dft_small(x_local, y, world, c, omega_g)
+    for k1 in range(1, world):
+        blk = y[k1 * c * 32:(k1 + 1) * c * 32]
+        ops.scale_powers(blk, c, pow(omega, k1, FR_MODULUS), None, rank * c)           # omega^(k1 (d c + t))
+    recv = ops.empty_like(y)
+    dist.all_to_all_single(recv, y, group=group)                                     # block k1 -> rank k1, ordered by source d
+    ops.ntt(recv, m, pow(omega, world, FR_MODULUS))
+    return recv
+
+
+def scale_blocked(ops, x_local, n: int, world: int, rank: int, scale: Optional[int], coset: Optional[int]):
+    """x[i] *= scale * coset^i for data in the blocked layout (global index i = a M + rank c + t at [a][t])."""
+    m = n // world
+    c = m // world
+    for a in range(world):
+        blk = x_local[a * c * 32:(a + 1) * c * 32]
+        ops.scale_powers(blk, c, coset, scale, a * m + rank * c)
+
+
+def witness_map_distributed(ops, A, B, C, n: int, group=None, exchange: Optional[PeerExchange] = None):
+    """R1CStoQAP.R1CStoQAPWitness's transform chain (src/main/java/reductions/r1cs_to_qap/R1CStoQAP.java:165-227) on a
+    domain of n points sharded over the ranks: A, B, C hold the evaluations a_i, b_i, c_i of this rank's cyclic shard
+    (index rank + G * i2, overwritten).  Inverse transform (cyclic -> blocked), coset scaling in the blocked layout, coset
+    forward transform (blocked -> cyclic), H' = A B - C pointwise, inverse coset transform (cyclic -> blocked) with the
+    divide-by-Z factor folded in.  Returns H in the blocked layout: rank d holds the coefficients h[k1 M + d c + t] at [k1][t]
+    -- the order in which this rank's slice of queryH must be stored for the H MSM."""
+    world = _world(group)
+    rank = _rank(group)
+    R = FR_MODULUS
+    g = FR_MULTIPLICATIVE_GENERATOR
+    omega = pow(FR_ROOT, R // n, R)                                                  # Fp.rootOfUnity, Fp.java:98-102
+    omega_inv = pow(omega, -1, R)
+    n_inv = pow(n, -1, R)
+    m = n // world
+    on_coset = []
+    for X in (A, B, C):
+        if world == 1:
+            ops.ntt(X, n, omega_inv)
+            ops.scale_powers(X, n, g, n_inv, 0)
+            ops.ntt(X, n, omega)
+            on_coset.append(X)
+            continue
+        co = ntt_distributed(ops, X, n, omega_inv, group, exchange)                   # coefficients * n, blocked
+        scale_blocked(ops, co, n, world, rank, n_inv, g)                              # radix2InverseFFT's 1/n and multiplyByCoset
+        on_coset.append(ntt_distributed_blocked_in(ops, co, n, omega, group, exchange))   # evaluations on the coset, cyclic
+    a, b, c = on_coset
+    ops.mul_sub(a, b, c, a, m)                                                        # R1CStoQAP.java:211-214
+    z_inv = pow((pow(g, n, R) - 1) % R, -1, R)                                        # divideByZOnCoset, SerialFFT.java:157-162
+    if world == 1:
+        ops.ntt(a, n, omega_inv)
+        ops.scale_powers(a, n, pow(g, -1, R), n_inv * z_inv % R, 0)
+        return a
+    h = ntt_distributed(ops, a, n, omega_inv, group, exchange)
+    scale_blocked(ops, h, n, world, rank, n_inv * z_inv % R, pow(g, -1, R))           # radix2CosetInverseFFT
+    return h
 
 
 def ntt_scatter_cyclic(x: bytes, world: int, rank: int) -> bytes:

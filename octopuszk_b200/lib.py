@@ -45,6 +45,7 @@ SIGNATURES = {
     "ozk_fr_mul_sub_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _sz]),
     "ozk_fr_lagrange_dev": (_int, [_vp, _vp, _sz, _c_u8p, _c_u8p]),
     "ozk_ntt_fr_scatter_dev": (_int, [_vp, _vp, ctypes.POINTER(_vp), _sz, _sz, _sz, _c_u8p, _c_u8p]),
+    "ozk_fr_dft_small_scatter_dev": (_int, [_vp, _vp, ctypes.POINTER(_vp), _sz, _sz, _sz, _c_u8p, _c_u8p]),
     "ozk_peer_alloc": (_int, [_vp, _sz, ctypes.POINTER(_vp), ctypes.c_char_p]),
     "ozk_peer_open": (_int, [_vp, ctypes.c_char_p, ctypes.POINTER(_vp)]),
     "ozk_peer_close": (_int, [_vp, _vp]),
@@ -216,6 +217,10 @@ class Context:
     def ntt_scatter_dev(self, d_in, peer_ptrs, rank: int, n_local: int, omega_local: bytes, twiddle_base: bytes):
         arr = (ctypes.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
         self._check(self.lib.ozk_ntt_fr_scatter_dev(self._h, _ptr(d_in), arr, len(peer_ptrs), rank, n_local, omega_local, twiddle_base))
+
+    def dft_small_scatter_dev(self, d_in, peer_ptrs, rank: int, length: int, omega_g: bytes, omega_n: bytes):
+        arr = (ctypes.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        self._check(self.lib.ozk_fr_dft_small_scatter_dev(self._h, _ptr(d_in), arr, len(peer_ptrs), rank, length, omega_g, omega_n))
 
     def peer_alloc(self, nbytes: int):
         """(device pointer, 64-byte IPC handle) of a fresh cudaMalloc block other processes can map."""

@@ -29,10 +29,17 @@ class OracleOps:
         out = C.fft_fr(x.numpy().tobytes(), O.le32(omega))
         x.copy_(torch.frombuffer(bytearray(out), dtype=torch.uint8))
 
-    def scale_powers(self, x, n, coset):
+    def scale_powers(self, x, n, coset, scale=None, first_index=0):
         v = [O.from_le(bytes(x[32 * i:32 * i + 32].tolist())) for i in range(n)]
-        O.multiply_by_coset(v, coset)
+        s = 1 if scale is None else scale
+        g = 1 if coset is None else coset
+        v = [a * s * pow(g, first_index + i, O.R) % O.R for i, a in enumerate(v)]
         x.copy_(torch.frombuffer(bytearray(O.pack_scalars(v)), dtype=torch.uint8))
+
+    def mul_sub(self, a, b, c, out, n):
+        f = lambda t: [O.from_le(bytes(t[32 * i:32 * i + 32].tolist())) for i in range(n)]
+        va, vb, vc = f(a), f(b), f(c)
+        out.copy_(torch.frombuffer(bytearray(O.pack_scalars([(x * y - z) % O.R for x, y, z in zip(va, vb, vc)])), dtype=torch.uint8))
 
     def dft_small(self, x, out, groups, length, omega_g):
         raw = x.numpy().tobytes()
@@ -77,7 +84,13 @@ def _worker(rank, world, port, q):
     lo, hi = rank * total // world, (rank + 1) * total // world
     res = D.msm_distributed(ops, torch.frombuffer(bytearray(O.pack_scalars(scalars[lo:hi])), dtype=torch.uint8),
                             torch.frombuffer(bytearray(O.pack_g1(bases[lo:hi])), dtype=torch.uint8), hi - lo)
-    q.put((rank, out.numpy().tobytes(), res, x, scalars, bases))
+    # ---- mirrored transform: blocked layout in, cyclic out (chains with the one above without a re-layout)
+    back = D.ntt_distributed_blocked_in(ops, out.clone(), n, pow(omega, -1, O.R))     # inverse of the transform above, times n
+    # ---- sharded R1CStoQAPWitness transform chain
+    ev = [[rng.randrange(O.R) for _ in range(n)] for _ in range(3)]
+    sh = [torch.frombuffer(bytearray(D.ntt_scatter_cyclic(O.pack_scalars(v), world, rank)), dtype=torch.uint8) for v in ev]
+    h = D.witness_map_distributed(ops, sh[0], sh[1], sh[2], n)
+    q.put((rank, out.numpy().tobytes(), res, x, scalars, bases, back.numpy().tobytes(), ev, h.numpy().tobytes()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -102,6 +115,25 @@ def test_world_size_2_gloo():
     O.serial_radix2_fft(exp, O.root_of_unity(n))                       # DistributedFFTTest.java:41-67: distributed == serial
     got = D.ntt_gather_natural([r[1] for r in results], n)
     assert [O.from_le(got[32 * i:32 * i + 32]) for i in range(n)] == exp
+    # blocked-in transform with omega^-1 undoes it (up to the factor n), and returns the cyclic layout
+    for r in results:
+        cyc = [O.from_le(r[6][32 * i:32 * i + 32]) for i in range(n // world)]
+        assert cyc == [x[r[0] + world * i] * n % O.R for i in range(n // world)]
+    # witness map: H = cosetIFFT((cosetFFT(IFFT(A)) * cosetFFT(IFFT(B)) - cosetFFT(IFFT(C))) / Z), R1CStoQAP.java:165-227
+    ev = results[0][7]
+    dom = O.SerialFFT(n)
+    g = O.FR_MULT_GEN
+    cos = []
+    for v in ev:
+        v = list(v)
+        dom.radix2_inverse_fft(v)
+        dom.radix2_coset_fft(v, g)
+        cos.append(v)
+    hh = [(a * b - c) % O.R for a, b, c in zip(*cos)]
+    dom.divide_by_z_on_coset(g, hh)
+    dom.radix2_coset_inverse_fft(hh, g)
+    got_h = D.ntt_gather_natural([r[8] for r in results], n)
+    assert [O.from_le(got_h[32 * i:32 * i + 32]) for i in range(n)] == hh
     scalars, bases = results[0][4], results[0][5]
     e = O.pippenger_msm(O.G1, scalars, bases)
     for r in results:                                                  # every rank holds the same global sum

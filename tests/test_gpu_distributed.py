@@ -103,6 +103,36 @@ def test_four_step_fused_scatter_emulated_ranks(world, log_n):
     ctx.close()
 
 
+@pytest.mark.parametrize("world,log_n", [(2, 4), (2, 9), (4, 10), (8, 12), (8, 17), (4, 22)])
+def test_mirrored_transform_scatter_emulated_ranks(world, log_n):
+    """ozk_fr_dft_small_scatter_dev + local transform: blocked layout in ([a][t] per rank), cyclic layout out, every rank
+    emulated on one GPU; against the single-GPU transform (itself checked against the oracle)."""
+    from octopuszk_b200 import Context
+    from octopuszk_b200 import distributed as D
+    ctx = Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    ops = D.GpuOps(ctx)
+    n = 1 << log_n
+    m, c = n // world, n // world // world
+    raw = util.rand_scalars_bytes(n, seed=200 + log_n)
+    omega = O.root_of_unity(n)
+    full = torch.from_numpy(raw.copy()).view(world, world, c, 32)            # [a][d][t]
+    recv = [torch.zeros(m * 32, dtype=torch.uint8, device="cuda") for _ in range(world)]
+    ptrs = [t.data_ptr() for t in recv]
+    for d in range(world):
+        x_d = full[:, d].contiguous().view(-1).cuda()                        # [a][t] of rank d
+        ops.dft_small_scatter(x_d, ptrs, d, c, pow(omega, m, O.R), omega)
+    outs = []
+    for d in range(world):
+        out = torch.empty_like(recv[d])
+        ops.ntt_from(recv[d], out, m, pow(omega, world, O.R))
+        ctx.sync()
+        outs.append(out.cpu().view(m, 32))
+    got = torch.stack(outs, dim=1).contiguous().view(-1).numpy().tobytes()   # X[d + G k2] = outs[d][k2]
+    ref = ctx.ntt(raw.tobytes(), O.le32(omega))
+    assert got == ref
+    ctx.close()
+
+
 @pytest.mark.parametrize("world,log_n", [(2, 8), (4, 10), (8, 12), (8, 16)])
 def test_four_step_emulated_ranks(world, log_n):
     from octopuszk_b200 import Context
@@ -150,6 +180,21 @@ def _nccl_worker(rank, world, port, q):
     out = D.ntt_distributed(ops, shard, n, omega)                            # NCCL all_to_all form (overwrites shard)
     torch.cuda.synchronize()
     assert torch.equal(fused, out) and torch.equal(fused2, out)
+    # sharded R1CStoQAPWitness chain: fused exchange == NCCL form == the single-GPU chain on the whole vectors
+    import numpy as np
+    R_, g_ = O.R, O.FR_MULT_GEN
+    ev = [util.rand_scalars_bytes(n, seed=70 + k) for k in range(3)]
+    shards = [torch.from_numpy(np.ascontiguousarray(v[rank::world])).view(-1).cuda() for v in ev]
+    h_fused = D.witness_map_distributed(ops, *[t.clone() for t in shards], n, exchange=ex)
+    h_nccl = D.witness_map_distributed(ops, *[t.clone() for t in shards], n)
+    torch.cuda.synchronize()
+    assert torch.equal(h_fused, h_nccl)
+    whole = [torch.from_numpy(v.copy()).view(-1).cuda() for v in ev]
+    solo = [dist.new_group([r]) for r in range(world)]                                    # new_group is collective: same calls on every rank
+    h_one = D.witness_map_distributed(ops, *whole, n, group=solo[rank])                   # world 1: plain single-GPU chain
+    m_, c_ = n // world, n // world // world
+    mine = h_one.view(world, world, c_, 32)[:, rank].contiguous().view(-1)                # [k1][t] of this rank
+    assert torch.equal(h_fused, mine)
     ex.close()
     ks, pool = util.known_dlog_points(O.G1, 16, seed=4)
     total = 1 << 12
