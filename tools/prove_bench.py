@@ -6,7 +6,10 @@ proving-key points produced by the fixed-base path (Z = 1, as this library's set
 of the Java (linear-combination evaluation) are outside the hot path and not included.
 
     python tools/prove_bench.py [log_m ...]            # one GPU
-    torchrun --nproc-per-node N tools/prove_bench.py   # MSMs sharded over N GPUs (transforms replicated)"""
+    torchrun --nproc-per-node N tools/prove_bench.py   # everything sharded over N GPUs: the seven transforms as four-step
+                                                       # transforms with the exchange fused into the kernels (peer stores,
+                                                       # distributed.witness_map_distributed), the MSMs over point shards
+    OZK_PROVE_REPLICATED_NTT=1 keeps the earlier form (every rank runs the whole transforms) for comparison."""
 import json
 import os
 import sys
@@ -56,21 +59,35 @@ for log_m in [int(a) for a in sys.argv[1:]] or [20]:
     ctx.fixed_g1_dev(O.pack_g1([g1]), kh, hshard, 15, 17, qh)
     del k, kh
     w = rand_fr(shard, 7 + rank)         # this rank's slice of the witness
-    A, B, C = rand_fr(n, 11), rand_fr(n, 12), rand_fr(n, 13)
+    sharded = world > 1 and not os.environ.get("OZK_PROVE_REPLICATED_NTT")
+    nloc = n // world if sharded else n  # elements of A, B, C this rank holds (its cyclic shard, or everything)
+    A0, B0, C0 = rand_fr(nloc, 11 + 100 * rank), rand_fr(nloc, 12 + 100 * rank), rand_fr(nloc, 13 + 100 * rank)
+    A, B, C = A0.clone(), B0.clone(), C0.clone()
+    ex = D.PeerExchange(ctx, nloc * 32) if sharded else None
     omega = O.root_of_unity(n)
     wf, wi = O.le32(omega), O.le32(pow(omega, -1, R))
     ninv, g = O.le32(pow(n, -1, R)), O.FR_MULT_GEN
     zscale = O.le32(pow(n, -1, R) * pow((pow(g, n, R) - 1) % R, -1, R) % R)
 
     def witness_map():
+        if sharded:
+            # the evaluations arrive from the host each proof; here: fresh copies of the synthetic shard
+            A.copy_(A0); B.copy_(B0); C.copy_(C0)
+            return D.witness_map_distributed(ops, A.view(-1), B.view(-1), C.view(-1), n, exchange=ex)
         for d in (A, B, C):
             ctx.ntt_ex_dev(d, d, n, wi, None, ninv, None)
             ctx.ntt_ex_dev(d, d, n, wf, O.le32(g), None, None)
         ctx.fr_mul_sub_dev(A, B, C, A, n)
         ctx.ntt_ex_dev(A, A, n, wi, None, zscale, O.le32(pow(g, -1, R)))
+        return A
+
+    hbuf = [None]
 
     def msms():
-        h = A.view(n, 32)[rank * hshard:(rank + 1) * hshard]
+        if sharded:
+            h = hbuf[0].view(nloc, 32)             # this rank's coefficients of H (blocked layout; queryH is stored to match)
+        else:
+            h = A.view(n, 32)[rank * hshard:(rank + 1) * hshard]
         out = [D.msm_distributed(ops, w, qa, shard),                       # query A
                D.msm_distributed(ops, w, qa, shard),                       # query B, G1 half
                D.msm_distributed(ops, w, qb2, shard, g2=True),             # query B, G2 half
@@ -79,7 +96,7 @@ for log_m in [int(a) for a in sys.argv[1:]] or [20]:
         return out
 
     def step():
-        witness_map()
+        hbuf[0] = witness_map()
         return msms()
 
     step()
@@ -102,7 +119,10 @@ for log_m in [int(a) for a in sys.argv[1:]] or [20]:
             ts.append(float(t.item()))
         res[name + "_ms"] = sorted(ts)[1]
     if rank == 0:
-        print(json.dumps({"op": "groth16_prove_hot_path", "log_constraints": log_m, "fft_domain_log": log_m + 1, "n_gpus": world, **res}), flush=True)
-    del A, B, C, qa, qb2, qh, w
+        print(json.dumps({"op": "groth16_prove_hot_path", "log_constraints": log_m, "fft_domain_log": log_m + 1, "n_gpus": world,
+                          "transforms": "sharded, fused exchange" if sharded else ("replicated" if world > 1 else "single GPU"), **res}), flush=True)
+    if ex is not None:
+        ex.close()
+    del A, B, C, A0, B0, C0, qa, qb2, qh, w
 if world > 1:
     dist.destroy_process_group()
