@@ -15,7 +15,7 @@ One "step" = one pass of the hot path (ozk_msm_g1*) over one batch of synthetic 
            cannot run, no JVM in the image) on all host cores, on a bounded sample.
 --impl reference times that same CPU restatement as the reference arm.
 Multi-GPU (torchrun): every rank owns 2^log_n pairs (weak scaling, no data-path collective); the only exchange is an
-all_gather of the 96-byte partial sums, added on every rank by a tiny MSM.
+all_gather of the 96-byte partial sums, added on every rank by one tiny launch (ozk_sum_g1_dev).
 """
 from __future__ import annotations
 
@@ -160,8 +160,6 @@ def run_ours(args):
     _ks, _pool = _util.known_dlog_points(O.G1, 64, seed=100 + rank, random_z=True)
     _pool = [O.G1.to_affine(p) for p in _pool]                                          # the same points with Z = 1
     d_b = torch.from_numpy(np.ascontiguousarray(_util.tiled_bases_bytes(O.G1, _pool, n))).to(dev)
-    ones = torch.zeros((world, 32), dtype=torch.uint8, device=dev)
-    ones[:, 0] = 1
 
     def barrier():
         if world > 1:
@@ -174,7 +172,7 @@ def run_ours(args):
             part = torch.frombuffer(bytearray(out), dtype=torch.uint8).to(dev)
             gathered = torch.empty((world, 96), dtype=torch.uint8, device=dev)
             dist.all_gather_into_tensor(gathered, part)
-            out = ctx.msm_g1_dev(ones, gathered, world)
+            out = ctx.sum_points_dev(1, gathered, world)
         return out
 
     def step_e2e():

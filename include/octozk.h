@@ -170,6 +170,11 @@ OZK_API int ozk_msm_g1g2_keyed(ozk_ctx* ctx, const uint8_t* scalars, const ozk_b
 OZK_API int ozk_msm_g1g2_keyed_dev(ozk_ctx* ctx, const void* d_scalars, const ozk_bases* key1, const ozk_bases* key2, size_t first, size_t n,
                                    uint8_t out[288]);
 
+/* out = sum of k <= 4096 points given in the wire format in device memory: the reduce(add) over the partial sums of a
+ * sharded MSM (VariableBaseMSM.distributedMSM, src/main/java/algebra/msm/VariableBaseMSM.java:777-783). */
+OZK_API int ozk_sum_g1_dev(ozk_ctx* ctx, const void* d_points, size_t k, uint8_t out[96]);
+OZK_API int ozk_sum_g2_dev(ozk_ctx* ctx, const void* d_points, size_t k, uint8_t out[192]);
+
 /* last MSM on this context: {window bits, windows, buckets per window, overflow tasks, overflow buckets,
  * ms sort, ms convert, ms accumulate, ms merge, ms reduce+final} (device times from events on the context's stream;
  * for the paired call the per-group phases are those of the G2 half) */

@@ -752,6 +752,29 @@ int ozk_msm_g1g2_keyed_dev(ozk_ctx* ctx, const void* d_scalars, const ozk_bases*
                    BaseSrc{nullptr, (const char*)key2->d_affine + first * kMsmG2.affine_bytes}, n, out);
 }
 
+// out = sum of k points in the wire format (device memory): the reduce(add) of the partial sums of a sharded MSM
+// (VariableBaseMSM.distributedMSM, VariableBaseMSM.java:777-783) as one tiny launch instead of a k-point MSM.
+static int sum_points(ozk_ctx* ctx, const MsmLaunch& L, const void* d_points, size_t k, uint8_t* out, size_t coord_bytes) {
+    OZK_ARG(out && (k == 0 || d_points) && k <= 4096, "ozk_sum: null pointer or more than 4096 points");
+    if (k == 0) { write_inf(out, coord_bytes); return OZK_OK; }
+    OZK_TRY(ctx->io_out.reserve(512, ctx->stream));
+    if (L.sum_wire(ctx->stream, d_points, (uint32_t)k, ctx->io_out.p)) { set_error("sum: launch failed"); return OZK_ERR_CUDA; }
+    ctx->launches += 1;
+    uint8_t* pin = (uint8_t*)ctx->pinned;
+    OZK_CUDA(cudaMemcpyAsync(pin, ctx->io_out.p, L.jac_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    OZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(out, pin, L.jac_bytes);
+    return OZK_OK;
+}
+int ozk_sum_g1_dev(ozk_ctx* ctx, const void* d_points, size_t k, uint8_t out[96]) {
+    OZK_TRY(ctx_enter(ctx));
+    return sum_points(ctx, kMsmG1, d_points, k, out, 32);
+}
+int ozk_sum_g2_dev(ozk_ctx* ctx, const void* d_points, size_t k, uint8_t out[192]) {
+    OZK_TRY(ctx_enter(ctx));
+    return sum_points(ctx, kMsmG2, d_points, k, out, 64);
+}
+
 int ozk_msm_last_stats(ozk_ctx* ctx, double* out, int cap) {
     if (!ctx || !out) return 0;
     int k = cap < 10 ? cap : 10;

@@ -3,7 +3,7 @@
 Replaces the reference's Spark distribution:
   * VariableBaseMSM.distributedMSM (src/main/java/algebra/msm/VariableBaseMSM.java:772-786: mapPartitions + reduce(add))
     -> every rank runs the full single-GPU MSM on its contiguous shard; the only exchange is an all_gather of the
-       96/192-byte partial sums, added on every rank.  No data-path collective.
+       96/192-byte partial sums, added on every rank (ozk_sum_g1_dev / _g2_dev).  No data-path collective.
   * FFTAuxiliary.distributedRadix2FFT (src/main/java/algebra/fft/FFTAuxiliary.java:129-219: two shuffles)
     -> four-step with n = G * M over G ranks and ONE all-to-all:
          input  : rank d holds x[d + G * i2], i2 < M                      (cyclic shard)
@@ -72,6 +72,9 @@ class GpuOps:
     def msm_g2(self, scalars, bases, n):
         return self.ctx.msm_g2_dev(scalars, bases, n)
 
+    def sum_points(self, points, k, g2=False):
+        return self.ctx.sum_points_dev(2 if g2 else 1, points, k)
+
     def to_device(self, b: bytes):
         return torch.frombuffer(bytearray(b), dtype=torch.uint8).to(self.device)
 
@@ -95,6 +98,8 @@ def msm_distributed(ops, scalars_local, bases_local, n_local: int, g2: bool = Fa
     mine = ops.to_device(part)
     gathered = torch.empty((world * size,), dtype=torch.uint8, device=mine.device)
     dist.all_gather_into_tensor(gathered, mine, group=group)
+    if hasattr(ops, "sum_points"):
+        return ops.sum_points(gathered, world, g2)            # one tiny launch: reduce(add) of the partial sums
     ones = bytearray(32 * world)
     for r in range(world):
         ones[32 * r] = 1

@@ -68,6 +68,8 @@ SIGNATURES = {
     "ozk_fixed_g1_dev": (_int, [_vp, _c_u8p, _vp, _sz, _int, _int, _vp]),
     "ozk_fixed_g2": (_int, [_vp, _c_u8p, _vp, _sz, _int, _int, _vp]),
     "ozk_fixed_g2_dev": (_int, [_vp, _c_u8p, _vp, _sz, _int, _int, _vp]),
+    "ozk_sum_g1_dev": (_int, [_vp, _vp, _sz, _vp]),
+    "ozk_sum_g2_dev": (_int, [_vp, _vp, _sz, _vp]),
     "ozk_msm_last_stats": (_int, [_vp, ctypes.POINTER(ctypes.c_double), _int]),
     "ozk_bases_upload_g1": (_int, [_vp, _vp, _sz, ctypes.POINTER(_vp)]),
     "ozk_bases_upload_g1_dev": (_int, [_vp, _vp, _sz, ctypes.POINTER(_vp)]),
@@ -307,6 +309,11 @@ class Context:
         out = ctypes.create_string_buffer(288)
         fn = getattr(self.lib, "ozk_msm_g1g2_keyed" + ("_dev" if device else ""))
         self._check(fn(self._h, _ptr(scalars), key1._h, key2._h, first, n, out))
+        return out.raw
+
+    def sum_points_dev(self, group: int, d_points, k: int) -> bytes:
+        out = ctypes.create_string_buffer(96 if group == 1 else 192)
+        self._check(getattr(self.lib, f"ozk_sum_g{group}_dev")(self._h, _ptr(d_points), k, out))
         return out.raw
 
     def msm_last_stats(self):

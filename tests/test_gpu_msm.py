@@ -245,3 +245,20 @@ def test_keyed_paired_and_errors(ctx):
         ctx.upload_bases(1, b"".join(O.le32(v) for p in bad for v in p), 1)
     key1.free()
     key2.free()
+
+
+def test_sum_of_wire_points(ctx):
+    """ozk_sum_g1_dev / _g2_dev: the reduce(add) of per-shard partial sums (VariableBaseMSM.java:777-783), with infinity,
+    a point twice (doubling) and a point with its negation among the summands."""
+    import torch
+    for G, grp, pack in ((O.G1, 1, O.pack_g1), (O.G2, 2, O.pack_g2)):
+        ks, pool = util.known_dlog_points(G, 5, seed=61, random_z=True)
+        pts = [pool[0], G.zero(), pool[1], pool[1], pool[2], G.negate(pool[2]), pool[3], G.to_affine(pool[4])]
+        d = torch.frombuffer(bytearray(pack(pts)), dtype=torch.uint8).cuda()
+        got = util.unpack_point(G, ctx.sum_points_dev(grp, d, len(pts)))
+        exp = G.zero()
+        for p in pts:
+            exp = G.add(exp, p)
+        assert G.equals(got, exp)
+        assert G.is_zero(util.unpack_point(G, ctx.sum_points_dev(grp, d, 0)))
+        assert G.equals(util.unpack_point(G, ctx.sum_points_dev(grp, d, 1)), pool[0])

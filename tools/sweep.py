@@ -92,8 +92,8 @@ if "msm" in what:
     msm_sweep(O.G1, [int(x) for x in os.environ.get("OZK_SWEEP_LOGS", "16,18,20,22,24,26").split(",")], "varmsm_g1")
 if "msm2" in what:
     msm_sweep(O.G2, [16, 18, 20, 22], "varmsm_g2")
-if "ntt" in what:
-    for log_n in [16, 18, 20, 22, 24, 26, 28]:
+if "ntt" in what or "ntt26" in what:
+    for log_n in ([26] if "ntt26" in what else [16, 18, 20, 22, 24, 26, 28]):
         n = 1 << log_n
         d = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device="cuda")
         d[:, 31] &= 0x1F
