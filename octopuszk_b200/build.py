@@ -24,7 +24,7 @@ NVCC_FLAGS = [
     "-I", os.path.join(ROOT, "include"),
 ]
 
-CU_SOURCES = ["capi.cu", "ntt.cu", "msm.cu", "msm_g1.cu", "msm_g2.cu", "fixed_base.cu"]
+CU_SOURCES = ["capi.cu", "ntt.cu", "msm.cu", "msm_g1.cu", "msm_g2.cu", "fixed_base.cu", "stage.cu"]
 HEADERS = ["common.h", "consts.cuh", "chains.cuh", "curve.cuh", "fp256.cuh", "ptx_arith.cuh", "msm_impl.cuh", "fixed_impl.cuh", os.path.join(ROOT, "include", "octozk.h")]
 
 

@@ -186,6 +186,7 @@ void ozk_ctx_destroy(ozk_ctx* c) {
     cudaStreamSynchronize(c->stream);
     ntt_free_plans(c);
     fixed_free_tables(c);
+    stager_free(c);
     c->io_a.release(); c->io_b.release(); c->io_c.release(); c->io_out.release();
     c->work.release();
     for (auto& b : c->msm) b.release();

@@ -65,6 +65,7 @@ struct DevBuf {
 
 struct NttPlan;
 struct FixedTable;
+struct Stager;
 
 }  // namespace ozk
 
@@ -89,6 +90,7 @@ struct ozk_ctx {
     void* pinned = nullptr;                    // small pinned host block for flags / results
     std::map<std::string, ozk::NttPlan*> ntt_plans;
     std::map<std::string, ozk::FixedTable*> fixed_tables;
+    ozk::Stager* stager = nullptr;              // bounce buffers for uploads from pageable host memory (stage.cu)
 };
 
 // Persistent device-resident bases (ozk_bases_upload_*): affine Montgomery coordinates, (0,0) for infinity.
@@ -103,4 +105,8 @@ namespace ozk {
 static constexpr int kCopyChunks = 8;      // chunks per uploaded base array (<= 2 arrays x 8 + 1 events)
 // activates ctx->device for the calling thread
 int ctx_enter(ozk_ctx* ctx);
+// stage.cu: uploads from pageable host memory through pinned bounce buffers on helper threads
+bool host_pointer_is_pageable(const void* p);
+int staged_h2d(ozk_ctx* ctx, void* dst, const void* src, size_t bytes, cudaEvent_t after, cudaStream_t consumer);
+void stager_free(ozk_ctx* ctx);
 }  // namespace ozk

@@ -522,14 +522,18 @@ static int msm_run_host(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* b1,
     // the copy stream must not overtake earlier work on the main stream that still uses the staging buffers
     OZK_CUDA(cudaEventRecord(ctx->copy_ev[2 * kCopyChunks], st));
     OZK_CUDA(cudaStreamWaitEvent(cs, ctx->copy_ev[2 * kCopyChunks], 0));
-    int k = 0;
-    for (size_t lo = 0; lo < n; lo += slice, k++) {
-        const size_t len = std::min(slice, n - lo);
-        OZK_CUDA(cudaMemcpyAsync((char*)ctx->io_a.p + lo * 32, scalars + lo * 32, len * 32, cudaMemcpyHostToDevice, cs));
-        if (b1) OZK_CUDA(cudaMemcpyAsync((char*)ctx->io_b.p + lo * 96, b1 + lo * 96, len * 96, cudaMemcpyHostToDevice, cs));
-        if (b2) OZK_CUDA(cudaMemcpyAsync((char*)ctx->io_c.p + lo * 192, b2 + lo * 192, len * 192, cudaMemcpyHostToDevice, cs));
-        OZK_CUDA(cudaEventRecord(ctx->copy_ev[k], cs));
-    }
+    // Uploads: pinned (or registered) host memory goes through cudaMemcpyAsync on the copy stream; pageable memory -- what the
+    // JNI shims pass, the arrays live on the JVM heap -- through the bounce-buffer stager (stage.cu), which blocks this thread
+    // only for the host-side memcpy of the slice while the GPU works on the previous one.
+    const bool page_s = host_pointer_is_pageable(scalars);
+    const bool page_1 = b1 && host_pointer_is_pageable(b1);
+    const bool page_2 = b2 && host_pointer_is_pageable(b2);
+    cudaEvent_t after = ctx->copy_ev[2 * kCopyChunks];
+    auto upload = [&](void* dst, const uint8_t* src, size_t nbytes, bool pageable) -> int {
+        if (pageable && nbytes >= ((size_t)8 << 20)) return staged_h2d(ctx, dst, src, nbytes, after, st);
+        OZK_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, cs));
+        return OZK_OK;
+    };
     if (b1) s1 = {ctx->io_b.p, nullptr};
     if (b2) s2 = {ctx->io_c.p, nullptr};
     char* d_res = (char*)ctx->io_out.p;
@@ -537,11 +541,15 @@ static int msm_run_host(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* b1,
     ctx->msm_stats[0] = sh.c;
     ctx->msm_stats[1] = sh.nwin;
     ctx->msm_stats[2] = sh.nb;
-    k = 0;
+    int k = 0;
     for (size_t lo = 0; lo < n; lo += slice, k++) {
         const size_t len = std::min(slice, n - lo);
-        sh = msm_shape(n, len);
+        OZK_TRY(upload((char*)ctx->io_a.p + lo * 32, scalars + lo * 32, len * 32, page_s));
+        if (b1) OZK_TRY(upload((char*)ctx->io_b.p + lo * 96, b1 + lo * 96, len * 96, page_1));
+        if (b2) OZK_TRY(upload((char*)ctx->io_c.p + lo * 192, b2 + lo * 192, len * 192, page_2));
+        OZK_CUDA(cudaEventRecord(ctx->copy_ev[k], cs));
         OZK_CUDA(cudaStreamWaitEvent(st, ctx->copy_ev[k], 0));
+        sh = msm_shape(n, len);
         OZK_TRY(msm_sort(ctx, (char*)ctx->io_a.p + lo * 32, len, sh));
         if (s1.any()) {
             BaseSrc b = {s1.wire ? (const char*)s1.wire + lo * kMsmG1.jac_bytes : nullptr, s1.affine ? (const char*)s1.affine + lo * kMsmG1.affine_bytes : nullptr};
