@@ -5,6 +5,7 @@
 // cached per (group, base, table window) on the context, so the four batchMSM calls of SerialSetup on the same
 // generator (SerialSetup.java:123-164) build it once; the reference rebuilds it on every call (:1030-1041).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.h"
@@ -25,14 +26,25 @@ void fixed_free_tables(ozk_ctx* ctx) {
     ctx->fixed_tables.clear();
 }
 
-// table window: minimise windows * (scalars + table entries * average build cost), entries = 2^(t-1) per window
-static uint32_t fixed_choose_t(size_t n) {
+// Table window t (signed digits, 2^(t-1) affine entries per window, ceil(255 / t) windows), in units of one mixed addition:
+//   walk  : windows * n             (measured 2^24 scalars: 41.5 ms at t = 16, 34.5 at 20, 32.2 at 22: the walk is bound by
+//                                    the additions, not by the 64-byte gathers, also when the table is 1.6 GB of HBM)
+//   build : 2.7 per entry (one mixed addition and a share of a batched inversion), divided by an assumed reuse of 2 --
+//           the table is cached per (group, base, t) and SerialSetup.generate walks the same G1 table five times
+//           (SerialSetup.java:123-164), every later setup or proof key too
+// capped at t = 22 (12 windows x 2^21 entries = 1.6 GB for G1) and at 4 GB of table.
+static uint32_t fixed_choose_t(size_t n, size_t affine_bytes) {
+    if (const char* e = getenv("OZK_FIXED_T")) {
+        int t = atoi(e);
+        if (t >= 4 && t <= 22) return (uint32_t)t;
+    }
     uint32_t best = 4;
     double best_cost = 1e300;
-    for (uint32_t t = 4; t <= 16; t++) {
+    for (uint32_t t = 4; t <= 22; t++) {
         const double nwin = (255 + t - 1) / t;
         const double entries = (double)(1u << (t - 1));
-        const double cost = nwin * ((double)n + entries * (0.5 * t + 3.0));
+        if (nwin * entries * (double)affine_bytes > 4.0e9) break;
+        const double cost = nwin * ((double)n + entries * (2.7 / 2.0));
         if (cost < best_cost) {
             best_cost = cost;
             best = t;
@@ -57,13 +69,15 @@ static int fixed_get_table(ozk_ctx* ctx, const FixedLaunch& L, int tag, const ui
     const uint32_t nwin = (255 + t - 1) / t;
     const size_t entries = ((size_t)1 << (t - 1)) * nwin;
     // small block: [flag 256 B][base][pow_xyzz 256][pow_aff 256]
-    const size_t small = 256 + 512 + kFixedPowers * (L.xyzz_bytes + L.affine_bytes);
+    const size_t nsub = (size_t)fixed_sub_count(t) * nwin;
+    const size_t small = 256 + 512 + kFixedPowers * (L.xyzz_bytes + L.affine_bytes) + nsub * (L.xyzz_bytes + L.affine_bytes);
     OZK_TRY(ctx->fb[FB_SMALL].reserve(small, st));
     char* sp = (char*)ctx->fb[FB_SMALL].p;
     uint32_t* flag = (uint32_t*)sp;
     void* d_base = sp + 256;
     void* pow_xyzz = sp + 256 + 512;
     void* pow_aff = (char*)pow_xyzz + kFixedPowers * L.xyzz_bytes;
+    void* sub = (char*)pow_aff + kFixedPowers * L.affine_bytes;
     OZK_CUDA(cudaMemsetAsync(flag, 0, 16, st));
     OZK_CUDA(cudaMemcpyAsync(d_base, base, L.jac_bytes, cudaMemcpyHostToDevice, st));
     OZK_TRY(ctx->fb[FB_TABLE_TMP].reserve(entries * L.xyzz_bytes, st));
@@ -79,9 +93,9 @@ static int fixed_get_table(ozk_ctx* ctx, const FixedLaunch& L, int tag, const ui
     int rc = 0;
     rc |= L.powers(st, d_base, pow_xyzz, flag);
     rc |= L.to_affine(st, pow_xyzz, pow_aff, kFixedPowers);
-    rc |= L.table(st, pow_aff, ctx->fb[FB_TABLE_TMP].p, t, nwin);
+    rc |= L.table(st, pow_aff, sub, ctx->fb[FB_TABLE_TMP].p, t, nwin);
     rc |= L.to_affine(st, ctx->fb[FB_TABLE_TMP].p, ft->table_aff, entries);
-    ctx->launches += 4;
+    ctx->launches += 6;
     uint32_t* hflag = (uint32_t*)ctx->pinned;
     cudaError_t e = cudaMemcpyAsync(hflag, flag, 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -110,7 +124,7 @@ static int fixed_run(ozk_ctx* ctx, const FixedLaunch& L, int tag, const uint8_t*
     if (n == 0) return OZK_OK;
     long long bits_ll = (long long)outerc * window;
     const uint32_t bits = (uint32_t)std::min<long long>(bits_ll, 256);
-    const uint32_t t = fixed_choose_t(n);
+    const uint32_t t = fixed_choose_t(n, L.affine_bytes);
     FixedTable* ft;
     OZK_TRY(fixed_get_table(ctx, L, tag, base, t, &ft));
     cudaStream_t st = ctx->stream;

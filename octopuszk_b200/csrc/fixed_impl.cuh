@@ -126,26 +126,50 @@ __global__ void __launch_bounds__(128) xyzz_to_wire_batch(const uint4* __restric
     }
 }
 
-// table_xyzz[k * half + (j-1)] = j * 2^(t k) * B for j in 1..half (half = 2^(t-1)), by binary decomposition of j over
-// the precomputed affine powers (the reference builds its table the same way, algebra_msm_FixedBaseMSM.cu:851-884).
+// table_xyzz[k * half + (j-1)] = j * 2^(t k) * B for j in 1..half (half = 2^(t-1)); the reference builds its table by binary
+// decomposition of every j over the powers of the base (algebra_msm_FixedBaseMSM.cu:851-884), ~t/2 additions per entry.
+// Two-level construction (one addition per entry): j = jl + jh 2^h with h = ceil((t-1)/2).
+//   sub[k][jl]           = jl * 2^(t k) B,        jl < 2^h                 (binary decomposition, a few thousand entries)
+//   sub[k][2^h + jh]     = jh * 2^(h + t k) B,    jh <= 2^(t-1-h)
+// normalised to affine, then table[k][j-1] = sub[k][jl] + sub[k][2^h + jh].
+__host__ __device__ __forceinline__ uint32_t fixed_sub_h(uint32_t t) { return t / 2; }                       // ceil((t-1)/2)
+__host__ __device__ __forceinline__ uint32_t fixed_sub_count(uint32_t t) {
+    const uint32_t h = fixed_sub_h(t);
+    return (1u << h) + (1u << (t - 1 - h)) + 1u;
+}
 template <class F>
-__global__ void __launch_bounds__(128) fixed_table_build(const uint4* __restrict__ pow_aff, uint4* __restrict__ table_xyzz,
-                                                         uint32_t t, uint32_t nwin) {
-    const uint32_t half = 1u << (t - 1);
-    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= (size_t)half * nwin) return;
-    const uint32_t k = (uint32_t)(e >> (t - 1));
-    const uint32_t j = (uint32_t)(e & (half - 1)) + 1;
+__global__ void __launch_bounds__(128) fixed_sub_build(const uint4* __restrict__ pow_aff, uint4* __restrict__ sub_xyzz, uint32_t t, uint32_t nwin) {
+    const uint32_t S = fixed_sub_count(t), h = fixed_sub_h(t);
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= S * nwin) return;
+    const uint32_t k = e / S, se = e % S;
+    const bool hi = se >= (1u << h);
+    const uint32_t j = hi ? se - (1u << h) : se;
+    const uint32_t first = k * t + (hi ? h : 0);
     XYZZ<F> acc = XYZZ<F>::inf();
     for (uint32_t b = 0; b < t; b++) {
         if ((j >> b) & 1) {
-            const uint32_t pw = k * t + b;
+            const uint32_t pw = first + b;
             if (pw < (uint32_t)kFixedPowers) {
                 Affine<F> q = load_affine<F>(pow_aff, pw);
                 xyzz_madd_hot(acc, q);
             }
         }
     }
+    store_xyzz<F>(sub_xyzz, e, acc);
+}
+template <class F>
+__global__ void __launch_bounds__(128) fixed_table_combine(const uint4* __restrict__ sub_aff, uint4* __restrict__ table_xyzz, uint32_t t, uint32_t nwin) {
+    const uint32_t half = 1u << (t - 1), S = fixed_sub_count(t), h = fixed_sub_h(t);
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)half * nwin) return;
+    const uint32_t k = (uint32_t)(e >> (t - 1));
+    const uint32_t j = (uint32_t)(e & (half - 1)) + 1;
+    const Affine<F> lo = load_affine<F>(sub_aff, (size_t)k * S + (j & ((1u << h) - 1)));
+    const Affine<F> hi = load_affine<F>(sub_aff, (size_t)k * S + (1u << h) + (j >> h));
+    XYZZ<F> acc = XYZZ<F>::inf();
+    xyzz_madd_hot(acc, lo);
+    xyzz_madd_hot(acc, hi);
     store_xyzz<F>(table_xyzz, e, acc);
 }
 
@@ -205,7 +229,8 @@ struct FixedLaunch {
     int (*powers)(cudaStream_t, const void* base_canon, void* pow_xyzz, uint32_t* flag);
     int (*to_affine)(cudaStream_t, const void* in_xyzz, void* out_aff, size_t n);
     int (*to_wire)(cudaStream_t, const void* in_xyzz, void* out_wire, size_t n);
-    int (*table)(cudaStream_t, const void* pow_aff, void* table_xyzz, uint32_t t, uint32_t nwin);
+    // sub: scratch of nwin * fixed_sub_count(t) * (xyzz_bytes + affine_bytes) bytes
+    int (*table)(cudaStream_t, const void* pow_aff, void* sub, void* table_xyzz, uint32_t t, uint32_t nwin);
     int (*walk)(cudaStream_t, const void* scalars, size_t n, const void* table_aff, uint32_t t, uint32_t nwin, uint32_t bits,
                 void* out_xyzz, uint32_t* flag);
     size_t affine_bytes, jac_bytes, xyzz_bytes;
@@ -232,9 +257,13 @@ extern const FixedLaunch kFixedG2;
         xyzz_to_wire_batch<F><<<NAME##_batch_grid(n), 128, 0, s>>>((const uint4*)in, (uint4*)out, n, conv_batch_for(n));     \
         return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                                   \
     }                                                                                                                        \
-    static int NAME##_table(cudaStream_t s, const void* pw, void* tb, uint32_t t, uint32_t nwin) {                           \
+    static int NAME##_table(cudaStream_t s, const void* pw, void* sub, void* tb, uint32_t t, uint32_t nwin) {                \
+        const size_t nsub = (size_t)fixed_sub_count(t) * nwin;                                                               \
+        void* sub_aff = (char*)sub + nsub * sizeof(XYZZ<F>);                                                                 \
+        fixed_sub_build<F><<<(unsigned)((nsub + 127) / 128), 128, 0, s>>>((const uint4*)pw, (uint4*)sub, t, nwin);           \
+        if (NAME##_to_affine(s, sub, sub_aff, nsub)) return -1;                                                              \
         size_t total = ((size_t)1 << (t - 1)) * nwin;                                                                        \
-        fixed_table_build<F><<<(unsigned)((total + 127) / 128), 128, 0, s>>>((const uint4*)pw, (uint4*)tb, t, nwin);         \
+        fixed_table_combine<F><<<(unsigned)((total + 127) / 128), 128, 0, s>>>((const uint4*)sub_aff, (uint4*)tb, t, nwin);  \
         return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                                   \
     }                                                                                                                        \
     static int NAME##_walk(cudaStream_t s, const void* sc, size_t n, const void* tb, uint32_t t, uint32_t nwin, uint32_t bits, \
