@@ -4,6 +4,7 @@
 // Test scaffolding only.
 #include <cstdarg>
 #include <cstdio>
+#include <atomic>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -23,7 +24,7 @@ struct Obj {
 };
 
 std::string g_exception;
-int g_live_pins = 0;
+std::atomic<int> g_live_pins{0};   // natives are entered from several threads at once (test_concurrent_executor_threads)
 int g_method_size = 1, g_method_get = 2;
 
 Obj* O(jobject o) { return reinterpret_cast<Obj*>(o); }

@@ -157,3 +157,37 @@ def test_fft_list_of_byte_arrays_and_direct(jvm):
     assert d(jvm.env, None, buf, n, jvm.bytes_(O.le32(omega)), 0) == 0
     out = jvm.read(buf)
     assert [O.from_le(out[32 * i:32 * i + 32]) for i in range(n)] == exp
+
+
+def test_concurrent_executor_threads(jvm):
+    """Spark "Executor task launch worker" threads call the natives concurrently in one JVM (hs_err_pid98479.log:260-272;
+    SURVEY.md section 8b): every thread gets its own context (stream, scratch) inside the shim, results must not mix."""
+    import threading
+    f = jvm.fn("libAlgebraMSMVariableBaseMSM.so", "Java_algebra_msm_VariableBaseMSM_variableBaseSerialMSMNativeHelper", [vp, vp, i32, i32, i32])
+    jobs = []
+    for t in range(6):
+        n = 3000 + 500 * t
+        ks, pool = util.known_dlog_points(O.G1, 64, seed=500 + t, random_z=True)
+        raw = util.rand_scalars_bytes(n, seed=500 + t)
+        bases = util.tiled_bases_bytes(O.G1, pool, n)
+        exp = util.expected_from_dlogs(O.G1, ks, util.column_sums(raw, 64))
+        jobs.append((n, jvm.bytes_(bases.tobytes()), jvm.bytes_(raw.tobytes()), exp))
+    results = [None] * len(jobs)
+
+    def worker(i):
+        n, jb, js, _ = jobs[i]
+        outs = []
+        for _ in range(4):                                   # several calls per thread, interleaving with the others
+            outs.append(jvm.read(f(jvm.env, None, jb, js, n, 1, i)))
+        results[i] = outs
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(len(jobs))]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert jvm.exception() is None
+    for (n, _, _, exp), outs in zip(jobs, results):
+        for out in outs:
+            assert len(out) == 192 and O.G1.equals(O.unpack_g1(out, stride=64)[0], exp)
+    assert jvm.live_pins() == 0

@@ -262,3 +262,25 @@ def test_sum_of_wire_points(ctx):
         assert G.equals(got, exp)
         assert G.is_zero(util.unpack_point(G, ctx.sum_points_dev(grp, d, 0)))
         assert G.equals(util.unpack_point(G, ctx.sum_points_dev(grp, d, 1)), pool[0])
+
+
+@pytest.mark.timeout(900)
+def test_headline_size_2_24_known_dlog(ctx):
+    """BASELINE.json configs[1] at its headline size: 2^24 (scalar, point) pairs, bases tiled from 64 points with known
+    discrete logs (random Z), exact answer (sum_i s_i k_{i mod 64}) G; device-resident entry point, then the same through a
+    persistent key with half of the pairs at an offset."""
+    import torch
+    n = 1 << 24
+    ks, pool = util.known_dlog_points(O.G1, 64, seed=24, random_z=True)
+    raw = util.rand_scalars_bytes(n, seed=24)
+    d_s = torch.from_numpy(raw).cuda()
+    d_b = torch.from_numpy(np.ascontiguousarray(util.tiled_bases_bytes(O.G1, pool, n))).cuda()
+    out = ctx.msm_g1_dev(d_s, d_b, n)
+    exp = util.expected_from_dlogs(O.G1, ks, util.column_sums(raw, 64))
+    assert O.G1.equals(O.unpack_g1(out)[0], exp)
+    key = ctx.upload_bases(1, d_b, n, device=True)
+    half = n // 2
+    out = ctx.msm_keyed(d_s[half:].contiguous(), key, half, first=half, device=True)
+    exp = util.expected_from_dlogs(O.G1, ks, util.column_sums(raw[half:], 64))
+    assert O.G1.equals(O.unpack_g1(out)[0], exp)
+    key.free()

@@ -172,3 +172,35 @@ def test_lagrange_large_interpolates(ctx):
     w4 = pow(omega, m // 4, O.R)
     cols = util.column_sums(raw, 4)
     assert sum(c * pow(w4, j, O.R) for j, c in enumerate(cols)) % O.R == pow(t, m // 4, O.R)
+
+
+@pytest.mark.parametrize("log_n", [24, 26])
+def test_ntt_headline_sizes_device_resident(ctx, log_n):
+    """BASELINE.json's NTT sizes (2^24, and the headline 2^26) through size-independent exact properties, all on the device:
+    forward then inverse transform times n^-1 gives the input back bit for bit; the transform of x plus a unit vector e_j
+    differs from the transform of x by exactly omega^(jk) at sampled k (linearity + delta response)."""
+    import torch
+    n = 1 << log_n
+    g = torch.Generator(device="cuda")
+    g.manual_seed(log_n)
+    x = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device="cuda", generator=g)
+    x[:, 31] &= 0x0F                                  # < 2^252: x + e_j stays canonical without a reduction
+    x[:, 0] &= 0xFE                                   # low bit clear: adding 1 to element j cannot carry
+    omega = O.root_of_unity(n)
+    y = torch.empty_like(x)
+    ctx.ntt_dev(x, y, n, O.le32(omega))
+    back = torch.empty_like(x)
+    ctx.ntt_ex_dev(y, back, n, O.le32(pow(omega, -1, O.R)), None, O.le32(pow(n, -1, O.R)), None)
+    ctx.sync()
+    assert torch.equal(back, x)
+    rng = random.Random(log_n)
+    j = rng.randrange(n)
+    x2 = x.clone()
+    x2[j, 0] |= 1                                     # x2 = x + e_j
+    y2 = torch.empty_like(x)
+    ctx.ntt_dev(x2, y2, n, O.le32(omega))
+    ctx.sync()
+    for k in [0, 1, n - 1, n // 2, j] + [rng.randrange(n) for _ in range(8)]:
+        a = O.from_le(y[k].cpu().numpy().tobytes())
+        b = O.from_le(y2[k].cpu().numpy().tobytes())
+        assert (b - a) % O.R == pow(omega, j * k, O.R), (log_n, k)
