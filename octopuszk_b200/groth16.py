@@ -8,6 +8,7 @@ Mirrors (reference paths under src/main/java/):
   R1CStoQAPRelation        reductions/r1cs_to_qap/R1CStoQAP.java:38-97       (host-side field loops, as in the Java)
   R1CStoQAPWitness         reductions/r1cs_to_qap/R1CStoQAP.java:126-238     (7 transforms on the GPU, device resident)
   R1CSConstruction.serialConstruct  profiler/generation/R1CSConstruction.java:31-110 (synthetic circuit)
+  DistributedProver.prove  zk_proof_systems/zkSNARK/DistributedProver.java:28-167  (prove_distributed: one rank per GPU)
 Every random() is Fp.random(seed 10) as in the reference's Configuration (configuration/Configuration.java:52).
 
 As in the Java, the O(n) field loops (linear-combination evaluation) run on the host; the Lagrange coefficients of the
@@ -220,6 +221,89 @@ class Groth16:
         neg_rs_delta = (rs_delta[0], (-rs_delta[1]) % FQ, rs_delta[2])
         C = self.add(ev_abc, self.mul(A, s), self.mul(B1, r), neg_rs_delta)
         return (A, B2, C), H
+
+
+    # ---- distributed prover
+    def prove_distributed(self, pk, cons, num_inputs, primary: Sequence[int], auxiliary: Sequence[int], group=None, exchange=None):
+        """DistributedProver.prove (zk_proof_systems/zkSNARK/DistributedProver.java:28-167) on the ranks of a torch.distributed
+        group, one GPU each, replacing the Spark RDD plumbing: every rank evaluates the constraints of its cyclic shard of the
+        domain, the seven transforms run sharded (distributed.witness_map_distributed: four-step transforms whose exchange is
+        fused into the kernels), every MSM runs on a contiguous shard of (scalar, base) pairs followed by a gather of the
+        partial sums.  The H coefficients come out in the blocked layout, so each rank pairs them with the matching entries of
+        queryH.  Returns the same ((A, B, C)) on every rank -- the same proof as `prove` -- and this rank's H shard."""
+        import torch.distributed as dist
+
+        from . import distributed as D
+        ctx = self.ctx
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        ops = D.GpuOps(ctx)
+        dev = torch.device("cuda", ctx.device)
+        num_constraints = len(cons)
+        n = SerialFFT(ctx, num_constraints + num_inputs).domainSize
+        assert n % (world * world) == 0
+        m, c = n // world, n // world // world
+        full = list(primary) + list(auxiliary)
+        num_variables = len(full)
+
+        def up(v):
+            return torch.frombuffer(bytearray(b"".join(_le32(x) for x in v)), dtype=torch.uint8).to(dev)
+
+        # this rank's rows of the QAP evaluation vectors: domain index i = rank + world * i2 (R1CStoQAP.java:143-160)
+        A, B, C = [0] * m, [0] * m, [0] * m
+        for i2 in range(m):
+            i = rank + world * i2
+            if i < num_constraints:
+                a, b, cc = cons[i]
+                A[i2], B[i2], C[i2] = self._evaluate(a, full), self._evaluate(b, full), self._evaluate(cc, full)
+            elif i < num_constraints + num_inputs:
+                A[i2] = full[i - num_constraints]
+        h_dev = D.witness_map_distributed(ops, up(A), up(B), up(C), n, group=group, exchange=exchange)
+        ctx.sync()
+        # global coefficient index of local element [k1][t]: k1 * m + rank * c + t (H[n] = 0 contributes nothing)
+        h_index = [k1 * m + rank * c + t for k1 in range(world) for t in range(c)]
+        qh = [pk["queryH"][i] for i in h_index]
+
+        def shard(seq):
+            lo, hi = rank * len(seq) // world, (rank + 1) * len(seq) // world
+            return seq[lo:hi]
+
+        def dmsm(scalars, bases, g2=False):
+            """sum over all ranks of this rank's (scalars, bases): local MSM, gather of the partial sums, one small sum"""
+            k = len(scalars)
+            if g2:
+                local = self.msm.serialMSM(list(scalars), list(bases)) if k else ((0, 0), (1, 0), (0, 0))
+                packed = b"".join(_le32(v) for f in local for v in f)
+            else:
+                local = self.msm.serialMSM(list(scalars), list(bases)) if k else (0, 1, 0)
+                packed = b"".join(_le32(v) for v in local)
+            if world == 1:
+                return local
+            mine = torch.frombuffer(bytearray(packed), dtype=torch.uint8).to(dev)
+            gathered = torch.empty(world * len(packed), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(gathered, mine, group=group)
+            out = ctx.sum_points_dev(2 if g2 else 1, gathered, world)
+            vals = [int.from_bytes(out[32 * i:32 * i + 32], "little") for i in range(len(out) // 32)]
+            return ((vals[0], vals[1]), (vals[2], vals[3]), (vals[4], vals[5])) if g2 else tuple(vals)
+
+        r = s = fr_random()
+        qa, qb = pk["queryA"], pk["queryB"]
+        ev_at = dmsm(shard(full), shard(qa[:num_variables]))
+        ev_b1 = dmsm(shard(full), shard([q[0] for q in qb[:num_variables]]))
+        ev_b2 = dmsm(shard(full), shard([q[1] for q in qb[:num_variables]]), g2=True)
+        hb = h_dev.cpu().numpy().tobytes()
+        h_local = [int.from_bytes(hb[32 * i:32 * i + 32], "little") for i in range(m)]
+        ev_h = dmsm(h_local, qh)
+        num_witness = num_variables - num_inputs
+        ev_w = dmsm(shard(list(auxiliary[:num_witness])), shard(pk["deltaABCG1"][:num_witness]))
+        ev_abc = self.add(ev_w, ev_h)
+        rs_delta = self.mul(pk["deltaG1"], r * s % R)
+        A_pt = self.add(pk["alphaG1"], ev_at, self.mul(pk["deltaG1"], r))
+        B1 = self.add(pk["betaG1"], ev_b1, self.mul(pk["deltaG1"], s))
+        B2 = self.add(pk["betaG2"], ev_b2, self.mul(pk["deltaG2"], s))
+        neg_rs_delta = (rs_delta[0], (-rs_delta[1]) % FQ, rs_delta[2])
+        C_pt = self.add(ev_abc, self.mul(A_pt, s), self.mul(B1, r), neg_rs_delta)
+        return (A_pt, B2, C_pt), h_local
 
 
 FQ = 21888242871839275222246405745257275088696311157297823662689037894645226208583

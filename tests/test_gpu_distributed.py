@@ -195,6 +195,17 @@ def _nccl_worker(rank, world, port, q):
     m_, c_ = n // world, n // world // world
     mine = h_one.view(world, world, c_, 32)[:, rank].contiguous().view(-1)                # [k1][t] of this rank
     assert torch.equal(h_fused, mine)
+    # distributed Groth16 prover (DistributedProver.prove mirrored): the same proof as the serial prover on one GPU
+    from octopuszk_b200.groth16 import Groth16
+    gz = Groth16(ctx)
+    cons, ni, na, prim, aux = Groth16.serial_construct(240, 15)
+    pk, vk, _info = gz.setup(cons, ni, ni + na)
+    (sA, sB, sC), sH = gz.prove(pk, cons, ni, prim, aux)
+    (dA, dB, dC), dH = gz.prove_distributed(pk, cons, ni, prim, aux, exchange=ex)
+    assert O.G1.to_affine(dA) == O.G1.to_affine(sA) and O.G2.to_affine(dB) == O.G2.to_affine(sB) and O.G1.to_affine(dC) == O.G1.to_affine(sC)
+    n_dom = len(sH) - 1
+    m_dom, c_dom = n_dom // world, n_dom // world // world
+    assert dH == [sH[k1 * m_dom + rank * c_dom + t] for k1 in range(world) for t in range(c_dom)]
     ex.close()
     ks, pool = util.known_dlog_points(O.G1, 16, seed=4)
     total = 1 << 12
