@@ -108,5 +108,8 @@ int ctx_enter(ozk_ctx* ctx);
 // stage.cu: uploads from pageable host memory through pinned bounce buffers on helper threads
 bool host_pointer_is_pageable(const void* p);
 int staged_h2d(ozk_ctx* ctx, void* dst, const void* src, size_t bytes, cudaEvent_t after, cudaStream_t consumer);
+int staged_d2h(ozk_ctx* ctx, void* dst, const void* src, size_t bytes, cudaEvent_t after);
+int upload_any(ozk_ctx* ctx, void* dst, const void* src, size_t bytes, cudaStream_t stream);      // ordered on `stream`
+int download_any(ozk_ctx* ctx, void* dst, const void* src, size_t bytes, cudaStream_t stream);    // returns with dst complete
 void stager_free(ozk_ctx* ctx);
 }  // namespace ozk

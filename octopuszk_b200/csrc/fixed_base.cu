@@ -152,11 +152,10 @@ static int fixed_run_host(ozk_ctx* ctx, const FixedLaunch& L, int tag, const uin
     if (n == 0) return OZK_OK;
     OZK_TRY(ctx->fb[FB_SCALARS].reserve(n * 32, ctx->stream));
     OZK_TRY(ctx->io_b.reserve(n * L.jac_bytes, ctx->stream));
-    OZK_CUDA(cudaMemcpyAsync(ctx->fb[FB_SCALARS].p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    // pageable buffers (JNI byte[]) go through the bounce-buffer stager (stage.cu)
+    OZK_TRY(upload_any(ctx, ctx->fb[FB_SCALARS].p, scalars, n * 32, ctx->stream));
     OZK_TRY(fixed_run(ctx, L, tag, base, ctx->fb[FB_SCALARS].p, n, outerc, window, ctx->io_b.p));
-    OZK_CUDA(cudaMemcpyAsync(out, ctx->io_b.p, n * L.jac_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    OZK_CUDA(cudaStreamSynchronize(ctx->stream));
-    return OZK_OK;
+    return download_any(ctx, out, ctx->io_b.p, n * L.jac_bytes, ctx->stream);
 }
 
 }  // namespace ozk

@@ -820,11 +820,9 @@ int ozk_ntt_fr(ozk_ctx* ctx, uint8_t* data, size_t n, const uint8_t omega[32]) {
     OZK_ARG(log_n >= 0 && log_n <= 28, "ozk_ntt_fr: n must be a power of two <= 2^28 (Fr has 2-adicity 28)");
     const size_t bytes = n * 32;
     OZK_TRY(ctx->io_a.reserve(bytes, ctx->stream));
-    OZK_CUDA(cudaMemcpyAsync(ctx->io_a.p, data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    OZK_TRY(upload_any(ctx, ctx->io_a.p, data, bytes, ctx->stream));
     OZK_TRY(ntt_run(ctx, ctx->io_a.p, ctx->io_a.p, log_n, omega));
-    OZK_CUDA(cudaMemcpyAsync(data, ctx->io_a.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    OZK_CUDA(cudaStreamSynchronize(ctx->stream));
-    return OZK_OK;
+    return download_any(ctx, data, ctx->io_a.p, bytes, ctx->stream);
 }
 
 int ozk_fr_scale_dev(ozk_ctx* ctx, const void* d_a, void* d_out, size_t n, const uint8_t b[32]) {
@@ -1009,11 +1007,9 @@ int ozk_fr_scale(ozk_ctx* ctx, const uint8_t* a, size_t n, const uint8_t b[32], 
     if (n == 0) return OZK_OK;
     const size_t bytes = n * 32;
     OZK_TRY(ctx->io_a.reserve(bytes, ctx->stream));
-    OZK_CUDA(cudaMemcpyAsync(ctx->io_a.p, a, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    OZK_TRY(upload_any(ctx, ctx->io_a.p, a, bytes, ctx->stream));
     OZK_TRY(scale_powers(ctx, ctx->io_a.p, ctx->io_a.p, n, b, nullptr));
-    OZK_CUDA(cudaMemcpyAsync(out, ctx->io_a.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    OZK_CUDA(cudaStreamSynchronize(ctx->stream));
-    return OZK_OK;
+    return download_any(ctx, out, ctx->io_a.p, bytes, ctx->stream);
 }
 
 }  // extern "C"

@@ -113,4 +113,79 @@ int staged_h2d(ozk_ctx* ctx, void* dst, const void* src, size_t bytes, cudaEvent
     return OZK_OK;
 }
 
+// dst (host, pageable) <- src (device): the mirror image.  The copies start after `after` (an event recorded after the
+// producer of src; may be null: then the caller has synchronised already).  Returns when dst is complete.
+int staged_d2h(ozk_ctx* ctx, void* dst, const void* src, size_t bytes, cudaEvent_t after) {
+    if (bytes == 0) return OZK_OK;
+    Stager* s;
+    OZK_TRY(stager_get(ctx, &s));
+    const size_t nchunks = (bytes + Stager::kChunk - 1) / Stager::kChunk;
+    const int nthreads = (int)std::min<size_t>(Stager::kThreads, nchunks);
+    cudaError_t err[Stager::kThreads];
+    auto work = [&](int t) {
+        cudaError_t e = cudaSetDevice(ctx->device);
+        if (e == cudaSuccess && after) e = cudaStreamWaitEvent(s->st[t], after, 0);
+        // software pipeline over this thread's chunks: the DMA of chunk i+1 runs while chunk i is copied out of its bounce buffer
+        size_t pend_off[Stager::kBufs] = {}, pend_len[Stager::kBufs] = {};
+        bool pending[Stager::kBufs] = {};
+        int i = 0;
+        auto drain = [&](int b) {
+            if (!pending[b] || e != cudaSuccess) return;
+            e = cudaEventSynchronize(s->ev[t][b]);
+            if (e == cudaSuccess) memcpy((char*)dst + pend_off[b], s->pinned[t][b], pend_len[b]);
+            pending[b] = false;
+        };
+        for (size_t c = (size_t)t; c < nchunks && e == cudaSuccess; c += (size_t)nthreads, i++) {
+            const int b = i % Stager::kBufs;
+            drain(b);                                              // the bounce buffer is free again
+            if (e != cudaSuccess) break;
+            const size_t off = c * Stager::kChunk;
+            const size_t len = std::min(Stager::kChunk, bytes - off);
+            e = cudaMemcpyAsync(s->pinned[t][b], (const char*)src + off, len, cudaMemcpyDeviceToHost, s->st[t]);
+            if (e == cudaSuccess) e = cudaEventRecord(s->ev[t][b], s->st[t]);
+            pend_off[b] = off;
+            pend_len[b] = len;
+            pending[b] = (e == cudaSuccess);
+        }
+        for (int k = 0; k < Stager::kBufs; k++) drain((i + k) % Stager::kBufs);
+        err[t] = e;
+    };
+    std::thread th[Stager::kThreads];
+    for (int t = 1; t < nthreads; t++) th[t] = std::thread(work, t);
+    work(0);
+    for (int t = 1; t < nthreads; t++) th[t].join();
+    for (int t = 0; t < nthreads; t++) {
+        if (err[t] != cudaSuccess) {
+            set_error("staged download: %s", cudaGetErrorString(err[t]));
+            return OZK_ERR_CUDA;
+        }
+    }
+    return OZK_OK;
+}
+
+// convenience for the host-pointer entry points: pick the stager for large pageable buffers, plain async copies otherwise.
+// upload: ordered after everything already on `stream`, and `stream` waits for it.  download: waits for `stream` first and
+// returns with dst complete.
+int upload_any(ozk_ctx* ctx, void* dst, const void* src, size_t bytes, cudaStream_t stream) {
+    if (bytes >= ((size_t)8 << 20) && host_pointer_is_pageable(src)) {
+        Stager* s;
+        OZK_TRY(stager_get(ctx, &s));
+        OZK_CUDA(cudaEventRecord(s->start, stream));
+        return staged_h2d(ctx, dst, src, bytes, s->start, stream);
+    }
+    OZK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
+    return OZK_OK;
+}
+int download_any(ozk_ctx* ctx, void* dst, const void* src, size_t bytes, cudaStream_t stream) {
+    if (bytes >= ((size_t)8 << 20) && host_pointer_is_pageable(dst)) {
+        Stager* s;
+        OZK_TRY(stager_get(ctx, &s));
+        OZK_CUDA(cudaEventRecord(s->start, stream));
+        return staged_d2h(ctx, dst, src, bytes, s->start);
+    }
+    OZK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
+    OZK_CUDA(cudaStreamSynchronize(stream));
+    return OZK_OK;
+}
+
 }  // namespace ozk
