@@ -82,6 +82,13 @@ OZK_API int ozk_fr_mul_sub_dev(ozk_ctx* ctx, const void* d_a, const void* d_b, c
  * setup.  m a power of two <= 2^28, omega a primitive m-th root of unity.  SURVEY.md section 8f row 4. */
 OZK_API int ozk_fr_lagrange_dev(ozk_ctx* ctx, void* d_out, size_t m, const uint8_t t[32], const uint8_t omega[32]);
 
+/* out[i] = sum_k coeff[k] * z[col[k]] over k in [row_ptr[i], row_ptr[i+1]) mod r: the linear combinations a_i, b_i, c_i of all
+ * constraints evaluated at the full assignment z (CSR: row_ptr has rows + 1 uint32 entries, col uint32 indices into z, coeff and
+ * z 32-byte canonical elements) -- the host loop of R1CStoQAP.R1CStoQAPWitness (src/main/java/reductions/r1cs_to_qap/
+ * R1CStoQAP.java:143-160, LinearCombination.evaluate).  At most 4096 rows may have more than 64 terms.  SURVEY.md 8f row 4. */
+OZK_API int ozk_fr_spmv_dev(ozk_ctx* ctx, const void* d_row_ptr, const void* d_col, const void* d_coeff, const void* d_z, size_t rows,
+                            void* d_out);
+
 /* ---- radix-2 NTT over Fr ---------------------------------------------------------------------------------
  * out[k] = sum_j in[j] * omega^(j k), natural order in and out, n a power of two <= 2^28, omega a primitive n-th
  * root of unity.  Replaces FFTAuxiliary.serialRadix2FFT (src/main/java/algebra/fft/FFTAuxiliary.java:60-124) and the

@@ -467,6 +467,56 @@ __global__ void __launch_bounds__(256) fr_lagrange_unit(uint4* __restrict__ out,
     }
 }
 
+// ---- sparse R1CS rows times the assignment ---------------------------------------------------------------------------------
+// out[i] = sum_{k in [row_ptr[i], row_ptr[i+1])} coeff[k] * z[col[k]] mod r: the evaluation of the linear combinations a_i, b_i,
+// c_i of every constraint at the full assignment, the host loop of R1CStoQAP.R1CStoQAPWitness
+// (src/main/java/reductions/r1cs_to_qap/R1CStoQAP.java:143-160 with LinearCombination.evaluate, relations/objects/
+// LinearCombination.java:47-55).  Rows of up to kSpmvShort terms take one thread; longer rows (the reference's synthetic
+// circuit ends with one constraint over all variables, R1CSConstruction.java:91-104) are queued and take one block each.
+static constexpr uint32_t kSpmvShort = 64;
+static constexpr uint32_t kSpmvLongCap = 4096;
+
+__device__ __forceinline__ Fr spmv_term(const uint4* coeff, const uint4* z, const uint32_t* col, size_t k) {
+    return Fr::mul(Fr::to_mont(load_fr(coeff + k * 2)), load_fr(z + (size_t)col[k] * 2));     // canonical coeff * z
+}
+
+__global__ void __launch_bounds__(256) fr_spmv_short(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col, const uint4* __restrict__ coeff,
+                                                     const uint4* __restrict__ z, size_t rows, uint4* __restrict__ out, uint32_t* __restrict__ long_rows,
+                                                     uint32_t* __restrict__ long_count) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    const uint32_t lo = row_ptr[i], hi = row_ptr[i + 1];
+    if (hi - lo > kSpmvShort) {
+        const uint32_t q = atomicAdd(long_count, 1u);
+        if (q < kSpmvLongCap) long_rows[q] = (uint32_t)i;
+        return;
+    }
+    Fr acc = Fr::zero();
+    for (uint32_t k = lo; k < hi; k++) acc = Fr::add(acc, spmv_term(coeff, z, col, k));
+    store_fr(out + i * 2, acc);
+}
+
+__global__ void __launch_bounds__(256) fr_spmv_long(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col, const uint4* __restrict__ coeff,
+                                                    const uint4* __restrict__ z, uint4* __restrict__ out, const uint32_t* __restrict__ long_rows,
+                                                    const uint32_t* __restrict__ long_count) {
+    __shared__ Fr part[256];
+    const uint32_t total = min(*long_count, kSpmvLongCap);
+    for (uint32_t q = blockIdx.x; q < total; q += gridDim.x) {
+        const uint32_t i = long_rows[q];
+        const uint32_t lo = row_ptr[i], hi = row_ptr[i + 1];
+        Fr acc = Fr::zero();
+        for (uint32_t k = lo + threadIdx.x; k < hi; k += blockDim.x) acc = Fr::add(acc, spmv_term(coeff, z, col, k));
+        part[threadIdx.x] = acc;
+        __syncthreads();
+        for (uint32_t s = 128; s >= 1; s >>= 1) {
+            if (threadIdx.x < s) part[threadIdx.x] = Fr::add(part[threadIdx.x], part[threadIdx.x + s]);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) store_fr(out + (size_t)i * 2, part[0]);
+        __syncthreads();
+    }
+}
+
 // ---- small cross-shard DFT (the second step of the multi-GPU transform) ---------------------------------------------------
 // out[k1 * len + j] = sum_{i1 < G} in[i1 * len + j] * omega_G^(i1 k1), G = 2^Q <= 8: one thread per j, all G values in registers.
 template <int Q>
@@ -962,6 +1012,32 @@ int ozk_ntt_fr_scatter_dev(ozk_ctx* ctx, const void* d_in, void* const* peer_out
     sc.pthi = tw->thi;
     for (size_t r = 0; r < groups; r++) sc.peer[r] = (uint4*)peer_out[r];
     return ntt_run(ctx, d_in, nullptr, log_m, omega_local, &sc);
+}
+
+int ozk_fr_spmv_dev(ozk_ctx* ctx, const void* d_row_ptr, const void* d_col, const void* d_coeff, const void* d_z, size_t rows, void* d_out) {
+    OZK_TRY(ctx_enter(ctx));
+    OZK_ARG(rows == 0 || (d_row_ptr && d_col && d_coeff && d_z && d_out), "ozk_fr_spmv_dev: null pointer");
+    OZK_ARG(rows < ((size_t)1 << 31), "ozk_fr_spmv_dev: too many rows");
+    if (rows == 0) return OZK_OK;
+    cudaStream_t st = ctx->stream;
+    OZK_TRY(ctx->io_out.reserve(512 + (size_t)kSpmvLongCap * 4, st));
+    uint32_t* long_count = (uint32_t*)((char*)ctx->io_out.p + 384);
+    uint32_t* long_rows = (uint32_t*)((char*)ctx->io_out.p + 512);
+    OZK_CUDA(cudaMemsetAsync(long_count, 0, 4, st));
+    fr_spmv_short<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>((const uint32_t*)d_row_ptr, (const uint32_t*)d_col, (const uint4*)d_coeff,
+                                                                  (const uint4*)d_z, rows, (uint4*)d_out, long_rows, long_count);
+    fr_spmv_long<<<ctx->sm_count, 256, 0, st>>>((const uint32_t*)d_row_ptr, (const uint32_t*)d_col, (const uint4*)d_coeff, (const uint4*)d_z,
+                                                (uint4*)d_out, long_rows, long_count);
+    ctx->launches += 2;
+    OZK_CUDA(cudaGetLastError());
+    uint32_t* pin = (uint32_t*)ctx->pinned;
+    OZK_CUDA(cudaMemcpyAsync(pin, long_count, 4, cudaMemcpyDeviceToHost, st));
+    OZK_CUDA(cudaStreamSynchronize(st));
+    if (pin[0] > kSpmvLongCap) {
+        set_error("ozk_fr_spmv_dev: more than %u rows with over %u terms", kSpmvLongCap, kSpmvShort);
+        return OZK_ERR_ARG;
+    }
+    return OZK_OK;
 }
 
 int ozk_fr_lagrange_dev(ozk_ctx* ctx, void* d_out, size_t m, const uint8_t t[32], const uint8_t omega[32]) {

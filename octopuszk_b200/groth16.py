@@ -11,8 +11,8 @@ Mirrors (reference paths under src/main/java/):
   DistributedProver.prove  zk_proof_systems/zkSNARK/DistributedProver.java:28-167  (prove_distributed: one rank per GPU)
 Every random() is Fp.random(seed 10) as in the reference's Configuration (configuration/Configuration.java:52).
 
-As in the Java, the O(n) field loops (linear-combination evaluation) run on the host; the Lagrange coefficients of the
-setup come from the GPU (ozk_fr_lagrange_dev); all group
+The O(n) field loops of the Java also run on the GPU where they sit on the path: the constraint rows times the assignment
+(ozk_fr_spmv_dev) in the prover and the Lagrange coefficients (ozk_fr_lagrange_dev) in the setup; all group
 arithmetic and all transforms go through liboctozk.  Single scalar multiplications and additions of the Java
 (AbstractGroup.mul / add, SerialProver.java:67,106-114) are issued as tiny MSMs."""
 from __future__ import annotations
@@ -111,6 +111,19 @@ class Groth16:
             acc += val * assignment[idx]
         return acc % R
 
+    @staticmethod
+    def _csr(rows):
+        """CSR arrays (row_ptr, col, coefficient list) of a list of linear combinations [(index, value), ...]."""
+        import numpy as np
+        row_ptr = np.zeros(len(rows) + 1, dtype=np.uint32)
+        cols, coeffs = [], []
+        for i, lc in enumerate(rows):
+            for idx, val in lc:
+                cols.append(idx)
+                coeffs.append(val % R)
+            row_ptr[i + 1] = len(cols)
+        return row_ptr, np.asarray(cols if cols else [0], dtype=np.uint32), coeffs
+
     def r1cs_to_qap_relation(self, cons, num_inputs, num_variables, t):
         num_constraints = len(cons)
         dom = SerialFFT(self.ctx, num_constraints + num_inputs)
@@ -140,21 +153,22 @@ class Groth16:
         dom = SerialFFT(ctx, num_constraints + num_inputs)
         n = dom.domainSize
         full = list(primary) + list(auxiliary)
-        A, B, C = [0] * n, [0] * n, [0] * n
-        for i in range(num_inputs):
-            A[i + num_constraints] = full[i]
-        for i, (a, b, c) in enumerate(cons):
-            A[i] = (self._evaluate(a, full) + A[i]) % R
-            B[i] = self._evaluate(b, full)
-            C[i] = self._evaluate(c, full)
         dev = torch.device("cuda", ctx.device)
 
         def up(v):
             return torch.frombuffer(bytearray(b"".join(_le32(x) for x in v)), dtype=torch.uint8).to(dev)
 
+        # a_i, b_i, c_i = <row i, assignment> on the GPU (ozk_fr_spmv_dev; R1CStoQAP.java:143-160), inputs appended to A (:151-153)
+        d_z = up(full)
+        dA, dB, dC = (torch.zeros(n * 32, dtype=torch.uint8, device=dev) for _ in range(3))
+        for which, d in ((0, dA), (1, dB), (2, dC)):
+            rp, col, cf = self._csr([c[which] for c in cons])
+            ctx.fr_spmv_dev(torch.from_numpy(rp).to(dev), torch.from_numpy(col).to(dev), up(cf) if cf else torch.zeros(32, dtype=torch.uint8, device=dev),
+                            d_z, num_constraints, d)
+        dA.view(n, 32)[num_constraints:num_constraints + num_inputs] = d_z.view(-1, 32)[:num_inputs]
+
         w, winv = _le32(dom.omega), _le32(pow(dom.omega, -1, R))
         ninv = _le32(pow(n, -1, R))
-        dA, dB, dC = up(A), up(B), up(C)
         for d in (dA, dB, dC):
             ctx.ntt_ex_dev(d, d, n, winv, None, ninv, None)                 # radix2InverseFFT
             ctx.ntt_ex_dev(d, d, n, w, _le32(g), None, None)                # radix2CosetFFT

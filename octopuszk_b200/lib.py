@@ -43,6 +43,7 @@ SIGNATURES = {
     "ozk_fr_scale_dev": (_int, [_vp, _vp, _vp, _sz, _c_u8p]),
     "ozk_fr_scale_powers_dev": (_int, [_vp, _vp, _vp, _sz, _c_u8p, _c_u8p, ctypes.c_uint64]),
     "ozk_fr_mul_sub_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _sz]),
+    "ozk_fr_spmv_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ozk_fr_lagrange_dev": (_int, [_vp, _vp, _sz, _c_u8p, _c_u8p]),
     "ozk_ntt_fr_scatter_dev": (_int, [_vp, _vp, ctypes.POINTER(_vp), _sz, _sz, _sz, _c_u8p, _c_u8p]),
     "ozk_fr_dft_small_scatter_dev": (_int, [_vp, _vp, ctypes.POINTER(_vp), _sz, _sz, _sz, _c_u8p, _c_u8p]),
@@ -212,6 +213,9 @@ class Context:
 
     def fr_mul_sub_dev(self, d_a, d_b, d_c, d_out, n: int):
         self._check(self.lib.ozk_fr_mul_sub_dev(self._h, _ptr(d_a), _ptr(d_b), _ptr(d_c) if d_c is not None else None, _ptr(d_out), n))
+
+    def fr_spmv_dev(self, d_row_ptr, d_col, d_coeff, d_z, rows: int, d_out):
+        self._check(self.lib.ozk_fr_spmv_dev(self._h, _ptr(d_row_ptr), _ptr(d_col), _ptr(d_coeff), _ptr(d_z), rows, _ptr(d_out)))
 
     def fr_lagrange_dev(self, d_out, m: int, t: bytes, omega: bytes):
         self._check(self.lib.ozk_fr_lagrange_dev(self._h, _ptr(d_out), m, t, omega))

@@ -204,3 +204,33 @@ def test_ntt_headline_sizes_device_resident(ctx, log_n):
         a = O.from_le(y[k].cpu().numpy().tobytes())
         b = O.from_le(y2[k].cpu().numpy().tobytes())
         assert (b - a) % O.R == pow(omega, j * k, O.R), (log_n, k)
+
+
+def test_sparse_rows_times_assignment(ctx):
+    """ozk_fr_spmv_dev against LinearCombination.evaluate restated: empty rows, single terms, rows at and above the
+    one-thread limit (64 terms), one row over all variables (the last constraint of R1CSConstruction.serialConstruct)."""
+    import numpy as np
+    import torch
+    rng = random.Random(77)
+    nvars = 5000
+    z = [rng.randrange(O.R) for _ in range(nvars)]
+    z[0] = 1
+    lengths = [0, 1, 2, 64, 65, 300, nvars, 3, 0, 1000] + [rng.randrange(0, 5) for _ in range(2000)]
+    rows = []
+    for L in lengths:
+        idx = rng.sample(range(nvars), L) if L < nvars else list(range(nvars))
+        rows.append([(i, rng.choice([1, 1, O.R - 1, rng.randrange(O.R)])) for i in idx])
+    row_ptr = np.zeros(len(rows) + 1, dtype=np.uint32)
+    cols, coeffs = [], []
+    for i, lc in enumerate(rows):
+        for j, v in lc:
+            cols.append(j)
+            coeffs.append(v)
+        row_ptr[i + 1] = len(cols)
+    d_out = torch.empty(len(rows) * 32, dtype=torch.uint8, device="cuda")
+    ctx.fr_spmv_dev(torch.from_numpy(row_ptr).cuda(), torch.from_numpy(np.asarray(cols, dtype=np.uint32)).cuda(),
+                    torch.frombuffer(bytearray(O.pack_scalars(coeffs)), dtype=torch.uint8).cuda(),
+                    torch.frombuffer(bytearray(O.pack_scalars(z)), dtype=torch.uint8).cuda(), len(rows), d_out)
+    got = d_out.cpu().numpy().tobytes()
+    exp = [sum(v * z[j] for j, v in lc) % O.R for lc in rows]
+    assert [O.from_le(got[32 * i:32 * i + 32]) for i in range(len(rows))] == exp
