@@ -28,8 +28,9 @@
 namespace ozk {
 
 static constexpr int kMaxLogT = 9;          // largest in-CTA transform: 512 points
-// Tile of 1024 elements (32 KB) per 128-thread CTA: four CTAs per SM whose load / transform / store phases interleave
-// (measured 2^26: 16.3 ms with 2048-element tiles and two CTAs per SM, 15.9 ms with 1024).
+// Tile of 1024 elements (32 KB) per 128-thread CTA, five CTAs per SM (__launch_bounds__(128, 5): 96 registers, ~100 bytes of
+// spills) whose load / transform / store phases interleave (measured 2^26: 16.3 ms with 2048-element tiles and two CTAs per SM,
+// 15.9 ms with 1024-element tiles and four, 14.7 ms with five together with the direct twiddle tables below).
 static constexpr int kTileLogDefault = 10;
 // Largest inter-pass twiddle range that gets a direct table: 2^26 entries = 2 GiB per (n, omega) plan.  HBM is < 10 % busy in
 // these passes, so one more 32-byte read per element is free, and it replaces the product of two table entries (one of the
@@ -257,7 +258,7 @@ __device__ __forceinline__ void run_step(uint4* lo, uint4* hi, const Fr* wtab, u
 }
 
 template <bool LAST>
-__global__ void __launch_bounds__(256, 2) ntt_pass_kernel(PassArgs a) {
+__global__ void __launch_bounds__(128, 5) ntt_pass_kernel(PassArgs a) {
     extern __shared__ uint4 smem[];
     const uint32_t LOGT = a.log_t;
     const uint32_t T = 1u << LOGT;
@@ -742,7 +743,7 @@ static int ntt_run(ozk_ctx* ctx, const void* d_in, void* d_out, int log_n, const
         a.log_outer = log_n - lt - log_inner;
         a.log_t = lt;
         if (!last) {
-            int lc = env_int("OZK_NTT_TILE_LOG", kTileLogDefault, 9, 11) - lt;
+            int lc = env_int("OZK_NTT_TILE_LOG", kTileLogDefault, 9, 10) - lt;
             if (lc > log_inner) lc = log_inner;
             a.log_c = lc;
             uint32_t grid = 1u << (log_n - lt - lc);
@@ -752,7 +753,7 @@ static int ntt_run(ozk_ctx* ctx, const void* d_in, void* d_out, int log_n, const
             a.nmid = p->npass > 2 ? p->npass - 2 : 0;
             a.logmid0 = a.nmid > 0 ? p->logt[1] : 0;
             a.logmid1 = a.nmid > 1 ? p->logt[2] : 0;
-            int lc = env_int("OZK_NTT_TILE_LOG", kTileLogDefault, 9, 11) - lt;
+            int lc = env_int("OZK_NTT_TILE_LOG", kTileLogDefault, 9, 10) - lt;
             if (lc > (int)a.log_n1) lc = a.log_n1;
             a.log_c = lc;
             if (sc) {
