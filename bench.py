@@ -303,7 +303,12 @@ def run_ours(args):
         t0 = time.perf_counter()
         C.msm_g1(sb, bb, m, threads)
         sec = time.perf_counter() - t0
+        m1 = min(m, 1 << 17)
+        t1 = time.perf_counter()
+        C.msm_g1(raw[:m1].tobytes(), bases[:m1].tobytes(), m1, 1)
+        sec1 = time.perf_counter() - t1
         cpu = {"value": m / sec, "unit": "points/s", "cores": threads, "kind": "port",
+               "single_thread": {"value": m1 / sec1, "unit": "points/s", "sample": f"first 2^{m1.bit_length() - 1} pairs, one thread"},
                "sample": f"first 2^{ls} pairs of the workload, C restatement of VariableBaseMSM.pippengerMSM per thread + reduce(add); "
                          "the reference's Java cannot run here (no JVM)"}
 
