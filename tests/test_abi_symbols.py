@@ -63,3 +63,37 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cc")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "dizk_oracle" not in src and "c_oracle" not in src and "from oracle" not in src, os.path.join(dirpath, f)
+
+
+def test_shims_cover_the_reference_javah_headers(built):
+    """Every native the reference's javah headers declare (algebra_msm_VariableBaseMSM.h, algebra_msm_FixedBaseMSM.h,
+    algebra_fft_FFTAuxiliary.h: name, return type and JNI signature) is exported by the shim library the Java loads for that
+    class, with the same parameter list in jni_shim.cc.  Needs the reference tree (the build container has it; skipped on
+    the GPU box)."""
+    ref = "/root/reference"
+    headers = {"algebra_msm_VariableBaseMSM.h": "libAlgebraMSMVariableBaseMSM.so", "algebra_msm_FixedBaseMSM.h": "libAlgebraMSMFixedBaseMSM.so",
+               "algebra_fft_FFTAuxiliary.h": "libAlgebraFFTAuxiliary.so"}
+    if not all(os.path.exists(os.path.join(ref, h)) for h in headers):
+        pytest.skip("reference tree not mounted")
+    shim_src = open(os.path.join(ROOT, "octopuszk_b200", "csrc", "jni", "jni_shim.cc")).read()
+    libdir = os.path.join(ROOT, "octopuszk_b200", "lib")
+    jni_letter = {"jbyteArray": "[B", "jint": "I", "jobject": "L", "jlong": "J"}
+    total = 0
+    for hdr, lib in headers.items():
+        text = open(os.path.join(ref, hdr)).read()
+        decls = re.findall(r"Signature:\s*(\S+)\s*\*/\s*JNIEXPORT\s+(\w+)\s+JNICALL\s+(Java_\w+)\s*\(([^)]*)\)", text)
+        assert decls, hdr
+        so = ctypes.CDLL(os.path.join(libdir, lib))
+        for sig, ret, name, params in decls:
+            total += 1
+            assert hasattr(so, name), (lib, name)
+            m = re.search(r"JNIEXPORT\s+(\w+)\s+JNICALL\s+" + name + r"\s*\(([^)]*)\)", shim_src)
+            assert m, name
+            assert m.group(1) == ret, (name, m.group(1), ret)
+            ours = [p.strip().split()[0].rstrip("*") for p in m.group(2).split(",")]
+            theirs = [p.strip().split()[0].rstrip("*") for p in params.split(",")]
+            assert ours == theirs, (name, ours, theirs)
+            # and the declared JNI signature agrees with that parameter list (after JNIEnv*, jclass)
+            letters = "".join(jni_letter[t] if t != "jobject" else "Ljava/util/List;" for t in theirs[2:])
+            assert sig.startswith("(" + letters + ")"), (name, sig, letters)
+    assert total == 6
