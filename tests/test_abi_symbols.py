@@ -97,3 +97,24 @@ def test_shims_cover_the_reference_javah_headers(built):
             letters = "".join(jni_letter[t] if t != "jobject" else "Ljava/util/List;" for t in theirs[2:])
             assert sig.startswith("(" + letters + ")"), (name, sig, letters)
     assert total == 6
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/octozk.h is the C ABI: it must compile as C99 (no C++ types, no torch types), and a C caller can link
+    against liboctozk.so (link check only; nothing is executed)."""
+    import subprocess
+    src = tmp_path / "caller.c"
+    src.write_text('#include "octozk.h"\n'
+                   "int main(void) {\n"
+                   "    ozk_ctx* c = 0; uint8_t out[96]; ozk_bases* k = 0;\n"
+                   "    if (ozk_device_count() <= 0) return 0;\n"
+                   "    if (ozk_ctx_create(0, &c) != OZK_OK) return 1;\n"
+                   "    ozk_msm_g1(c, 0, 0, 0, out);\n"
+                   "    ozk_bases_free(c, k);\n"
+                   "    ozk_ctx_destroy(c);\n"
+                   "    return 0;\n}\n")
+    inc = os.path.join(ROOT, "include")
+    libdir = os.path.join(ROOT, "octopuszk_b200", "lib")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", inc, "-c", str(src), "-o", str(tmp_path / "caller.o")])
+    subprocess.check_call(["gcc", str(tmp_path / "caller.o"), "-o", str(tmp_path / "caller"), "-L", libdir, "-loctozk", "-Wl,-rpath," + libdir,
+                           "-Wl,--unresolved-symbols=ignore-in-shared-libs"])
