@@ -511,7 +511,28 @@ static int msm_run_host(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* b1,
     else if (n >= ((size_t)1 << 20)) nslices = 4;
     else if (n >= ((size_t)1 << 18)) nslices = 2;
     if (const char* e = getenv("OZK_HOST_SLICES")) nslices = std::max(1, std::min(kCopyChunks, atoi(e)));
-    const size_t slice = (n + nslices - 1) / nslices;
+    // Slice lengths grow geometrically (x1.3, the ratio of compute to copy time per pair): the first slice is small, so the GPU
+    // starts after ~4 % of the copy instead of 1/8 of it, and every later copy still lands before the compute of the slices
+    // before it has finished.  OZK_HOST_SLICE_GROWTH=1 gives equal slices.
+    size_t bounds[kCopyChunks + 1];
+    {
+        double growth = 1.3;
+        if (const char* e = getenv("OZK_HOST_SLICE_GROWTH")) growth = std::max(1.0, atof(e));
+        double total = 0, w = 1;
+        for (int k = 0; k < nslices; k++, w *= growth) total += w;
+        double acc = 0;
+        w = 1;
+        bounds[0] = 0;
+        for (int k = 0; k < nslices; k++, w *= growth) {
+            acc += w;
+            size_t b = (size_t)((double)n * acc / total);
+            b = (b + 255) & ~(size_t)255;
+            bounds[k + 1] = (k + 1 == nslices) ? n : std::min(b, n);
+            if (bounds[k + 1] < bounds[k]) bounds[k + 1] = bounds[k];
+        }
+    }
+    size_t slice = 0;                                    // the longest slice sizes the per-slice scratch
+    for (int k = 0; k < nslices; k++) slice = std::max(slice, bounds[k + 1] - bounds[k]);
     OZK_TRY(ctx->io_a.reserve(n * 32, st));
     if (b1) OZK_TRY(ctx->io_b.reserve(n * 96, st));
     if (b2) OZK_TRY(ctx->io_c.reserve(n * 192, st));
@@ -541,9 +562,10 @@ static int msm_run_host(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* b1,
     ctx->msm_stats[0] = sh.c;
     ctx->msm_stats[1] = sh.nwin;
     ctx->msm_stats[2] = sh.nb;
-    int k = 0;
-    for (size_t lo = 0; lo < n; lo += slice, k++) {
-        const size_t len = std::min(slice, n - lo);
+    bool first = true;
+    for (int k = 0; k < nslices; k++) {
+        const size_t lo = bounds[k], len = bounds[k + 1] - bounds[k];
+        if (len == 0) continue;
         OZK_TRY(upload((char*)ctx->io_a.p + lo * 32, scalars + lo * 32, len * 32, page_s));
         if (b1) OZK_TRY(upload((char*)ctx->io_b.p + lo * 96, b1 + lo * 96, len * 96, page_1));
         if (b2) OZK_TRY(upload((char*)ctx->io_c.p + lo * 192, b2 + lo * 192, len * 192, page_2));
@@ -553,12 +575,13 @@ static int msm_run_host(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* b1,
         OZK_TRY(msm_sort(ctx, (char*)ctx->io_a.p + lo * 32, len, sh));
         if (s1.any()) {
             BaseSrc b = {s1.wire ? (const char*)s1.wire + lo * kMsmG1.jac_bytes : nullptr, s1.affine ? (const char*)s1.affine + lo * kMsmG1.affine_bytes : nullptr};
-            OZK_TRY(msm_accumulate_phase(ctx, kMsmG1, b, len, sh, B_AFF1, B_BUCKETS, k != 0));
+            OZK_TRY(msm_accumulate_phase(ctx, kMsmG1, b, len, sh, B_AFF1, B_BUCKETS, !first));
         }
         if (s2.any()) {
             BaseSrc b = {s2.wire ? (const char*)s2.wire + lo * kMsmG2.jac_bytes : nullptr, s2.affine ? (const char*)s2.affine + lo * kMsmG2.affine_bytes : nullptr};
-            OZK_TRY(msm_accumulate_phase(ctx, kMsmG2, b, len, sh, B_AFF2, B_BUCKETS2, k != 0));
+            OZK_TRY(msm_accumulate_phase(ctx, kMsmG2, b, len, sh, B_AFF2, B_BUCKETS2, !first));
         }
+        first = false;
     }
     size_t bytes = 0;
     if (s1.any()) {
