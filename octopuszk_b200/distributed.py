@@ -109,11 +109,13 @@ def msm_distributed(ops, scalars_local, bases_local, n_local: int, g2: bool = Fa
 class PeerExchange:
     """The receive buffers of all ranks of one node, mapped into this process (cudaMalloc + CUDA IPC through
     ozk_peer_alloc / ozk_peer_open), for the fused exchange of `ntt_distributed`.  One instance serves transforms of up
-    to `nbytes` bytes per rank; the torch current stream must be the context's stream (Context(stream=...)), so that the
-    NCCL barriers below order the kernels of all ranks on the device, without host synchronisation."""
+    to `nbytes` bytes per rank.  The barriers below must order the KERNELS of all ranks: with stream_ordered=True the caller
+    guarantees that the context runs on the torch current stream (Context(stream=torch.cuda.current_stream().cuda_stream)),
+    so the NCCL all_reduce enqueued on that stream is a device-side barrier and nothing synchronises with the host; otherwise
+    (default, any context) each barrier also drains the context's stream and the torch stream on the host."""
 
-    def __init__(self, ctx, nbytes: int, group=None):
-        self.ctx, self.group, self.nbytes = ctx, group, nbytes
+    def __init__(self, ctx, nbytes: int, group=None, stream_ordered: bool = False):
+        self.ctx, self.group, self.nbytes, self.stream_ordered = ctx, group, nbytes, stream_ordered
         self.world, self.rank = _world(group), _rank(group)
         dev = torch.device("cuda", ctx.device)
         self.ptr, handle = ctx.peer_alloc(nbytes)
@@ -125,9 +127,13 @@ class PeerExchange:
         self._token = torch.zeros(1, dtype=torch.int32, device=dev)
 
     def barrier(self):
-        """Stream-ordered barrier over the ranks: every kernel enqueued before it, on every rank, completes before any
-        kernel enqueued after it starts (a 4-byte all_reduce on the current stream)."""
+        """Barrier over the ranks: every kernel enqueued before it, on every rank, completes before any kernel enqueued after
+        it starts (a 4-byte all_reduce; see the class docstring for the two modes)."""
+        if not self.stream_ordered:
+            self.ctx.sync()
         dist.all_reduce(self._token, group=self.group)
+        if not self.stream_ordered:
+            torch.cuda.current_stream().synchronize()
 
     def close(self):
         self.barrier()

@@ -174,12 +174,15 @@ def _nccl_worker(rank, world, port, q):
     x = [rng.randrange(O.R) for _ in range(n)]
     omega = O.root_of_unity(n)
     shard = ops.to_device(D.ntt_scatter_cyclic(O.pack_scalars(x), world, rank))
-    ex = D.PeerExchange(ctx, shard.numel())
+    ex = D.PeerExchange(ctx, shard.numel(), stream_ordered=True)        # ctx runs on the torch current stream
     fused = D.ntt_distributed(ops, shard, n, omega, exchange=ex)             # peer stores over NVLink, input preserved
     fused2 = D.ntt_distributed(ops, shard, n, omega, exchange=ex)            # receive buffers are reusable
+    ex_any = D.PeerExchange(ctx, shard.numel())                              # default mode: host-synchronising barriers, any context
+    fused3 = D.ntt_distributed(ops, shard, n, omega, exchange=ex_any)
+    ex_any.close()
     out = D.ntt_distributed(ops, shard, n, omega)                            # NCCL all_to_all form (overwrites shard)
     torch.cuda.synchronize()
-    assert torch.equal(fused, out) and torch.equal(fused2, out)
+    assert torch.equal(fused, out) and torch.equal(fused2, out) and torch.equal(fused3, out)
     # sharded R1CStoQAPWitness chain: fused exchange == NCCL form == the single-GPU chain on the whole vectors
     import numpy as np
     R_, g_ = O.R, O.FR_MULT_GEN

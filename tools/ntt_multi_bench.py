@@ -47,7 +47,7 @@ for log_n in [int(a) for a in sys.argv[1:]] or [26, 28]:
         k = rank * c + 5
         got = O.from_le(out[32 * 5:32 * 6].cpu().numpy().tobytes())
         assert got == pow(omega, j * k, O.R), "distributed NTT delta response mismatch"
-    ex = D.PeerExchange(ctx, m * 32) if world > 1 else None
+    ex = D.PeerExchange(ctx, m * 32, stream_ordered=True) if world > 1 else None
     if ex is not None and log_n <= 26:
         a1 = D.ntt_distributed(ops, x, n, omega, exchange=ex)
         a2 = D.ntt_distributed(ops, x.clone(), n, omega)

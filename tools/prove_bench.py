@@ -63,7 +63,7 @@ for log_m in [int(a) for a in sys.argv[1:]] or [20]:
     nloc = n // world if sharded else n  # elements of A, B, C this rank holds (its cyclic shard, or everything)
     A0, B0, C0 = rand_fr(nloc, 11 + 100 * rank), rand_fr(nloc, 12 + 100 * rank), rand_fr(nloc, 13 + 100 * rank)
     A, B, C = A0.clone(), B0.clone(), C0.clone()
-    ex = D.PeerExchange(ctx, nloc * 32) if sharded else None
+    ex = D.PeerExchange(ctx, nloc * 32, stream_ordered=True) if sharded else None
     omega = O.root_of_unity(n)
     wf, wi = O.le32(omega), O.le32(pow(omega, -1, R))
     ninv, g = O.le32(pow(n, -1, R)), O.FR_MULT_GEN
