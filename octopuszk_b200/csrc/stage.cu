@@ -63,6 +63,27 @@ static int stager_get(ozk_ctx* ctx, Stager** out) {
     return OZK_OK;
 }
 
+// work(0) on the calling thread, work(1..n-1) on helper threads; a helper that cannot be started (thread limit reached)
+// has its share run inline instead -- no exception may cross the C ABI.
+template <class W>
+static void run_on_threads(W& work, int nthreads) {
+    std::thread th[Stager::kThreads];
+    bool started[Stager::kThreads] = {};
+    for (int t = 1; t < nthreads; t++) {
+        try {
+            th[t] = std::thread([&work, t] { work(t); });
+            started[t] = true;
+        } catch (...) {
+            started[t] = false;
+        }
+    }
+    work(0);
+    for (int t = 1; t < nthreads; t++) {
+        if (started[t]) th[t].join();
+        else work(t);
+    }
+}
+
 bool host_pointer_is_pageable(const void* p) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
@@ -99,10 +120,7 @@ int staged_h2d(ozk_ctx* ctx, void* dst, const void* src, size_t bytes, cudaEvent
         if (e == cudaSuccess) e = cudaEventRecord(s->done[t], s->st[t]);
         err[t] = e;
     };
-    std::thread th[Stager::kThreads];
-    for (int t = 1; t < nthreads; t++) th[t] = std::thread(work, t);
-    work(0);
-    for (int t = 1; t < nthreads; t++) th[t].join();
+    run_on_threads(work, nthreads);
     for (int t = 0; t < nthreads; t++) {
         if (err[t] != cudaSuccess) {
             set_error("staged upload: %s", cudaGetErrorString(err[t]));
@@ -150,10 +168,7 @@ int staged_d2h(ozk_ctx* ctx, void* dst, const void* src, size_t bytes, cudaEvent
         for (int k = 0; k < Stager::kBufs; k++) drain((i + k) % Stager::kBufs);
         err[t] = e;
     };
-    std::thread th[Stager::kThreads];
-    for (int t = 1; t < nthreads; t++) th[t] = std::thread(work, t);
-    work(0);
-    for (int t = 1; t < nthreads; t++) th[t].join();
+    run_on_threads(work, nthreads);
     for (int t = 0; t < nthreads; t++) {
         if (err[t] != cudaSuccess) {
             set_error("staged download: %s", cudaGetErrorString(err[t]));
