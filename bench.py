@@ -93,6 +93,10 @@ def _make_inputs(n, seed, random_z=True):
     from tests import util
     ks, pool = util.known_dlog_points(O.G1, 64, seed=seed, random_z=random_z)
     raw = util.rand_scalars_bytes(n, seed=seed)
+    # forced edge entries at fixed positions: 0, 1, r - 1, and the digit boundaries of the 16/17-bit windows
+    for pos, val in enumerate([0, 1, O.R - 1, 1 << 16, (1 << 16) + 1, (1 << 17) - 1, 1 << 17, (1 << 253) - 1]):
+        if pos < n:
+            raw[pos] = np.frombuffer(O.le32(val), dtype=np.uint8)
     bases = np.ascontiguousarray(util.tiled_bases_bytes(O.G1, pool, n))
     expected = util.expected_from_dlogs(O.G1, ks, util.column_sums(raw, 64))
     return raw, bases, expected
