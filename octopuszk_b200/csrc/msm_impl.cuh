@@ -8,7 +8,7 @@
 //   scatter  : counting-sort the point indices of every window by bucket                     [msm.cu]
 //   accumulate : one thread per (window, bucket) adds its run of points into an XYZZ accumulator (mixed add 8M+2S);
 //                runs longer than SEG are split into extra tasks and merged by a warp-cooperative reduction
-//   reduce   : sum_b (b+1) * B_b per window by a 32-ary hierarchy of running sums (all windows in parallel)
+//   reduce   : sum_b (b+1) * B_b per window by an 8-ary hierarchy of running sums (kWsumS; all windows in parallel)
 //   final    : Horner over the windows, conversion to the canonical Jacobian wire format
 #pragma once
 #include "curve.cuh"
