@@ -42,6 +42,7 @@ extern "C" {
 #define OZK_ERR_DOMAIN (-3) /* omega is not a primitive n-th root of unity, value not reduced, ... */
 
 typedef struct ozk_ctx ozk_ctx;
+typedef struct ozk_bases ozk_bases; /* persistent device-resident bases, see below */
 
 /* ---- context -------------------------------------------------------------------------------------------
  * One context per calling thread and device: own stream, scratch arena and caches, so concurrent JVM executor
@@ -51,7 +52,12 @@ typedef struct ozk_ctx ozk_ctx;
 OZK_API int ozk_device_count(void);
 OZK_API int ozk_ctx_create(int device, ozk_ctx** out);
 OZK_API void ozk_ctx_destroy(ozk_ctx* ctx);
-/* use an externally owned cudaStream_t (e.g. the caller's current stream) for all later work */
+/* Use an externally owned cudaStream_t (e.g. the caller's current stream) for all later work.  Work already enqueued by this
+ * context is ordered before it (the new stream waits for the old one on the device).
+ * STREAM CONTRACT of every "_dev" entry point: it only ENQUEUES on the context's stream.  Buffers written by the caller on
+ * another stream must be ordered before the call, and results must be ordered before the caller reads them, by the caller:
+ * either make the context run on the caller's stream with this function, or synchronise explicitly (ozk_ctx_sync).  The
+ * Python binding does the former automatically whenever it is handed a CUDA torch tensor (octopuszk_b200/lib.py). */
 OZK_API int ozk_ctx_set_stream(ozk_ctx* ctx, void* cuda_stream);
 OZK_API int ozk_ctx_sync(ozk_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py reports the per-step delta as gpu_launches) */
@@ -151,6 +157,26 @@ OZK_API int ozk_msm_g2(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* base
 OZK_API int ozk_msm_g2_dev(ozk_ctx* ctx, const void* d_scalars, const void* d_bases, size_t n, uint8_t out[192]);
 OZK_API int ozk_msm_g1g2(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* bases1, const uint8_t* bases2, size_t n, uint8_t out[288]);
 OZK_API int ozk_msm_g1g2_dev(ozk_ctx* ctx, const void* d_scalars, const void* d_bases1, const void* d_bases2, size_t n, uint8_t out[288]);
+/* Streaming form of the host-pointer MSM (what ozk_msm_g1 / _g2 / _g1g2 and the keyed forms do internally): announce the total,
+ * feed the (scalar, point) pairs in slices, collect the result.  groups: 1 = G1, 2 = G2, 3 = both on the same scalars.
+ *   ozk_msm_begin(ctx, groups, n_total, max_slice, key1, key2, first)   key1/key2: persistent bases for that group (then feed
+ *                                      takes NULL for its base array) or NULL; max_slice: longest slice to come (0 = unknown),
+ *                                      lets all scratch be reserved up front
+ *   ozk_msm_feed(ctx, scalars, bases1, bases2, len)   next `len` pairs; returns as soon as the host arrays are no longer read
+ *                                      (copied to pinned staging or to the device) while the GPU works on them -- a JNI
+ *                                      caller pins its byte[] only around this call, one slice at a time, instead of across the
+ *                                      whole MSM (the Java's own 2^23-element chunk loop, VariableBaseMSM.java:211-265, maps
+ *                                      onto feeds of one MSM too)
+ *   ozk_msm_end(ctx, out)              bucket reduction + window recombination, result as for ozk_msm_*
+ *   ozk_msm_plan_slices(n, bounds, cap) the slice schedule the whole-array entry points use: returns k <= cap and fills
+ *                                      bounds[0..k] (bounds[0] = 0, bounds[k] = n)
+ * Unreduced inputs are reported by ozk_msm_end.  One MSM in progress per context. */
+OZK_API int ozk_msm_begin(ozk_ctx* ctx, int groups, size_t n_total, size_t max_slice, const ozk_bases* key1, const ozk_bases* key2,
+                          size_t first);
+OZK_API int ozk_msm_feed(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* bases1, const uint8_t* bases2, size_t len);
+OZK_API int ozk_msm_end(ozk_ctx* ctx, uint8_t* out);
+OZK_API int ozk_msm_plan_slices(size_t n, size_t* bounds, int cap);
+
 /* ---- persistent bases (device-resident proving key) ---------------------------------------------------------
  * The query vectors of a Groth16 proving key (src/main/java/zk_proof_systems/zkSNARK/objects/ProvingKey.java:16-47:
  * queryA, queryB, deltaABCG1, queryH) are the same for every proof, but the reference re-marshals and re-uploads them on
@@ -161,7 +187,6 @@ OZK_API int ozk_msm_g1g2_dev(ozk_ctx* ctx, const void* d_scalars, const void* d_
  * (`first` covers both the Java chunk loop and the subList calls of the prover.)  Results are identical to the plain
  * entry points on the same points.  A handle belongs to the device of the context that made it; free it with
  * ozk_bases_free before destroying that context.  SURVEY.md section 8f, row 3. */
-typedef struct ozk_bases ozk_bases;
 OZK_API int ozk_bases_upload_g1(ozk_ctx* ctx, const uint8_t* bases, size_t n, ozk_bases** out);
 OZK_API int ozk_bases_upload_g1_dev(ozk_ctx* ctx, const void* d_bases, size_t n, ozk_bases** out);
 OZK_API int ozk_bases_upload_g2(ozk_ctx* ctx, const uint8_t* bases, size_t n, ozk_bases** out);
@@ -199,6 +224,15 @@ OZK_API int ozk_fixed_g1(ozk_ctx* ctx, const uint8_t base[96], const uint8_t* sc
 OZK_API int ozk_fixed_g1_dev(ozk_ctx* ctx, const uint8_t base[96], const void* d_scalars, size_t n, int outerc, int windowSize, void* d_out);
 OZK_API int ozk_fixed_g2(ozk_ctx* ctx, const uint8_t base[192], const uint8_t* scalars, size_t n, int outerc, int windowSize, uint8_t* out);
 OZK_API int ozk_fixed_g2_dev(ozk_ctx* ctx, const uint8_t base[192], const void* d_scalars, size_t n, int outerc, int windowSize, void* d_out);
+/* Same with flags.  OZK_FIXED_KEEP_Z: skip the normalisation and return every point as the Jacobian triple of the accumulator's
+ * own denominator (arbitrary Z, one launch less) -- the form the reference's own outputs have on the wire
+ * (fixedbase_MSM_unit_processing_G1, algebra_msm_FixedBaseMSM.cu:750-850, returns unnormalised Jacobian sums).  The points are
+ * the same group elements; only the representative differs. */
+#define OZK_FIXED_KEEP_Z 1u
+OZK_API int ozk_fixed_g1_ex_dev(ozk_ctx* ctx, const uint8_t base[96], const void* d_scalars, size_t n, int outerc, int windowSize,
+                                unsigned flags, void* d_out);
+OZK_API int ozk_fixed_g2_ex_dev(ozk_ctx* ctx, const uint8_t base[192], const void* d_scalars, size_t n, int outerc, int windowSize,
+                                unsigned flags, void* d_out);
 
 /* ---- diagnostics ----------------------------------------------------------------------------------------- */
 /* Integer-pipe microbenchmark: independent 32x32+64 multiply-add chains on every SM; reports billions of

@@ -203,8 +203,13 @@ void ozk_ctx_destroy(ozk_ctx* c) {
 
 int ozk_ctx_set_stream(ozk_ctx* c, void* s) {
     OZK_TRY(ctx_enter(c));
-    OZK_CUDA(cudaStreamSynchronize(c->stream));
-    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    if ((cudaStream_t)s == c->stream) return OZK_OK;
+    // Work already enqueued on the old stream stays ordered before anything enqueued on the new one (device-side, no host
+    // synchronisation): the new stream waits for an event recorded at the tail of the old one.
+    cudaEvent_t ev = c->copy_ev[19];
+    OZK_CUDA(cudaEventRecord(ev, c->stream));
+    OZK_CUDA(cudaStreamWaitEvent((cudaStream_t)s, ev, 0));
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);     // returns at once; released when its work has drained
     c->stream = (cudaStream_t)s;
     c->own_stream = false;
     return OZK_OK;

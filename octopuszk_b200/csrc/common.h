@@ -86,6 +86,7 @@ struct ozk_ctx {
     ozk::DevBuf work;                          // NTT ping-pong buffer
     ozk::DevBuf msm[16];                       // MSM pipeline buffers (see msm.cu)
     ozk::DevBuf fb[4];                         // fixed-base buffers
+    alignas(8) unsigned char msm_stream[96] = {};  // state of the host-pointer MSM in progress (MsmStream, msm.cu)
     double msm_stats[16] = {};                  // last MSM: window c, windows, buckets/window, overflow tasks, overflow buckets
     void* pinned = nullptr;                    // small pinned host block for flags / results
     std::map<std::string, ozk::NttPlan*> ntt_plans;

@@ -119,7 +119,7 @@ static int fixed_get_table(ozk_ctx* ctx, const FixedLaunch& L, int tag, const ui
 }
 
 static int fixed_run(ozk_ctx* ctx, const FixedLaunch& L, int tag, const uint8_t* base, const void* d_scalars, size_t n, int outerc,
-                     int window, void* d_out) {
+                     int window, void* d_out, unsigned flags = 0) {
     OZK_ARG(outerc >= 0 && window >= 1 && window <= 256, "fixed-base: outerc must be >= 0 and 1 <= windowSize <= 256");
     if (n == 0) return OZK_OK;
     long long bits_ll = (long long)outerc * window;
@@ -132,7 +132,7 @@ static int fixed_run(ozk_ctx* ctx, const FixedLaunch& L, int tag, const uint8_t*
     uint32_t* flag = (uint32_t*)ctx->fb[FB_SMALL].p;
     OZK_CUDA(cudaMemsetAsync(flag, 0, 16, st));
     if (L.walk(st, d_scalars, n, ft->table_aff, ft->t, ft->nwin, bits, ctx->fb[FB_OUT_XYZZ].p, flag) ||
-        L.to_wire(st, ctx->fb[FB_OUT_XYZZ].p, d_out, n)) {
+        ((flags & OZK_FIXED_KEEP_Z) ? L.to_wire_raw : L.to_wire)(st, ctx->fb[FB_OUT_XYZZ].p, d_out, n)) {
         set_error("fixed-base: kernel launch failed");
         return OZK_ERR_CUDA;
     }
@@ -173,6 +173,18 @@ int ozk_fixed_g2_dev(ozk_ctx* ctx, const uint8_t base[192], const void* d_scalar
     OZK_TRY(ctx_enter(ctx));
     OZK_ARG(base && (n == 0 || (d_scalars && d_out)), "ozk_fixed_g2_dev: null pointer");
     return fixed_run(ctx, kFixedG2, 2, base, d_scalars, n, outerc, window, d_out);
+}
+int ozk_fixed_g1_ex_dev(ozk_ctx* ctx, const uint8_t base[96], const void* d_scalars, size_t n, int outerc, int window, unsigned flags, void* d_out) {
+    OZK_TRY(ctx_enter(ctx));
+    OZK_ARG(base && (n == 0 || (d_scalars && d_out)), "ozk_fixed_g1_ex_dev: null pointer");
+    OZK_ARG((flags & ~(unsigned)OZK_FIXED_KEEP_Z) == 0, "ozk_fixed_g1_ex_dev: unknown flag");
+    return fixed_run(ctx, kFixedG1, 1, base, d_scalars, n, outerc, window, d_out, flags);
+}
+int ozk_fixed_g2_ex_dev(ozk_ctx* ctx, const uint8_t base[192], const void* d_scalars, size_t n, int outerc, int window, unsigned flags, void* d_out) {
+    OZK_TRY(ctx_enter(ctx));
+    OZK_ARG(base && (n == 0 || (d_scalars && d_out)), "ozk_fixed_g2_ex_dev: null pointer");
+    OZK_ARG((flags & ~(unsigned)OZK_FIXED_KEEP_Z) == 0, "ozk_fixed_g2_ex_dev: unknown flag");
+    return fixed_run(ctx, kFixedG2, 2, base, d_scalars, n, outerc, window, d_out, flags);
 }
 int ozk_fixed_g1(ozk_ctx* ctx, const uint8_t base[96], const uint8_t* scalars, size_t n, int outerc, int window, uint8_t* out) {
     OZK_TRY(ctx_enter(ctx));

@@ -126,6 +126,29 @@ __global__ void __launch_bounds__(128) xyzz_to_wire_batch(const uint4* __restric
     }
 }
 
+// Jacobian wire format WITHOUT normalisation: (X ZZ ZZZ^2, Y ZZ^3 ZZZ^2, ZZ ZZZ), the accumulator's own denominator, one thread
+// per element and no inversion.  This is what the reference's fixed-base outputs look like on the wire -- Jacobian triples with
+// arbitrary Z straight out of its window walk (algebra_msm_FixedBaseMSM.cu:750-850) -- and what a later variable-base MSM over
+// them has to normalise (OZK_FIXED_KEEP_Z in include/octozk.h).
+template <class F>
+__global__ void __launch_bounds__(128) xyzz_to_wire_raw(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n) {
+    constexpr int U = FieldIO<F>::kU4;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const XYZZ<F> p = load_xyzz<F>(in, i);
+    uint4* o = out + i * (3 * U);
+    if (p.is_inf()) {
+        FieldIO<F>::store(o, F::zero());
+        FieldIO<F>::store(o + U, canon_one((F*)nullptr));
+        FieldIO<F>::store(o + 2 * U, F::zero());
+        return;
+    }
+    const Jacobian<F> j = xyzz_to_jacobian(p);
+    FieldIO<F>::store(o, F::from_mont(j.x));
+    FieldIO<F>::store(o + U, F::from_mont(j.y));
+    FieldIO<F>::store(o + 2 * U, F::from_mont(j.z));
+}
+
 // table_xyzz[k * half + (j-1)] = j * 2^(t k) * B for j in 1..half (half = 2^(t-1)); the reference builds its table by binary
 // decomposition of every j over the powers of the base (algebra_msm_FixedBaseMSM.cu:851-884), ~t/2 additions per entry.
 // Two-level construction (one addition per entry): j = jl + jh 2^h with h = ceil((t-1)/2).
@@ -229,6 +252,7 @@ struct FixedLaunch {
     int (*powers)(cudaStream_t, const void* base_canon, void* pow_xyzz, uint32_t* flag);
     int (*to_affine)(cudaStream_t, const void* in_xyzz, void* out_aff, size_t n);
     int (*to_wire)(cudaStream_t, const void* in_xyzz, void* out_wire, size_t n);
+    int (*to_wire_raw)(cudaStream_t, const void* in_xyzz, void* out_wire, size_t n);
     // sub: scratch of nwin * fixed_sub_count(t) * (xyzz_bytes + affine_bytes) bytes
     int (*table)(cudaStream_t, const void* pow_aff, void* sub, void* table_xyzz, uint32_t t, uint32_t nwin);
     int (*walk)(cudaStream_t, const void* scalars, size_t n, const void* table_aff, uint32_t t, uint32_t nwin, uint32_t bits,
@@ -257,6 +281,10 @@ extern const FixedLaunch kFixedG2;
         xyzz_to_wire_batch<F><<<NAME##_batch_grid(n), 128, 0, s>>>((const uint4*)in, (uint4*)out, n, conv_batch_for(n));     \
         return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                                   \
     }                                                                                                                        \
+    static int NAME##_to_wire_raw(cudaStream_t s, const void* in, void* out, size_t n) {                                     \
+        xyzz_to_wire_raw<F><<<(unsigned)((n + 127) / 128), 128, 0, s>>>((const uint4*)in, (uint4*)out, n);                   \
+        return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                                   \
+    }                                                                                                                        \
     static int NAME##_table(cudaStream_t s, const void* pw, void* sub, void* tb, uint32_t t, uint32_t nwin) {                \
         const size_t nsub = (size_t)fixed_sub_count(t) * nwin;                                                               \
         void* sub_aff = (char*)sub + nsub * sizeof(XYZZ<F>);                                                                 \
@@ -272,7 +300,7 @@ extern const FixedLaunch kFixedG2;
                                                                   (uint4*)out, flag);                                        \
         return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                                   \
     }                                                                                                                        \
-    const FixedLaunch NAME = {NAME##_powers, NAME##_to_affine, NAME##_to_wire, NAME##_table, NAME##_walk,                    \
+    const FixedLaunch NAME = {NAME##_powers, NAME##_to_affine, NAME##_to_wire, NAME##_to_wire_raw, NAME##_table, NAME##_walk,                    \
                               sizeof(Affine<F>), sizeof(Jacobian<F>), sizeof(XYZZ<F>)};
 
 }  // namespace ozk

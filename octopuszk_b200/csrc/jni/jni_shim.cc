@@ -6,8 +6,12 @@
 //   -DOZK_SHIM_FFT      -> libAlgebraFFTAuxiliary.so        (src/main/java/algebra/fft/SerialFFT.java:20-23)
 // Symbol names, argument order and byte layouts are those of the javah headers (algebra_msm_VariableBaseMSM.h:10-24,
 // algebra_msm_FixedBaseMSM.h:10-32, algebra_fft_FFTAuxiliary.h:10-16) and of SURVEY.md Appendix A.  What changes:
-//   * arrays are pinned with Get/ReleasePrimitiveArrayCritical(JNI_ABORT) -- the reference calls GetByteArrayElements
-//     and never releases (algebra_msm_VariableBaseMSM.cu:1624,1634);
+//   * the reference calls GetByteArrayElements and never releases (algebra_msm_VariableBaseMSM.cu:1624,1634).  Here the large
+//     MSM inputs are pinned with Get/ReleasePrimitiveArrayCritical(JNI_ABORT) for ONE SLICE's host copy at a time (ozk_msm_feed
+//     returns as soon as the slice sits in pinned staging; the GPU work, the final reduction and every JNI call -- FindClass,
+//     ThrowNew, NewByteArray -- happen outside any critical region, so the collector is never locked out for a whole MSM and
+//     the JNI rule "no JNI calls inside a critical region" holds); the smaller fixed-base / field inputs are copied out with
+//     GetByteArrayRegion and never pinned;
 //   * errors become java.lang.RuntimeException via ThrowNew and a NULL return -- the reference prints and continues or
 //     exit(-1)s (algebra_msm_VariableBaseMSM.cu:23-28,1417-1422);
 //   * one liboctozk context per (thread, device): Spark executor threads enter concurrently (hs_err_pid98479.log:260-272);
@@ -19,6 +23,8 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
+#include <set>
 #include <vector>
 
 #include "jni_min.h"
@@ -96,6 +102,56 @@ jbyteArray to_java(JNIEnv* env, const std::vector<uint8_t>& v) {
 
 bool long_enough(JNIEnv* env, jbyteArray a, size_t need) { return a && (size_t)env->GetArrayLength(a) >= need; }
 
+// first `bytes` bytes of a Java byte[] into a native buffer, in pieces (no pin; a piece is a plain memcpy inside the JVM)
+void copy_out(JNIEnv* env, jbyteArray a, size_t bytes, uint8_t* dst) {
+    const size_t piece = (size_t)4 << 20;
+    for (size_t off = 0; off < bytes; off += piece) {
+        const size_t len = bytes - off < piece ? bytes - off : piece;
+        env->GetByteArrayRegion(a, (jsize)off, (jsize)len, (jbyte*)(dst + off));
+    }
+}
+
+// One variable-base MSM over Java arrays, slice by slice: the arrays are pinned only while ozk_msm_feed copies a slice out of
+// them.  groups: 1 = G1 (b1), 2 = G2 (b2), 3 = both.  Returns OZK_OK, an ozk error (message in ozk_last_error), or 1 when an
+// array could not be pinned.  No JNI call is made while a pin is live.
+int msm_over_arrays(JNIEnv* env, ozk_ctx* ctx, int groups, jbyteArray scalars, jbyteArray b1, jbyteArray b2, size_t n, uint8_t* res) {
+    if (n == 0) return groups == 1 ? ozk_msm_g1(ctx, nullptr, nullptr, 0, res) : groups == 2 ? ozk_msm_g2(ctx, nullptr, nullptr, 0, res)
+                                                                                             : ozk_msm_g1g2(ctx, nullptr, nullptr, nullptr, 0, res);
+    size_t bounds[9];
+    const int k = ozk_msm_plan_slices(n, bounds, 8);
+    size_t longest = 0;
+    for (int i = 0; i < k; i++) longest = bounds[i + 1] - bounds[i] > longest ? bounds[i + 1] - bounds[i] : longest;
+    int rc = ozk_msm_begin(ctx, groups, n, longest, nullptr, nullptr, 0);
+    if (rc != OZK_OK) return rc;
+    bool pin_failed = false;
+    for (int i = 0; i < k && rc == OZK_OK && !pin_failed; i++) {
+        const size_t lo = bounds[i], len = bounds[i + 1] - bounds[i];
+        if (len == 0) continue;
+        Pinned s(env, scalars), p1(env, (groups & 1) ? b1 : nullptr), p2(env, (groups & 2) ? b2 : nullptr);
+        if (!s.p || ((groups & 1) && !p1.p) || ((groups & 2) && !p2.p)) {
+            pin_failed = true;
+        } else {
+            rc = ozk_msm_feed(ctx, s.bytes() + lo * 32, (groups & 1) ? p1.bytes() + lo * 96 : nullptr,
+                              (groups & 2) ? p2.bytes() + lo * 192 : nullptr, len);
+        }
+    }                                                    // pins are released here, before anything else happens
+    if (pin_failed) {
+        uint8_t scratch[288];
+        ozk_msm_end(ctx, scratch);                       // closes the unfinished stream (reports "fewer pairs fed")
+        return 1;
+    }
+    if (rc != OZK_OK) return rc;
+    return ozk_msm_end(ctx, res);
+}
+
+// handles of persistent bases handed to Java: a stale or foreign jlong must become a RuntimeException, not a wild pointer
+std::mutex g_keys_mu;
+std::set<const ozk_bases*> g_keys;
+bool key_known(jlong h) {
+    std::lock_guard<std::mutex> g(g_keys_mu);
+    return g_keys.count((const ozk_bases*)(intptr_t)h) != 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -112,12 +168,8 @@ JNIEXPORT jbyteArray JNICALL Java_algebra_msm_VariableBaseMSM_variableBaseSerial
     ozk_ctx* ctx = context_for_task(taskID);
     if (!ctx) return fail(env, "variableBaseSerialMSMNativeHelper");
     uint8_t res[192];
-    int rc;
-    {
-        Pinned s(env, scalars), b(env, basesXYZ);
-        if ((n && (!s.p || !b.p))) return fail_msg(env, "variableBaseSerialMSMNativeHelper: could not pin the input arrays");
-        rc = g1 ? ozk_msm_g1(ctx, s.bytes(), b.bytes(), n, res) : ozk_msm_g2(ctx, s.bytes(), b.bytes(), n, res);
-    }
+    const int rc = msm_over_arrays(env, ctx, g1 ? 1 : 2, scalars, g1 ? basesXYZ : nullptr, g1 ? nullptr : basesXYZ, n, res);
+    if (rc == 1) return fail_msg(env, "variableBaseSerialMSMNativeHelper: could not pin the input arrays");
     if (rc != OZK_OK) return fail(env, "variableBaseSerialMSMNativeHelper");
     std::vector<uint8_t> out(g1 ? 192 : 384);
     widen(res, g1 ? 3 : 6, out.data(), false);
@@ -134,12 +186,8 @@ JNIEXPORT jbyteArray JNICALL Java_algebra_msm_VariableBaseMSM_variableBaseDouble
     ozk_ctx* ctx = context_for_task(taskID);
     if (!ctx) return fail(env, "variableBaseDoubleMSMNativeHelper");
     uint8_t res[288];
-    int rc;
-    {
-        Pinned s(env, scalars), b1(env, bases1), b2(env, bases2);
-        if (n && (!s.p || !b1.p || !b2.p)) return fail_msg(env, "variableBaseDoubleMSMNativeHelper: could not pin the input arrays");
-        rc = ozk_msm_g1g2(ctx, s.bytes(), b1.bytes(), b2.bytes(), n, res);
-    }
+    const int rc = msm_over_arrays(env, ctx, 3, scalars, bases1, bases2, n, res);
+    if (rc == 1) return fail_msg(env, "variableBaseDoubleMSMNativeHelper: could not pin the input arrays");
     if (rc != OZK_OK) return fail(env, "variableBaseDoubleMSMNativeHelper");
     std::vector<uint8_t> out(576);
     widen(res, 9, out.data(), false);                // G1 (X,Y,Z) || G2 (Xa,Xb,Ya,Yb,Za,Zb), :1781-1784
@@ -186,11 +234,22 @@ JNIEXPORT jlong JNICALL Java_algebra_msm_VariableBaseMSM_uploadBasesDirect(
     ozk_bases* key = nullptr;
     int rc = type == 1 ? ozk_bases_upload_g1(ctx, b, n, &key) : ozk_bases_upload_g2(ctx, b, n, &key);
     if (rc != OZK_OK) { fail(env, "uploadBasesDirect"); return 0; }
+    {
+        std::lock_guard<std::mutex> g(g_keys_mu);
+        g_keys.insert(key);
+    }
     return (jlong)(intptr_t)key;
 }
 
 JNIEXPORT void JNICALL Java_algebra_msm_VariableBaseMSM_freeBases(JNIEnv* env, jclass, jlong key, jint taskID) {
     if (!key) return;
+    {
+        std::lock_guard<std::mutex> g(g_keys_mu);
+        if (g_keys.erase((const ozk_bases*)(intptr_t)key) == 0) {
+            fail_msg(env, "freeBases: not a live handle of uploadBasesDirect (stale or already freed)");
+            return;
+        }
+    }
     ozk_ctx* ctx = context_for_task(taskID);
     if (!ctx) { fail(env, "freeBases"); return; }
     ozk_bases_free(ctx, (ozk_bases*)(intptr_t)key);
@@ -207,6 +266,10 @@ JNIEXPORT jint JNICALL Java_algebra_msm_VariableBaseMSM_variableBaseMSMKeyedDire
     if (batch_size < 0 || first < 0 || type < 1 || type > 3 || !o || (size_t)env->GetDirectBufferCapacity(out) < out_need ||
         (n && (!s || (size_t)env->GetDirectBufferCapacity(scalars) < n * 32))) {
         fail_msg(env, "variableBaseMSMKeyedDirect: buffers must be direct and hold batch_size elements");
+        return -1;
+    }
+    if ((type != 2 && !key_known(key1)) || (type != 1 && !key_known(key2))) {
+        fail_msg(env, "variableBaseMSMKeyedDirect: not a live handle of uploadBasesDirect (stale or already freed)");
         return -1;
     }
     ozk_ctx* ctx = context_for_task(taskID);
@@ -238,14 +301,12 @@ JNIEXPORT jbyteArray JNICALL Java_algebra_msm_FixedBaseMSM_batchMSMNativeHelper(
     if (n * pt * 2 > 0x7fffffffu) return fail_msg(env, "batchMSMNativeHelper: result exceeds the 2 GiB limit of a Java byte[]");
     ozk_ctx* ctx = context_for_task(taskID);
     if (!ctx) return fail(env, "batchMSMNativeHelper");
-    std::vector<uint8_t> res(n * pt);
-    int rc;
-    {
-        Pinned s(env, scalars), b(env, base);
-        if (!b.p || (n && !s.p)) return fail_msg(env, "batchMSMNativeHelper: could not pin the input arrays");
-        rc = g1 ? ozk_fixed_g1(ctx, b.bytes(), s.bytes(), n, outerc, windowSize, res.data())
-                : ozk_fixed_g2(ctx, b.bytes(), s.bytes(), n, outerc, windowSize, res.data());
-    }
+    std::vector<uint8_t> res(n * pt), sc(n * 32);
+    uint8_t b[192];
+    copy_out(env, base, pt, b);
+    copy_out(env, scalars, n * 32, sc.data());
+    const int rc = g1 ? ozk_fixed_g1(ctx, b, sc.data(), n, outerc, windowSize, res.data())
+                      : ozk_fixed_g2(ctx, b, sc.data(), n, outerc, windowSize, res.data());
     if (rc != OZK_OK) return fail(env, "batchMSMNativeHelper");
     std::vector<uint8_t> out(n * pt * 2);
     widen(res.data(), n * (g1 ? 3 : 6), out.data(), true);       // 64-byte big-endian coordinates, :783-787
@@ -265,14 +326,13 @@ JNIEXPORT jbyteArray JNICALL Java_algebra_msm_FixedBaseMSM_doubleBatchMSMNativeH
     if (n * 576 > 0x7fffffffu) return fail_msg(env, "doubleBatchMSMNativeHelper: result exceeds the 2 GiB limit of a Java byte[]");
     ozk_ctx* ctx = context_for_task(taskID);
     if (!ctx) return fail(env, "doubleBatchMSMNativeHelper");
-    std::vector<uint8_t> r1(n * 96), r2(n * 192);
-    int rc;
-    {
-        Pinned s(env, scalars), b1(env, baseG1), b2(env, baseG2);
-        if (!b1.p || !b2.p || (n && !s.p)) return fail_msg(env, "doubleBatchMSMNativeHelper: could not pin the input arrays");
-        rc = ozk_fixed_g1(ctx, b1.bytes(), s.bytes(), n, outerc1, windowSize1, r1.data());
-        if (rc == OZK_OK) rc = ozk_fixed_g2(ctx, b2.bytes(), s.bytes(), n, outerc2, windowSize2, r2.data());
-    }
+    std::vector<uint8_t> r1(n * 96), r2(n * 192), sc(n * 32);
+    uint8_t b1[96], b2[192];
+    copy_out(env, baseG1, 96, b1);
+    copy_out(env, baseG2, 192, b2);
+    copy_out(env, scalars, n * 32, sc.data());
+    int rc = ozk_fixed_g1(ctx, b1, sc.data(), n, outerc1, windowSize1, r1.data());
+    if (rc == OZK_OK) rc = ozk_fixed_g2(ctx, b2, sc.data(), n, outerc2, windowSize2, r2.data());
     if (rc != OZK_OK) return fail(env, "doubleBatchMSMNativeHelper");
     std::vector<uint8_t> out(n * 576);
     for (size_t i = 0; i < n; i++) {
@@ -292,13 +352,9 @@ JNIEXPORT jbyteArray JNICALL Java_algebra_msm_FixedBaseMSM_fieldBatchMSMNativeHe
     if (n * 64 > 0x7fffffffu) return fail_msg(env, "fieldBatchMSMNativeHelper: result exceeds the 2 GiB limit of a Java byte[]");
     ozk_ctx* ctx = context_for_task(taskID);
     if (!ctx) return fail(env, "fieldBatchMSMNativeHelper");
-    std::vector<uint8_t> res(n * 32);
-    int rc;
-    {
-        Pinned a(env, scalarsPlusBase);
-        if (!a.p) return fail_msg(env, "fieldBatchMSMNativeHelper: could not pin the input array");
-        rc = ozk_fr_scale(ctx, a.bytes(), n, a.bytes() + n * 32, res.data());
-    }
+    std::vector<uint8_t> res(n * 32), in((n + 1) * 32);
+    copy_out(env, scalarsPlusBase, (n + 1) * 32, in.data());
+    const int rc = ozk_fr_scale(ctx, in.data(), n, in.data() + n * 32, res.data());
     if (rc != OZK_OK) return fail(env, "fieldBatchMSMNativeHelper");
     std::vector<uint8_t> out(n * 64);
     widen(res.data(), n, out.data(), true);

@@ -497,102 +497,177 @@ static int msm_run(ozk_ctx* ctx, const void* d_scalars, BaseSrc s1, BaseSrc s2, 
     return msm_finish(ctx, d_res, bytes, out);
 }
 
-// Host-pointer entry.  Large inputs are cut into up to kCopyChunks slices: slice k+1 crosses PCIe on a second stream
-// while slice k is sorted, normalised and accumulated.  All slices add into the same buckets (an MSM is a sum over
-// points, so a bucket may receive its points in any grouping), so the window shape is that of the whole input and the
-// bucket reduction and the Horner tail run once.  This is the partition the Java does with its 2^23-element chunks
-// (VariableBaseMSM.java:211-265), except that here it only exists to overlap the copies.
-// Host arrays may be null when the matching BaseSrc already points at device memory (persistent bases).
-static int msm_run_host(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* b1, const uint8_t* b2, BaseSrc s1, BaseSrc s2, size_t n, uint8_t* out) {
-    OZK_ARG(n > 0 && n < ((size_t)1 << 31), "msm: between 1 and 2^31 - 1 points per call");
+// Host-pointer entry, as a stream of slices.  begin fixes the window shape from the TOTAL number of pairs; every feed uploads one
+// slice on the copy stream (or through the bounce-buffer stager when the memory is pageable, which is what the JNI shims pass) and
+// enqueues its sort / normalise / accumulate behind the copy, so slice k+1 crosses PCIe while slice k is computed; all slices add
+// into the same buckets (an MSM is a sum over points, so a bucket may receive its points in any grouping), so the bucket
+// reduction and the Horner tail run once, in end.  This is the partition the Java does with its 2^23-element chunks
+// (VariableBaseMSM.java:211-265), except that here it only exists to overlap the copies -- and to let a JNI caller hold its
+// array pins for one slice's host copy at a time instead of the whole call (csrc/jni/jni_shim.cc).
+// Host base arrays may be null when the group's bases are a persistent key (affine device memory).
+struct MsmStream {
+    bool active = false;
+    size_t n_total = 0, fed = 0;
+    BaseSrc s1, s2;                 // device sources of the two groups (wire staging or persistent affine)
+    bool host1 = false, host2 = false;
+    bool first = true;
+    int slices = 0;
+};
+static MsmStream& stream_of(ozk_ctx* ctx) {
+    static_assert(sizeof(MsmStream) <= sizeof(ctx->msm_stream), "msm_stream storage in common.h is too small");
+    return *reinterpret_cast<MsmStream*>(ctx->msm_stream);
+}
+
+// all per-slice scratch for slices of up to `len` pairs, reserved once: a regrow in the middle of the pipeline is a stream
+// synchronisation plus cudaFree / cudaMalloc exactly where the copies should overlap the compute
+static int msm_reserve_slices(ozk_ctx* ctx, size_t n_total, size_t len, bool g1, bool g2, bool conv1, bool conv2) {
+    cudaStream_t st = ctx->stream;
+    const MsmShape sh = msm_shape(n_total, len);
+    OZK_TRY(ctx->msm[B_SORTED].reserve((size_t)sh.nwin * len * 4, st));
+    OZK_TRY(ctx->msm[B_OVFTASK].reserve((size_t)sh.ovf_task_cap * sizeof(OvfTask), st));
+    OZK_TRY(ctx->msm[B_OVFBUCKET].reserve((size_t)sh.ovf_bucket_cap * sizeof(OvfBucket), st));
+    const size_t part = (size_t)sh.ovf_task_cap * (g2 ? kMsmG2.xyzz_bytes : kMsmG1.xyzz_bytes);
+    OZK_TRY(ctx->msm[B_OVFPART].reserve(part, st));
+    if (g1 && conv1) OZK_TRY(ctx->msm[B_AFF1].reserve(len * kMsmG1.affine_bytes, st));
+    if (g2 && conv2) OZK_TRY(ctx->msm[B_AFF2].reserve(len * kMsmG2.affine_bytes, st));
+    return OZK_OK;
+}
+
+static int msm_stream_begin(ozk_ctx* ctx, bool g1, bool g2, size_t n_total, size_t max_slice, const void* aff1, const void* aff2) {
+    OZK_ARG(n_total > 0 && n_total < ((size_t)1 << 31), "msm: between 1 and 2^31 - 1 points per call");
+    OZK_ARG(g1 || g2, "msm: no group selected");
+    MsmStream& ms = stream_of(ctx);
+    ms = MsmStream();
+    cudaStream_t st = ctx->stream;
+    ms.host1 = g1 && !aff1;
+    ms.host2 = g2 && !aff2;
+    OZK_TRY(ctx->io_a.reserve(n_total * 32, st));
+    if (ms.host1) OZK_TRY(ctx->io_b.reserve(n_total * 96, st));
+    if (ms.host2) OZK_TRY(ctx->io_c.reserve(n_total * 192, st));
+    OZK_TRY(ctx->msm[B_MISC].reserve(kMiscWords * 4, st));
+    OZK_TRY(ctx->io_out.reserve(512, st));
+    if (max_slice) OZK_TRY(msm_reserve_slices(ctx, n_total, std::min(max_slice, n_total), g1, g2, ms.host1, ms.host2));
+    OZK_CUDA(cudaMemsetAsync(ctx->msm[B_MISC].p, 0, 4, st));
+    OZK_CUDA(cudaEventRecord(ctx->evs[0], st));
+    // the copy stream must not overtake earlier work on the main stream that still uses the staging buffers
+    OZK_CUDA(cudaEventRecord(ctx->copy_ev[2 * kCopyChunks], st));
+    OZK_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[2 * kCopyChunks], 0));
+    if (g1) ms.s1 = ms.host1 ? BaseSrc{ctx->io_b.p, nullptr} : BaseSrc{nullptr, aff1};
+    if (g2) ms.s2 = ms.host2 ? BaseSrc{ctx->io_c.p, nullptr} : BaseSrc{nullptr, aff2};
+    ms.n_total = n_total;
+    ms.active = true;
+    const MsmShape sh = msm_shape(n_total, n_total);
+    ctx->msm_stats[0] = sh.c;
+    ctx->msm_stats[1] = sh.nwin;
+    ctx->msm_stats[2] = sh.nb;
+    return OZK_OK;
+}
+
+// release_host: return only when the host arrays are no longer read (always true for pageable memory, which goes through
+// the stager; for pinned memory it costs a wait for the slice's DMA)
+static int msm_stream_feed(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* b1, const uint8_t* b2, size_t len, bool release_host) {
+    MsmStream& ms = stream_of(ctx);
+    OZK_ARG(ms.active, "ozk_msm_feed: no MSM in progress on this context (ozk_msm_begin first)");
+    OZK_ARG(len <= ms.n_total - ms.fed, "ozk_msm_feed: more pairs than announced to ozk_msm_begin");
+    OZK_ARG(len == 0 || (scalars && (!ms.host1 || b1) && (!ms.host2 || b2)), "ozk_msm_feed: null pointer");
+    if (len == 0) return OZK_OK;
     cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
+    const size_t lo = ms.fed;
+    cudaEvent_t after = ctx->copy_ev[2 * kCopyChunks];
+    bool any_async = false;
+    auto upload = [&](void* dst, const uint8_t* src, size_t nbytes) -> int {
+        if (nbytes >= ((size_t)8 << 20) && host_pointer_is_pageable(src)) return staged_h2d(ctx, dst, src, nbytes, after, st);
+        OZK_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, cs));
+        any_async = any_async || !host_pointer_is_pageable(src);
+        return OZK_OK;
+    };
+    OZK_TRY(upload((char*)ctx->io_a.p + lo * 32, scalars, len * 32));
+    if (ms.host1) OZK_TRY(upload((char*)ctx->io_b.p + lo * 96, b1, len * 96));
+    if (ms.host2) OZK_TRY(upload((char*)ctx->io_c.p + lo * 192, b2, len * 192));
+    cudaEvent_t ev = ctx->copy_ev[ms.slices % kCopyChunks];
+    OZK_CUDA(cudaEventRecord(ev, cs));
+    OZK_CUDA(cudaStreamWaitEvent(st, ev, 0));
+    if (release_host && any_async) OZK_CUDA(cudaEventSynchronize(ev));
+    const MsmShape sh = msm_shape(ms.n_total, len);
+    OZK_TRY(msm_sort(ctx, (char*)ctx->io_a.p + lo * 32, len, sh));
+    if (ms.s1.any()) {
+        BaseSrc b = {ms.s1.wire ? (const char*)ms.s1.wire + lo * kMsmG1.jac_bytes : nullptr,
+                     ms.s1.affine ? (const char*)ms.s1.affine + lo * kMsmG1.affine_bytes : nullptr};
+        OZK_TRY(msm_accumulate_phase(ctx, kMsmG1, b, len, sh, B_AFF1, B_BUCKETS, !ms.first));
+    }
+    if (ms.s2.any()) {
+        BaseSrc b = {ms.s2.wire ? (const char*)ms.s2.wire + lo * kMsmG2.jac_bytes : nullptr,
+                     ms.s2.affine ? (const char*)ms.s2.affine + lo * kMsmG2.affine_bytes : nullptr};
+        OZK_TRY(msm_accumulate_phase(ctx, kMsmG2, b, len, sh, B_AFF2, B_BUCKETS2, !ms.first));
+    }
+    ms.first = false;
+    ms.fed += len;
+    ms.slices++;
+    return OZK_OK;
+}
+
+static int msm_stream_end(ozk_ctx* ctx, uint8_t* out) {
+    MsmStream& ms = stream_of(ctx);
+    OZK_ARG(ms.active, "ozk_msm_end: no MSM in progress on this context");
+    ms.active = false;
+    OZK_ARG(ms.fed == ms.n_total, "ozk_msm_end: fewer pairs were fed than announced to ozk_msm_begin");
+    const MsmShape sh = msm_shape(ms.n_total, ms.n_total);
+    char* d_res = (char*)ctx->io_out.p;
+    size_t bytes = 0;
+    if (ms.s1.any()) {
+        OZK_TRY(msm_reduce_phase(ctx, kMsmG1, sh, B_BUCKETS, d_res));
+        bytes += 96;
+    }
+    if (ms.s2.any()) {
+        OZK_TRY(msm_reduce_phase(ctx, kMsmG2, sh, B_BUCKETS2, d_res + bytes));
+        bytes += 192;
+    }
+    return msm_finish(ctx, d_res, bytes, out);
+}
+
+// Slice schedule of a whole-array call: 1 / 2 / 4 / 8 slices by size, lengths growing geometrically (x1.3, the ratio of compute
+// to copy time per pair): the first slice is small, so the GPU starts after ~4 % of the copy instead of 1/8 of it, and every
+// later copy still lands before the compute of the slices before it has finished.  OZK_HOST_SLICE_GROWTH=1 gives equal slices.
+static int msm_plan_slices(size_t n, size_t* bounds, int cap) {
     int nslices = 1;
     if (n >= ((size_t)1 << 22)) nslices = 8;
     else if (n >= ((size_t)1 << 20)) nslices = 4;
     else if (n >= ((size_t)1 << 18)) nslices = 2;
     if (const char* e = getenv("OZK_HOST_SLICES")) nslices = std::max(1, std::min(kCopyChunks, atoi(e)));
-    // Slice lengths grow geometrically (x1.3, the ratio of compute to copy time per pair): the first slice is small, so the GPU
-    // starts after ~4 % of the copy instead of 1/8 of it, and every later copy still lands before the compute of the slices
-    // before it has finished.  OZK_HOST_SLICE_GROWTH=1 gives equal slices.
-    size_t bounds[kCopyChunks + 1];
-    {
-        double growth = 1.3;
-        if (const char* e = getenv("OZK_HOST_SLICE_GROWTH")) growth = std::max(1.0, atof(e));
-        double total = 0, w = 1;
-        for (int k = 0; k < nslices; k++, w *= growth) total += w;
-        double acc = 0;
-        w = 1;
-        bounds[0] = 0;
-        for (int k = 0; k < nslices; k++, w *= growth) {
-            acc += w;
-            size_t b = (size_t)((double)n * acc / total);
-            b = (b + 255) & ~(size_t)255;
-            bounds[k + 1] = (k + 1 == nslices) ? n : std::min(b, n);
-            if (bounds[k + 1] < bounds[k]) bounds[k + 1] = bounds[k];
-        }
+    nslices = std::min(nslices, cap);
+    double growth = 1.3;
+    if (const char* e = getenv("OZK_HOST_SLICE_GROWTH")) growth = std::max(1.0, atof(e));
+    double total = 0, w = 1;
+    for (int k = 0; k < nslices; k++, w *= growth) total += w;
+    double acc = 0;
+    w = 1;
+    bounds[0] = 0;
+    for (int k = 0; k < nslices; k++, w *= growth) {
+        acc += w;
+        size_t b = (size_t)((double)n * acc / total);
+        b = (b + 255) & ~(size_t)255;
+        bounds[k + 1] = (k + 1 == nslices) ? n : std::min(b, n);
+        if (bounds[k + 1] < bounds[k]) bounds[k + 1] = bounds[k];
     }
+    return nslices;
+}
+
+static int msm_run_host(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* b1, const uint8_t* b2, BaseSrc s1, BaseSrc s2, size_t n, uint8_t* out) {
+    OZK_ARG(n > 0 && n < ((size_t)1 << 31), "msm: between 1 and 2^31 - 1 points per call");
+    size_t bounds[kCopyChunks + 1];
+    const int nslices = msm_plan_slices(n, bounds, kCopyChunks);
     size_t slice = 0;                                    // the longest slice sizes the per-slice scratch
     for (int k = 0; k < nslices; k++) slice = std::max(slice, bounds[k + 1] - bounds[k]);
-    OZK_TRY(ctx->io_a.reserve(n * 32, st));
-    if (b1) OZK_TRY(ctx->io_b.reserve(n * 96, st));
-    if (b2) OZK_TRY(ctx->io_c.reserve(n * 192, st));
-    OZK_TRY(ctx->msm[B_MISC].reserve(kMiscWords * 4, st));
-    OZK_TRY(ctx->io_out.reserve(512, st));
-    OZK_CUDA(cudaMemsetAsync(ctx->msm[B_MISC].p, 0, 4, st));
-    OZK_CUDA(cudaEventRecord(ctx->evs[0], st));
-    // the copy stream must not overtake earlier work on the main stream that still uses the staging buffers
-    OZK_CUDA(cudaEventRecord(ctx->copy_ev[2 * kCopyChunks], st));
-    OZK_CUDA(cudaStreamWaitEvent(cs, ctx->copy_ev[2 * kCopyChunks], 0));
-    // Uploads: pinned (or registered) host memory goes through cudaMemcpyAsync on the copy stream; pageable memory -- what the
-    // JNI shims pass, the arrays live on the JVM heap -- through the bounce-buffer stager (stage.cu), which blocks this thread
-    // only for the host-side memcpy of the slice while the GPU works on the previous one.
-    const bool page_s = host_pointer_is_pageable(scalars);
-    const bool page_1 = b1 && host_pointer_is_pageable(b1);
-    const bool page_2 = b2 && host_pointer_is_pageable(b2);
-    cudaEvent_t after = ctx->copy_ev[2 * kCopyChunks];
-    auto upload = [&](void* dst, const uint8_t* src, size_t nbytes, bool pageable) -> int {
-        if (pageable && nbytes >= ((size_t)8 << 20)) return staged_h2d(ctx, dst, src, nbytes, after, st);
-        OZK_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, cs));
-        return OZK_OK;
-    };
-    if (b1) s1 = {ctx->io_b.p, nullptr};
-    if (b2) s2 = {ctx->io_c.p, nullptr};
-    char* d_res = (char*)ctx->io_out.p;
-    MsmShape sh = msm_shape(n, slice);
-    ctx->msm_stats[0] = sh.c;
-    ctx->msm_stats[1] = sh.nwin;
-    ctx->msm_stats[2] = sh.nb;
-    bool first = true;
+    OZK_TRY(msm_stream_begin(ctx, b1 || s1.any(), b2 || s2.any(), n, slice, s1.affine, s2.affine));
     for (int k = 0; k < nslices; k++) {
         const size_t lo = bounds[k], len = bounds[k + 1] - bounds[k];
-        if (len == 0) continue;
-        OZK_TRY(upload((char*)ctx->io_a.p + lo * 32, scalars + lo * 32, len * 32, page_s));
-        if (b1) OZK_TRY(upload((char*)ctx->io_b.p + lo * 96, b1 + lo * 96, len * 96, page_1));
-        if (b2) OZK_TRY(upload((char*)ctx->io_c.p + lo * 192, b2 + lo * 192, len * 192, page_2));
-        OZK_CUDA(cudaEventRecord(ctx->copy_ev[k], cs));
-        OZK_CUDA(cudaStreamWaitEvent(st, ctx->copy_ev[k], 0));
-        sh = msm_shape(n, len);
-        OZK_TRY(msm_sort(ctx, (char*)ctx->io_a.p + lo * 32, len, sh));
-        if (s1.any()) {
-            BaseSrc b = {s1.wire ? (const char*)s1.wire + lo * kMsmG1.jac_bytes : nullptr, s1.affine ? (const char*)s1.affine + lo * kMsmG1.affine_bytes : nullptr};
-            OZK_TRY(msm_accumulate_phase(ctx, kMsmG1, b, len, sh, B_AFF1, B_BUCKETS, !first));
+        int rc = msm_stream_feed(ctx, scalars + lo * 32, b1 ? b1 + lo * 96 : nullptr, b2 ? b2 + lo * 192 : nullptr, len, false);
+        if (rc != OZK_OK) {
+            stream_of(ctx).active = false;
+            return rc;
         }
-        if (s2.any()) {
-            BaseSrc b = {s2.wire ? (const char*)s2.wire + lo * kMsmG2.jac_bytes : nullptr, s2.affine ? (const char*)s2.affine + lo * kMsmG2.affine_bytes : nullptr};
-            OZK_TRY(msm_accumulate_phase(ctx, kMsmG2, b, len, sh, B_AFF2, B_BUCKETS2, !first));
-        }
-        first = false;
     }
-    size_t bytes = 0;
-    if (s1.any()) {
-        OZK_TRY(msm_reduce_phase(ctx, kMsmG1, sh, B_BUCKETS, d_res));
-        bytes += 96;
-    }
-    if (s2.any()) {
-        OZK_TRY(msm_reduce_phase(ctx, kMsmG2, sh, B_BUCKETS2, d_res + bytes));
-        bytes += 192;
-    }
-    return msm_finish(ctx, d_res, bytes, out);
+    return msm_stream_end(ctx, out);
 }
 
 // ---- persistent bases -------------------------------------------------------------------------------------------
@@ -699,6 +774,33 @@ int ozk_msm_g1g2(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* bases1, co
         return OZK_OK;
     }
     return msm_run_host(ctx, scalars, bases1, bases2, BaseSrc{}, BaseSrc{}, n, out);
+}
+
+int ozk_msm_begin(ozk_ctx* ctx, int groups, size_t n_total, size_t max_slice, const ozk_bases* key1, const ozk_bases* key2, size_t first) {
+    OZK_TRY(ctx_enter(ctx));
+    OZK_ARG(groups >= 1 && groups <= 3, "ozk_msm_begin: groups must be 1 (G1), 2 (G2) or 3 (both)");
+    if (key1) OZK_TRY(keyed_check(ctx, key1, 1, first, n_total));
+    if (key2) OZK_TRY(keyed_check(ctx, key2, 2, first, n_total));
+    OZK_ARG((!key1 || (groups & 1)) && (!key2 || (groups & 2)), "ozk_msm_begin: a key was given for a group that is not selected");
+    return msm_stream_begin(ctx, (groups & 1) != 0, (groups & 2) != 0, n_total, max_slice,
+                            key1 ? (const char*)key1->d_affine + first * kMsmG1.affine_bytes : nullptr,
+                            key2 ? (const char*)key2->d_affine + first * kMsmG2.affine_bytes : nullptr);
+}
+int ozk_msm_feed(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* bases1, const uint8_t* bases2, size_t len) {
+    OZK_TRY(ctx_enter(ctx));
+    int rc = msm_stream_feed(ctx, scalars, bases1, bases2, len, true);
+    if (rc != OZK_OK) stream_of(ctx).active = false;
+    return rc;
+}
+int ozk_msm_end(ozk_ctx* ctx, uint8_t* out) {
+    OZK_TRY(ctx_enter(ctx));
+    OZK_ARG(out != nullptr, "ozk_msm_end: null pointer");
+    return msm_stream_end(ctx, out);
+}
+int ozk_msm_plan_slices(size_t n, size_t* bounds, int cap) {
+    if (!bounds || cap < 1) return 0;
+    if (n == 0) { bounds[0] = 0; return 0; }
+    return msm_plan_slices(n, bounds, std::min(cap, kCopyChunks));
 }
 
 int ozk_bases_upload_g1(ozk_ctx* ctx, const uint8_t* bases, size_t n, ozk_bases** out) {

@@ -65,10 +65,16 @@ SIGNATURES = {
     "ozk_msm_g2_dev": (_int, [_vp, _vp, _vp, _sz, _vp]),
     "ozk_msm_g1g2": (_int, [_vp, _vp, _vp, _vp, _sz, _vp]),
     "ozk_msm_g1g2_dev": (_int, [_vp, _vp, _vp, _vp, _sz, _vp]),
+    "ozk_msm_begin": (_int, [_vp, _int, _sz, _sz, _vp, _vp, _sz]),
+    "ozk_msm_feed": (_int, [_vp, _vp, _vp, _vp, _sz]),
+    "ozk_msm_end": (_int, [_vp, _vp]),
+    "ozk_msm_plan_slices": (_int, [_sz, ctypes.POINTER(_sz), _int]),
     "ozk_fixed_g1": (_int, [_vp, _c_u8p, _vp, _sz, _int, _int, _vp]),
     "ozk_fixed_g1_dev": (_int, [_vp, _c_u8p, _vp, _sz, _int, _int, _vp]),
     "ozk_fixed_g2": (_int, [_vp, _c_u8p, _vp, _sz, _int, _int, _vp]),
     "ozk_fixed_g2_dev": (_int, [_vp, _c_u8p, _vp, _sz, _int, _int, _vp]),
+    "ozk_fixed_g1_ex_dev": (_int, [_vp, _c_u8p, _vp, _sz, _int, _int, ctypes.c_uint, _vp]),
+    "ozk_fixed_g2_ex_dev": (_int, [_vp, _c_u8p, _vp, _sz, _int, _int, ctypes.c_uint, _vp]),
     "ozk_sum_g1_dev": (_int, [_vp, _vp, _sz, _vp]),
     "ozk_sum_g2_dev": (_int, [_vp, _vp, _sz, _vp]),
     "ozk_msm_last_stats": (_int, [_vp, ctypes.POINTER(ctypes.c_double), _int]),
@@ -155,6 +161,7 @@ class Context:
         self._check(self.lib.ozk_ctx_create(device, ctypes.byref(h)))
         self._h = h
         self.device = device
+        self._stream = None                  # None: the context's own stream
         if stream is not None:
             self.set_stream(stream)
 
@@ -175,6 +182,24 @@ class Context:
 
     def set_stream(self, cuda_stream: int):
         self._check(self.lib.ozk_ctx_set_stream(self._h, ctypes.c_void_p(cuda_stream)))
+        self._stream = cuda_stream
+
+    def use_torch_stream(self):
+        """Run all later work of this context on torch's CURRENT stream of the context's device.  The "_dev" entry points only
+        enqueue on the context's stream (stream contract in include/octozk.h), so work that mixes torch operations, NCCL
+        collectives and liboctozk kernels on the same buffers is ordered only if they share a stream.  Every wrapper below that
+        is handed a CUDA torch tensor calls this first, so the contract holds for any caller (also inside
+        `with torch.cuda.stream(s):`); switching streams is ordered on the device and costs nothing when the stream is unchanged."""
+        import torch
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        if s != self._stream:
+            self.set_stream(s)
+
+    def _dp(self, x):
+        """Device-pointer argument: address of a CUDA torch tensor (binding the context to torch's current stream) or a raw int."""
+        if x is not None and getattr(x, "is_cuda", False):
+            self.use_torch_stream()
+        return _ptr(x)
 
     def sync(self):
         self._check(self.lib.ozk_ctx_sync(self._h))
@@ -206,27 +231,27 @@ class Context:
         return out.raw
 
     def fr_scale_dev(self, d_a, d_out, n: int, b: bytes):
-        self._check(self.lib.ozk_fr_scale_dev(self._h, _ptr(d_a), _ptr(d_out), n, b))
+        self._check(self.lib.ozk_fr_scale_dev(self._h, self._dp(d_a), self._dp(d_out), n, b))
 
     def fr_scale_powers_dev(self, d_a, d_out, n: int, scale=None, coset=None, first_index: int = 0):
-        self._check(self.lib.ozk_fr_scale_powers_dev(self._h, _ptr(d_a), _ptr(d_out), n, scale, coset, first_index))
+        self._check(self.lib.ozk_fr_scale_powers_dev(self._h, self._dp(d_a), self._dp(d_out), n, scale, coset, first_index))
 
     def fr_mul_sub_dev(self, d_a, d_b, d_c, d_out, n: int):
-        self._check(self.lib.ozk_fr_mul_sub_dev(self._h, _ptr(d_a), _ptr(d_b), _ptr(d_c) if d_c is not None else None, _ptr(d_out), n))
+        self._check(self.lib.ozk_fr_mul_sub_dev(self._h, self._dp(d_a), self._dp(d_b), self._dp(d_c) if d_c is not None else None, self._dp(d_out), n))
 
     def fr_spmv_dev(self, d_row_ptr, d_col, d_coeff, d_z, rows: int, d_out):
-        self._check(self.lib.ozk_fr_spmv_dev(self._h, _ptr(d_row_ptr), _ptr(d_col), _ptr(d_coeff), _ptr(d_z), rows, _ptr(d_out)))
+        self._check(self.lib.ozk_fr_spmv_dev(self._h, self._dp(d_row_ptr), self._dp(d_col), self._dp(d_coeff), self._dp(d_z), rows, self._dp(d_out)))
 
     def fr_lagrange_dev(self, d_out, m: int, t: bytes, omega: bytes):
-        self._check(self.lib.ozk_fr_lagrange_dev(self._h, _ptr(d_out), m, t, omega))
+        self._check(self.lib.ozk_fr_lagrange_dev(self._h, self._dp(d_out), m, t, omega))
 
     def ntt_scatter_dev(self, d_in, peer_ptrs, rank: int, n_local: int, omega_local: bytes, twiddle_base: bytes):
         arr = (ctypes.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
-        self._check(self.lib.ozk_ntt_fr_scatter_dev(self._h, _ptr(d_in), arr, len(peer_ptrs), rank, n_local, omega_local, twiddle_base))
+        self._check(self.lib.ozk_ntt_fr_scatter_dev(self._h, self._dp(d_in), arr, len(peer_ptrs), rank, n_local, omega_local, twiddle_base))
 
     def dft_small_scatter_dev(self, d_in, peer_ptrs, rank: int, length: int, omega_g: bytes, omega_n: bytes):
         arr = (ctypes.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
-        self._check(self.lib.ozk_fr_dft_small_scatter_dev(self._h, _ptr(d_in), arr, len(peer_ptrs), rank, length, omega_g, omega_n))
+        self._check(self.lib.ozk_fr_dft_small_scatter_dev(self._h, self._dp(d_in), arr, len(peer_ptrs), rank, length, omega_g, omega_n))
 
     def peer_alloc(self, nbytes: int):
         """(device pointer, 64-byte IPC handle) of a fresh cudaMalloc block other processes can map."""
@@ -247,7 +272,7 @@ class Context:
         self._check(self.lib.ozk_peer_free(self._h, ctypes.c_void_p(ptr)))
 
     def fr_dft_small_dev(self, d_in, d_out, groups: int, length: int, omega_g: bytes):
-        self._check(self.lib.ozk_fr_dft_small_dev(self._h, _ptr(d_in), _ptr(d_out), groups, length, omega_g))
+        self._check(self.lib.ozk_fr_dft_small_dev(self._h, self._dp(d_in), self._dp(d_out), groups, length, omega_g))
 
     # ---- NTT
     def ntt(self, data: bytes, omega: bytes) -> bytes:
@@ -260,10 +285,10 @@ class Context:
         self._check(self.lib.ozk_ntt_fr(self._h, _ptr(buf), n, omega))
 
     def ntt_dev(self, d_in, d_out, n: int, omega: bytes):
-        self._check(self.lib.ozk_ntt_fr_dev(self._h, _ptr(d_in), _ptr(d_out), n, omega))
+        self._check(self.lib.ozk_ntt_fr_dev(self._h, self._dp(d_in), self._dp(d_out), n, omega))
 
     def ntt_ex_dev(self, d_in, d_out, n: int, omega: bytes, pre_coset=None, post_scale=None, post_coset=None):
-        self._check(self.lib.ozk_ntt_fr_ex_dev(self._h, _ptr(d_in), _ptr(d_out), n, omega, pre_coset, post_scale, post_coset))
+        self._check(self.lib.ozk_ntt_fr_ex_dev(self._h, self._dp(d_in), self._dp(d_out), n, omega, pre_coset, post_scale, post_coset))
 
     # ---- variable-base MSM
     def msm_g1(self, scalars, bases, n: int) -> bytes:
@@ -273,7 +298,7 @@ class Context:
 
     def msm_g1_dev(self, d_scalars, d_bases, n: int) -> bytes:
         out = ctypes.create_string_buffer(96)
-        self._check(self.lib.ozk_msm_g1_dev(self._h, _ptr(d_scalars), _ptr(d_bases), n, out))
+        self._check(self.lib.ozk_msm_g1_dev(self._h, self._dp(d_scalars), self._dp(d_bases), n, out))
         return out.raw
 
     def msm_g2(self, scalars, bases, n: int) -> bytes:
@@ -283,7 +308,7 @@ class Context:
 
     def msm_g2_dev(self, d_scalars, d_bases, n: int) -> bytes:
         out = ctypes.create_string_buffer(192)
-        self._check(self.lib.ozk_msm_g2_dev(self._h, _ptr(d_scalars), _ptr(d_bases), n, out))
+        self._check(self.lib.ozk_msm_g2_dev(self._h, self._dp(d_scalars), self._dp(d_bases), n, out))
         return out.raw
 
     def msm_g1g2(self, scalars, bases1, bases2, n: int) -> bytes:
@@ -293,31 +318,43 @@ class Context:
 
     def msm_g1g2_dev(self, d_scalars, d_bases1, d_bases2, n: int) -> bytes:
         out = ctypes.create_string_buffer(288)
-        self._check(self.lib.ozk_msm_g1g2_dev(self._h, _ptr(d_scalars), _ptr(d_bases1), _ptr(d_bases2), n, out))
+        self._check(self.lib.ozk_msm_g1g2_dev(self._h, self._dp(d_scalars), self._dp(d_bases1), self._dp(d_bases2), n, out))
+        return out.raw
+
+    # ---- streaming form: announce the total, feed slices of host arrays, collect the result
+    def msm_begin(self, groups: int, n_total: int, max_slice: int = 0, key1=None, key2=None, first: int = 0):
+        self._check(self.lib.ozk_msm_begin(self._h, groups, n_total, max_slice, key1._h if key1 else None, key2._h if key2 else None, first))
+
+    def msm_feed(self, scalars, bases1, bases2, n: int):
+        self._check(self.lib.ozk_msm_feed(self._h, _ptr(scalars), _ptr(bases1), _ptr(bases2), n))
+
+    def msm_end(self, groups: int) -> bytes:
+        out = ctypes.create_string_buffer({1: 96, 2: 192, 3: 288}[groups])
+        self._check(self.lib.ozk_msm_end(self._h, out))
         return out.raw
 
     # ---- persistent bases + keyed MSM (scalars only per call)
     def upload_bases(self, group: int, bases, n: int, device: bool = False) -> Bases:
         fn = getattr(self.lib, f"ozk_bases_upload_g{group}" + ("_dev" if device else ""))
         h = ctypes.c_void_p()
-        self._check(fn(self._h, _ptr(bases), n, ctypes.byref(h)))
+        self._check(fn(self._h, self._dp(bases) if device else _ptr(bases), n, ctypes.byref(h)))
         return Bases(self, h, group)
 
     def msm_keyed(self, scalars, key: Bases, n: int, first: int = 0, device: bool = False) -> bytes:
         out = ctypes.create_string_buffer(96 if key.group == 1 else 192)
         fn = getattr(self.lib, f"ozk_msm_g{key.group}_keyed" + ("_dev" if device else ""))
-        self._check(fn(self._h, _ptr(scalars), key._h, first, n, out))
+        self._check(fn(self._h, self._dp(scalars) if device else _ptr(scalars), key._h, first, n, out))
         return out.raw
 
     def msm_g1g2_keyed(self, scalars, key1: Bases, key2: Bases, n: int, first: int = 0, device: bool = False) -> bytes:
         out = ctypes.create_string_buffer(288)
         fn = getattr(self.lib, "ozk_msm_g1g2_keyed" + ("_dev" if device else ""))
-        self._check(fn(self._h, _ptr(scalars), key1._h, key2._h, first, n, out))
+        self._check(fn(self._h, self._dp(scalars) if device else _ptr(scalars), key1._h, key2._h, first, n, out))
         return out.raw
 
     def sum_points_dev(self, group: int, d_points, k: int) -> bytes:
         out = ctypes.create_string_buffer(96 if group == 1 else 192)
-        self._check(getattr(self.lib, f"ozk_sum_g{group}_dev")(self._h, _ptr(d_points), k, out))
+        self._check(getattr(self.lib, f"ozk_sum_g{group}_dev")(self._h, self._dp(d_points), k, out))
         return out.raw
 
     def msm_last_stats(self):
@@ -331,13 +368,13 @@ class Context:
         self._check(self.lib.ozk_fixed_g1(self._h, base, _ptr(scalars), n, outerc, window, out))
         return out.raw
 
-    def fixed_g1_dev(self, base: bytes, d_scalars, n: int, outerc: int, window: int, d_out):
-        self._check(self.lib.ozk_fixed_g1_dev(self._h, base, _ptr(d_scalars), n, outerc, window, _ptr(d_out)))
+    def fixed_g1_dev(self, base: bytes, d_scalars, n: int, outerc: int, window: int, d_out, keep_z: bool = False):
+        self._check(self.lib.ozk_fixed_g1_ex_dev(self._h, base, self._dp(d_scalars), n, outerc, window, 1 if keep_z else 0, self._dp(d_out)))
 
     def fixed_g2(self, base: bytes, scalars, n: int, outerc: int, window: int) -> bytes:
         out = ctypes.create_string_buffer(n * 192)
         self._check(self.lib.ozk_fixed_g2(self._h, base, _ptr(scalars), n, outerc, window, out))
         return out.raw
 
-    def fixed_g2_dev(self, base: bytes, d_scalars, n: int, outerc: int, window: int, d_out):
-        self._check(self.lib.ozk_fixed_g2_dev(self._h, base, _ptr(d_scalars), n, outerc, window, _ptr(d_out)))
+    def fixed_g2_dev(self, base: bytes, d_scalars, n: int, outerc: int, window: int, d_out, keep_z: bool = False):
+        self._check(self.lib.ozk_fixed_g2_ex_dev(self._h, base, self._dp(d_scalars), n, outerc, window, 1 if keep_z else 0, self._dp(d_out)))

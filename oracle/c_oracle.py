@@ -25,6 +25,11 @@ def load():
     lib.oracle_fft_fr_batch.argtypes = [vp, sz, sz, vp, i]
     lib.oracle_fixed_g1.argtypes = [vp, vp, sz, i, i, i, vp]
     lib.oracle_fr_scale.argtypes = [vp, sz, vp, vp]
+    lib.oracle_fr_dot.argtypes = [vp, vp, sz, i, vp]
+    lib.oracle_fr_coset_scale.argtypes = [vp, sz, vp, vp]
+    lib.oracle_fr_horner.argtypes = [vp, sz, vp, sz, i, vp]
+    lib.oracle_fr_lagrange_eval.argtypes = [vp, sz, vp, vp, i, vp]
+    lib.oracle_r1cs_chain.argtypes = [sz, vp, vp, vp]
     _lib = lib
     return lib
 
@@ -78,4 +83,49 @@ def fr_scale(a: bytes, b: bytes) -> bytes:
     n = len(a) // 32
     out = ctypes.create_string_buffer(32 * n)
     load().oracle_fr_scale(a, n, b, out)
+    return out.raw
+
+
+def default_threads() -> int:
+    import os
+    return os.cpu_count() or max_threads()
+
+
+def fr_dot(a, b, n: int, threads: int = 0) -> int:
+    """sum_i a[i] * b[i] mod r of two arrays of n canonical 32-byte elements."""
+    out = ctypes.create_string_buffer(32)
+    assert load().oracle_fr_dot(_addr(a), _addr(b), n, threads or default_threads(), out) == 0
+    return int.from_bytes(out.raw, "little")
+
+
+def fr_horner(coeffs, n: int, xs, threads: int = 0):
+    """[sum_j coeffs[j] * x^j mod r for x in xs] (xs: list of ints)."""
+    xb = b"".join(int(x).to_bytes(32, "little") for x in xs)
+    out = ctypes.create_string_buffer(32 * len(xs))
+    assert load().oracle_fr_horner(_addr(coeffs), n, xb, len(xs), threads or default_threads(), out) == 0
+    return [int.from_bytes(out.raw[32 * q:32 * q + 32], "little") for q in range(len(xs))]
+
+
+def fr_lagrange_eval(vals, n: int, omega: int, t: int, threads: int = 0) -> int:
+    """sum_j vals[j] * L_j(t) over the domain {omega^j}: the interpolant of vals evaluated at t."""
+    out = ctypes.create_string_buffer(32)
+    rc = load().oracle_fr_lagrange_eval(_addr(vals), n, int(omega).to_bytes(32, "little"), int(t).to_bytes(32, "little"),
+                                        threads or default_threads(), out)
+    assert rc == 0, rc
+    return int.from_bytes(out.raw, "little")
+
+
+def r1cs_chain(num_constraints: int, a0: int, b0: int):
+    """Full assignment (numpy (num_constraints + 3, 32) uint8) of R1CSConstruction.serialConstruct."""
+    import numpy as np
+    out = np.empty((num_constraints + 3, 32), dtype=np.uint8)
+    assert load().oracle_r1cs_chain(num_constraints, int(a0).to_bytes(32, "little"), int(b0).to_bytes(32, "little"), out.ctypes.data) == 0
+    return out
+
+
+def fr_coset_scale(a, g: int) -> bytes:
+    """[a_i * g^i mod r] (FFTAuxiliary.multiplyByCoset)."""
+    n = len(a) // 32
+    out = ctypes.create_string_buffer(32 * n)
+    load().oracle_fr_coset_scale(_addr(a), n, int(g).to_bytes(32, "little"), out)
     return out.raw

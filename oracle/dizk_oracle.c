@@ -481,6 +481,175 @@ int oracle_fr_scale(const uint8_t* a, size_t n, const uint8_t b[32], uint8_t* ou
     return 0;
 }
 
+/* ---- exact size-independent checks (SURVEY.md section 8c "scale-parity technique") -------------------------------- */
+/* out = sum_i a[i] * b[i] mod r.  With bases P_i = k_i * G the definition of the MSM (NaiveMSM.variableBaseMSM,
+ * src/main/java/algebra/msm/NaiveMSM.java:21-46: sum of scalar.mul(base)) gives sum_i s_i P_i = (sum_i s_i k_i mod r) * G,
+ * so this dot product is the whole expected answer at any size. */
+int oracle_fr_dot(const uint8_t* a, const uint8_t* b, size_t n, int threads, uint8_t out[32]) {
+    init_once();
+    if (threads < 1) threads = 1;
+    fe* part = (fe*)calloc((size_t)threads, sizeof(fe));
+#pragma omp parallel for num_threads(threads) schedule(static, 1)
+    for (int t = 0; t < threads; t++) {
+        size_t lo = n * (size_t)t / (size_t)threads, hi = n * (size_t)(t + 1) / (size_t)threads;
+        fe acc;
+        memset(&acc, 0, sizeof acc);
+        for (size_t i = lo; i < hi; i++) {
+            fe x, y;
+            load_fe(&FR, &x, a + 32 * i);
+            load_fe(&FR, &y, b + 32 * i);
+            fe_mul(&FR, &x, &x, &y);
+            fe_add(&FR, &acc, &acc, &x);
+        }
+        part[t] = acc;
+    }
+    fe total;
+    memset(&total, 0, sizeof total);
+    for (int t = 0; t < threads; t++) fe_add(&FR, &total, &total, &part[t]);
+    store_fe(&FR, out, &total);
+    free(part);
+    return 0;
+}
+
+/* out[q] = sum_j coeffs[j] * xs[q]^j mod r (Horner): naive evaluation, the definition the reference's own FFT test compares
+ * with (src/test/java/algebra/fft/SerialFFTTest.java:168-190: FFT output k == polynomial evaluated at omega^k).
+ * One point per thread at a time; O(n) each. */
+int oracle_fr_horner(const uint8_t* coeffs, size_t n, const uint8_t* xs, size_t npts, int threads, uint8_t* out) {
+    init_once();
+    if (threads < 1) threads = 1;
+    fe* c = (fe*)malloc((n ? n : 1) * sizeof(fe));
+#pragma omp parallel for num_threads(threads) schedule(static)
+    for (long j = 0; j < (long)n; j++) load_fe(&FR, &c[j], coeffs + 32 * (size_t)j);
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 1)
+    for (long q = 0; q < (long)npts; q++) {
+        fe x, acc;
+        load_fe(&FR, &x, xs + 32 * (size_t)q);
+        memset(&acc, 0, sizeof acc);
+        for (size_t j = n; j-- > 0;) {
+            fe_mul(&FR, &acc, &acc, &x);
+            fe_add(&FR, &acc, &acc, &c[j]);
+        }
+        store_fe(&FR, out + 32 * (size_t)q, &acc);
+    }
+    free(c);
+    return 0;
+}
+
+/* out = sum_j vals[j] * L_j(t) over the domain {omega^j, j < n}: the polynomial with evaluations vals[] evaluated at t through
+ * the Lagrange coefficients L_j(t) = (t^n - 1)/n * omega^j / (t - omega^j) of FFTAuxiliary.serialRadix2LagrangeCoefficients
+ * (src/main/java/algebra/fft/FFTAuxiliary.java:249-302; t outside the domain).  Used to derive the expected Groth16 proof
+ * "in the exponent": A(t) = sum_i z_i A_i(t) = sum_j L_j(t) <a_j, z> (R1CStoQAP.java:54-91 combined with :143-160).
+ * Returns -2 when t is a point of the domain. */
+int oracle_fr_lagrange_eval(const uint8_t* vals, size_t n, const uint8_t omega_b[32], const uint8_t t_b[32], int threads,
+                            uint8_t out[32]) {
+    init_once();
+    if (threads < 1) threads = 1;
+    if ((size_t)threads > n) threads = (int)(n ? n : 1);
+    fe omega, t;
+    load_fe(&FR, &omega, omega_b);
+    load_fe(&FR, &t, t_b);
+    fe* part = (fe*)calloc((size_t)threads, sizeof(fe));
+    int bad = 0;
+#pragma omp parallel for num_threads(threads) schedule(static, 1)
+    for (int th = 0; th < threads; th++) {
+        size_t lo = n * (size_t)th / (size_t)threads, hi = n * (size_t)(th + 1) / (size_t)threads;
+        size_t len = hi - lo;
+        if (len == 0) continue;
+        fe* den = (fe*)malloc(len * sizeof(fe));
+        fe* pre = (fe*)malloc(len * sizeof(fe));
+        fe* num = (fe*)malloc(len * sizeof(fe));
+        uint64_t e[4] = {lo, 0, 0, 0};
+        fe w;
+        fe_pow(&FR, &w, &omega, e);
+        for (size_t k = 0; k < len; k++) {
+            num[k] = w;
+            fe_sub(&FR, &den[k], &t, &w);
+            if (fe_is_zero(&den[k])) { bad = 1; den[k] = FR.one; }
+            if (k == 0) pre[k] = den[k];
+            else fe_mul(&FR, &pre[k], &pre[k - 1], &den[k]);
+            fe_mul(&FR, &w, &w, &omega);
+        }
+        fe inv, acc;
+        fe_inv(&FR, &inv, &pre[len - 1]);
+        memset(&acc, 0, sizeof acc);
+        for (size_t k = len; k-- > 0;) {
+            fe di, v, term;
+            if (k) fe_mul(&FR, &di, &inv, &pre[k - 1]);
+            else di = inv;
+            fe_mul(&FR, &inv, &inv, &den[k]);
+            load_fe(&FR, &v, vals + 32 * (lo + k));
+            fe_mul(&FR, &term, &num[k], &di);
+            fe_mul(&FR, &term, &term, &v);
+            fe_add(&FR, &acc, &acc, &term);
+        }
+        part[th] = acc;
+        free(den); free(pre); free(num);
+    }
+    fe total;
+    memset(&total, 0, sizeof total);
+    for (int th = 0; th < threads; th++) fe_add(&FR, &total, &total, &part[th]);
+    free(part);
+    if (bad) return -2;
+    /* (t^n - 1) / n */
+    fe tn = t, nn, ninv, f, c;
+    for (size_t m = 1; m < n; m <<= 1) fe_sqr(&FR, &tn, &tn);
+    fe_sub(&FR, &f, &tn, &FR.one);
+    memset(&c, 0, sizeof c);
+    c.v[0] = (uint64_t)n;
+    fe_to_mont(&FR, &nn, &c);
+    fe_inv(&FR, &ninv, &nn);
+    fe_mul(&FR, &f, &f, &ninv);
+    fe_mul(&FR, &total, &total, &f);
+    store_fe(&FR, out, &total);
+    return 0;
+}
+
+/* The assignment of the reference's synthetic circuit, R1CSConstruction.serialConstruct (src/main/java/profiler/generation/
+ * R1CSConstruction.java:31-110): full[0] = 1, full[1] = a, full[2] = b, then for constraint i < numConstraints - 1:
+ * odd i -> a*b, even i -> a+b, (a, b) <- (b, tmp); the last entry is (sum of full[1 .. numVariables-2])^2.  a0/b0 are the two
+ * Fp.random values (equal under the reference's fixed seed).  out: numVariables = numConstraints + 3 canonical elements. */
+int oracle_r1cs_chain(size_t num_constraints, const uint8_t a0[32], const uint8_t b0[32], uint8_t* out) {
+    init_once();
+    if (num_constraints < 1) return -1;
+    const size_t nv = num_constraints + 3;
+    fe a, b, sum;
+    load_fe(&FR, &a, a0);
+    load_fe(&FR, &b, b0);
+    store_fe(&FR, out, &FR.one);
+    store_fe(&FR, out + 32, &a);
+    store_fe(&FR, out + 64, &b);
+    fe_add(&FR, &sum, &a, &b);
+    for (size_t i = 0; i + 1 < num_constraints; i++) {
+        fe tmp;
+        if (i % 2 != 0) fe_mul(&FR, &tmp, &a, &b);
+        else fe_add(&FR, &tmp, &a, &b);
+        a = b;
+        b = tmp;
+        store_fe(&FR, out + 32 * (3 + i), &tmp);
+        fe_add(&FR, &sum, &sum, &tmp);
+    }
+    /* full has numVariables - 1 entries so far (indices 0 .. nv-2); res = sum of full[1 .. nv-2] */
+    fe sq;
+    fe_sqr(&FR, &sq, &sum);
+    store_fe(&FR, out + 32 * (nv - 1), &sq);
+    return 0;
+}
+
+/* out[i] = a[i] * g^i mod r: FFTAuxiliary.multiplyByCoset (src/main/java/algebra/fft/FFTAuxiliary.java:224-232) */
+int oracle_fr_coset_scale(const uint8_t* a, size_t n, const uint8_t g_b[32], uint8_t* out) {
+    init_once();
+    fe g, u = FR.one;
+    load_fe(&FR, &g, g_b);
+    for (size_t i = 0; i < n; i++) {
+        fe x;
+        load_fe(&FR, &x, a + 32 * i);
+        fe_mul(&FR, &x, &x, &u);
+        store_fe(&FR, out + 32 * i, &x);
+        fe_mul(&FR, &u, &u, &g);
+    }
+    return 0;
+}
+
 int oracle_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -48,6 +48,19 @@ def fixed_batch(outerc, window, out_len, inner_len, n, scalar_size, base: bytes,
     return out.raw
 
 
+def fixed_double_batch(outerc1, window1, outerc2, window2, out_len1, inner_len1, out_len2, inner_len2, n, base1: bytes, base2: bytes,
+                       scalars: bytes) -> bytes:
+    lib = _load("fixedmsm")
+    lib.ref_fixed_double_batch.restype = ctypes.c_long
+    lib.ref_fixed_double_batch.argtypes = [i32] * 9 + [vp, sz, vp, sz, vp, sz, vp, sz]
+    cap = n * 576
+    out = ctypes.create_string_buffer(cap)
+    r = lib.ref_fixed_double_batch(outerc1, window1, outerc2, window2, out_len1, inner_len1, out_len2, inner_len2, n, base1, len(base1),
+                                   base2, len(base2), scalars, len(scalars), out, cap)
+    assert r == cap, r
+    return out.raw
+
+
 def field_batch(scalars_plus_base: bytes, n: int) -> bytes:
     lib = _load("fixedmsm")
     lib.ref_field_batch.restype = ctypes.c_long

@@ -7,6 +7,8 @@ extern "C" {
 jbyteArray Java_algebra_msm_VariableBaseMSM_variableBaseSerialMSMNativeHelper(JNIEnv*, jclass, jbyteArray, jbyteArray, jint, jint, jint);
 jbyteArray Java_algebra_msm_VariableBaseMSM_variableBaseDoubleMSMNativeHelper(JNIEnv*, jclass, jbyteArray, jbyteArray, jbyteArray, jint, jint);
 jbyteArray Java_algebra_msm_FixedBaseMSM_batchMSMNativeHelper(JNIEnv*, jclass, jint, jint, jint, jint, jint, jint, jbyteArray, jbyteArray, jint, jint);
+jbyteArray Java_algebra_msm_FixedBaseMSM_doubleBatchMSMNativeHelper(JNIEnv*, jclass, jint, jint, jint, jint, jint, jint, jint, jint, jint, jbyteArray,
+                                                                   jbyteArray, jbyteArray, jint);
 jbyteArray Java_algebra_msm_FixedBaseMSM_fieldBatchMSMNativeHelper(JNIEnv*, jclass, jbyteArray, jint, jint);
 jbyteArray Java_algebra_fft_FFTAuxiliary_serialRadix2FFTNativeHelper(JNIEnv*, jclass, jobject, jbyteArray, jint);
 }
@@ -52,6 +54,16 @@ EXPORT long ref_fixed_batch(int outerc, int window, int out_len, int inner_len, 
     jbyteArray b = mk(base, base_len), s = mk(scalars, ls);
     long r = take(Java_algebra_msm_FixedBaseMSM_batchMSMNativeHelper(&env, nullptr, outerc, window, out_len, inner_len, n, scalar_size, b, s, bn_type, 0), out, cap);
     delete b; delete s;
+    return r;
+}
+EXPORT long ref_fixed_double_batch(int outerc1, int window1, int outerc2, int window2, int out_len1, int inner_len1, int out_len2, int inner_len2,
+                                   int n, const void* base1, size_t l1, const void* base2, size_t l2, const void* scalars, size_t ls, void* out,
+                                   size_t cap) {
+    JNIEnv env;
+    jbyteArray b1 = mk(base1, l1), b2 = mk(base2, l2), s = mk(scalars, ls);
+    long r = take(Java_algebra_msm_FixedBaseMSM_doubleBatchMSMNativeHelper(&env, nullptr, outerc1, window1, outerc2, window2, out_len1, inner_len1,
+                                                                         out_len2, inner_len2, n, b1, b2, s, 0), out, cap);
+    delete b1; delete b2; delete s;
     return r;
 }
 EXPORT long ref_field_batch(const void* scalars_plus_base, size_t len, int n, void* out, size_t cap) {

@@ -25,27 +25,40 @@ struct Obj {
 
 std::string g_exception;
 std::atomic<int> g_live_pins{0};   // natives are entered from several threads at once (test_concurrent_executor_threads)
+// JNI rule: between GetPrimitiveArrayCritical and ReleasePrimitiveArrayCritical a thread must not call any other JNI function.
+// Every fake function below except those two calls not_in_critical(); violations are counted for the tests.
+thread_local int t_pins = 0;
+std::atomic<int> g_critical_violations{0};
+std::atomic<int> g_pin_calls{0};
+std::atomic<int> g_fail_next_pin{0};   // test hook: the next GetPrimitiveArrayCritical calls return NULL
+void not_in_critical() {
+    if (t_pins > 0) g_critical_violations++;
+}
 int g_method_size = 1, g_method_get = 2;
 
 Obj* O(jobject o) { return reinterpret_cast<Obj*>(o); }
 jobject J(Obj* o) { return reinterpret_cast<jobject>(o); }
 
 jclass FindClass(JNIEnv*, const char* name) {
+    not_in_critical();
     Obj* c = new Obj{K_CLASS};
     c->name = name;
     return J(c);
 }
 jint ThrowNew(JNIEnv*, jclass c, const char* msg) {
+    not_in_critical();
     g_exception = O(c)->name + ": " + msg;
     return 0;
 }
-void DeleteLocalRef(JNIEnv*, jobject) {}
+void DeleteLocalRef(JNIEnv*, jobject) { not_in_critical(); }
 jmethodID GetMethodID(JNIEnv*, jclass, const char* name, const char*) {
+    not_in_critical();
     if (!strcmp(name, "size")) return reinterpret_cast<jmethodID>(&g_method_size);
     if (!strcmp(name, "get")) return reinterpret_cast<jmethodID>(&g_method_get);
     return nullptr;
 }
 jobject CallObjectMethod(JNIEnv*, jobject o, jmethodID m, ...) {
+    not_in_critical();
     va_list ap;
     va_start(ap, m);
     jint idx = va_arg(ap, jint);
@@ -55,30 +68,57 @@ jobject CallObjectMethod(JNIEnv*, jobject o, jmethodID m, ...) {
     return J(O(o)->items[idx]);
 }
 jint CallIntMethod(JNIEnv*, jobject o, jmethodID m, ...) {
+    not_in_critical();
     if (m != reinterpret_cast<jmethodID>(&g_method_size) || O(o)->kind != K_LIST) return -1;
     return (jint)O(o)->items.size();
 }
-jsize GetArrayLength(JNIEnv*, jarray a) { return (jsize)O(a)->bytes.size(); }
+jsize GetArrayLength(JNIEnv*, jarray a) {
+    not_in_critical();
+    return (jsize)O(a)->bytes.size();
+}
 jbyteArray NewByteArray(JNIEnv*, jsize n) {
+    not_in_critical();
     Obj* o = new Obj{K_BYTES};
     o->bytes.resize((size_t)n);
     return J(o);
 }
-void GetByteArrayRegion(JNIEnv*, jbyteArray a, jsize start, jsize len, jbyte* buf) { memcpy(buf, O(a)->bytes.data() + start, (size_t)len); }
-void SetByteArrayRegion(JNIEnv*, jbyteArray a, jsize start, jsize len, const jbyte* buf) { memcpy(O(a)->bytes.data() + start, buf, (size_t)len); }
+void GetByteArrayRegion(JNIEnv*, jbyteArray a, jsize start, jsize len, jbyte* buf) {
+    not_in_critical();
+    memcpy(buf, O(a)->bytes.data() + start, (size_t)len);
+}
+void SetByteArrayRegion(JNIEnv*, jbyteArray a, jsize start, jsize len, const jbyte* buf) {
+    not_in_critical();
+    memcpy(O(a)->bytes.data() + start, buf, (size_t)len);
+}
 void* GetPrimitiveArrayCritical(JNIEnv*, jarray a, jboolean* is_copy) {
     if (is_copy) *is_copy = 0;
+    g_pin_calls++;
+    if (g_fail_next_pin > 0) {
+        g_fail_next_pin--;
+        return nullptr;
+    }
     O(a)->pins++;
     g_live_pins++;
+    t_pins++;
     return O(a)->bytes.data();
 }
 void ReleasePrimitiveArrayCritical(JNIEnv*, jarray a, void*, jint) {
     O(a)->pins--;
     g_live_pins--;
+    t_pins--;
 }
-jboolean ExceptionCheck(JNIEnv*) { return g_exception.empty() ? 0 : 1; }
-void* GetDirectBufferAddress(JNIEnv*, jobject b) { return O(b)->kind == K_DIRECT ? O(b)->bytes.data() : nullptr; }
-jlong GetDirectBufferCapacity(JNIEnv*, jobject b) { return O(b)->kind == K_DIRECT ? (jlong)O(b)->bytes.size() : -1; }
+jboolean ExceptionCheck(JNIEnv*) {
+    not_in_critical();
+    return g_exception.empty() ? 0 : 1;
+}
+void* GetDirectBufferAddress(JNIEnv*, jobject b) {
+    not_in_critical();
+    return O(b)->kind == K_DIRECT ? O(b)->bytes.data() : nullptr;
+}
+jlong GetDirectBufferCapacity(JNIEnv*, jobject b) {
+    not_in_critical();
+    return O(b)->kind == K_DIRECT ? (jlong)O(b)->bytes.size() : -1;
+}
 
 JNINativeInterface_ g_table;
 JNIEnv_ g_env;
@@ -145,4 +185,7 @@ EXPORT void fj_free(void* o) {
 EXPORT const char* fj_exception() { return g_exception.empty() ? nullptr : g_exception.c_str(); }
 EXPORT void fj_clear_exception() { g_exception.clear(); }
 EXPORT int fj_live_pins() { return g_live_pins; }
+EXPORT int fj_critical_violations() { return g_critical_violations; }
+EXPORT int fj_pin_calls() { return g_pin_calls; }
+EXPORT void fj_fail_next_pins(int k) { g_fail_next_pin = k; }
 }

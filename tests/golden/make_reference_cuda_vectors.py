@@ -69,6 +69,19 @@ def main(out_path):
     sb = O.pack_scalars(sc)
     add("fixed_batch_g1", n=n, scalar_size=ss, window=w, outerc=outerc, base=O.pack_g1([base]), scalars=sb,
         out=R.isolated("fixed_batch", outerc, w, outerc, 1 << w, n, ss, O.pack_g1([base]), sb, 1))
+    # fixed-base batch on G2 (BNType != 1) and the paired G1 + G2 call (doubleBatchMSMNativeHelper,
+    # algebra_msm_FixedBaseMSM.cu:1395-1491), seed-10 generators, scalarSize 253 / 254 as the Java passes
+    base2 = O.G2.random(10)
+    ss2, w2 = 254, 4
+    outerc2 = (ss2 + w2 - 1) // w2
+    m = 12
+    sb2 = O.pack_scalars(sc[:m])
+    add("fixed_batch_g2", n=m, scalar_size=ss2, window=w2, outerc=outerc2, base=O.pack_g2([base2]), scalars=sb2,
+        out=R.isolated("fixed_batch", outerc2, w2, outerc2, 1 << w2, m, ss2, O.pack_g2([base2]), sb2, 2))
+    add("fixed_double_batch", n=m, scalar_size1=ss, window1=w, outerc1=outerc, scalar_size2=ss2, window2=w2, outerc2=outerc2,
+        base1=O.pack_g1([base]), base2=O.pack_g2([base2]), scalars=sb2,
+        out=R.isolated("fixed_double_batch", outerc, w, outerc2, w2, outerc, 1 << w, outerc2, 1 << w2, m, O.pack_g1([base]),
+                       O.pack_g2([base2]), sb2))
     b = rng.randrange(O.R)
     add("field_batch", n=n, scalars=sb, b=O.le32(b), out=R.isolated("field_batch", sb + O.le32(b), n))
     os.makedirs(os.path.dirname(os.path.abspath(out_path)), exist_ok=True)

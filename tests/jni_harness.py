@@ -79,3 +79,13 @@ class FakeJvm:
 
     def live_pins(self):
         return self.fj.fj_live_pins()
+
+    def critical_violations(self):
+        """JNI calls made by a thread while it held a GetPrimitiveArrayCritical pin (forbidden by the JNI specification)."""
+        return self.fj.fj_critical_violations()
+
+    def pin_calls(self):
+        return self.fj.fj_pin_calls()
+
+    def fail_next_pins(self, k):
+        self.fj.fj_fail_next_pins(k)

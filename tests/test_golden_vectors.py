@@ -24,7 +24,8 @@ def _scalars(h):
 
 def test_fixture_present_and_complete():
     kinds = [c["kind"] for c in _cases()]
-    assert kinds.count("var_msm_g1") == 3 and {"var_msm_g2", "var_double_msm", "fixed_batch_g1", "field_batch"} <= set(kinds)
+    assert kinds.count("var_msm_g1") == 3 and {"var_msm_g2", "var_double_msm", "fixed_batch_g1", "fixed_batch_g2", "fixed_double_batch",
+                                               "field_batch"} <= set(kinds)
 
 
 def test_oracle_reproduces_reference_outputs():
@@ -48,6 +49,19 @@ def test_oracle_reproduces_reference_outputs():
             exp = O.fixed_batch_msm(O.G1, c["scalar_size"], c["window"], base, sc)
             got = O.unpack_g1(out, stride=64, big_endian=True)
             assert len(got) == c["n"] and all(O.G1.equals(a, b) for a, b in zip(got, exp))
+        elif c["kind"] == "fixed_batch_g2":
+            base = O.unpack_g2(bytes.fromhex(c["base"]))[0]
+            exp = O.fixed_batch_msm(O.G2, c["scalar_size"], c["window"], base, sc)
+            got = O.unpack_g2(out, stride=64, big_endian=True)
+            assert len(got) == c["n"] and all(O.G2.equals(a, b) for a, b in zip(got, exp))
+        elif c["kind"] == "fixed_double_batch":
+            b1, b2 = O.unpack_g1(bytes.fromhex(c["base1"]))[0], O.unpack_g2(bytes.fromhex(c["base2"]))[0]
+            e1 = O.fixed_batch_msm(O.G1, c["scalar_size1"], c["window1"], b1, sc)
+            e2 = O.fixed_batch_msm(O.G2, c["scalar_size2"], c["window2"], b2, sc)
+            for i in range(c["n"]):                     # element i = G1 (192 B) || G2 (384 B), SURVEY.md Appendix A.2
+                blk = out[576 * i:576 * (i + 1)]
+                assert O.G1.equals(O.unpack_g1(blk[:192], stride=64, big_endian=True)[0], e1[i])
+                assert O.G2.equals(O.unpack_g2(blk[192:], stride=64, big_endian=True)[0], e2[i])
         elif c["kind"] == "field_batch":
             b = O.from_le(bytes.fromhex(c["b"]))
             assert [int.from_bytes(out[64 * i:64 * i + 64], "big") for i in range(c["n"])] == O.field_batch_msm(sc, b)
@@ -75,6 +89,17 @@ def test_liboctozk_reproduces_reference_outputs():
             got = O.unpack_g1(ctx.fixed_g1(bytes.fromhex(c["base"]), sb, n, c["outerc"], c["window"]))
             ref = O.unpack_g1(out, stride=64, big_endian=True)
             assert all(O.G1.equals(a, b) for a, b in zip(got, ref))
+        elif c["kind"] == "fixed_batch_g2":
+            got = O.unpack_g2(ctx.fixed_g2(bytes.fromhex(c["base"]), sb, n, c["outerc"], c["window"]))
+            ref = O.unpack_g2(out, stride=64, big_endian=True)
+            assert len(got) == n and all(O.G2.equals(a, b) for a, b in zip(got, ref))
+        elif c["kind"] == "fixed_double_batch":
+            g1 = O.unpack_g1(ctx.fixed_g1(bytes.fromhex(c["base1"]), sb, n, c["outerc1"], c["window1"]))
+            g2 = O.unpack_g2(ctx.fixed_g2(bytes.fromhex(c["base2"]), sb, n, c["outerc2"], c["window2"]))
+            for i in range(n):
+                blk = out[576 * i:576 * (i + 1)]
+                assert O.G1.equals(g1[i], O.unpack_g1(blk[:192], stride=64, big_endian=True)[0])
+                assert O.G2.equals(g2[i], O.unpack_g2(blk[192:], stride=64, big_endian=True)[0])
         elif c["kind"] == "field_batch":
             got = ctx.fr_scale(sb, bytes.fromhex(c["b"]))
             assert [O.from_le(got[32 * i:32 * i + 32]) for i in range(n)] == [int.from_bytes(out[64 * i:64 * i + 64], "big") for i in range(n)]

@@ -191,3 +191,65 @@ def test_concurrent_executor_threads(jvm):
         for out in outs:
             assert len(out) == 192 and O.G1.equals(O.unpack_g1(out, stride=64)[0], exp)
     assert jvm.live_pins() == 0
+
+
+def test_critical_regions_hold_no_jni_calls_and_are_per_slice(jvm):
+    """JNI rule: no JNI function between Get/ReleasePrimitiveArrayCritical; and the big MSM arrays are pinned one slice at a
+    time (ozk_msm_feed), not across the GPU call.  A pin that fails must surface as a RuntimeException raised OUTSIDE any
+    critical region, with every other pin released and the context usable afterwards."""
+    f = jvm.fn("libAlgebraMSMVariableBaseMSM.so", "Java_algebra_msm_VariableBaseMSM_variableBaseSerialMSMNativeHelper", [vp, vp, i32, i32, i32])
+    n = 1 << 18                                              # two slices (ozk_msm_plan_slices)
+    ks, pool = util.known_dlog_points(O.G1, 64, seed=91, random_z=True)
+    raw = util.rand_scalars_bytes(n, seed=91)
+    bases = util.tiled_bases_bytes(O.G1, pool, n)
+    exp = util.expected_from_dlogs(O.G1, ks, util.column_sums(raw, 64))
+    jb, js = jvm.bytes_(bases.tobytes()), jvm.bytes_(raw.tobytes())
+    p0 = jvm.pin_calls()
+    r = f(jvm.env, None, jb, js, n, 1, 0)
+    assert r and jvm.exception() is None
+    assert O.G1.equals(O.unpack_g1(jvm.read(r), stride=64)[0], exp)
+    assert jvm.pin_calls() - p0 == 4                         # 2 slices x (scalars, bases)
+    assert jvm.live_pins() == 0 and jvm.critical_violations() == 0
+    # a pin fails: exception, no pin left, nothing thrown from inside a critical region
+    jvm.fail_next_pins(1)                                    # the very first pin of the call fails
+    r = f(jvm.env, None, jb, js, n, 1, 0)
+    assert not r and "could not pin" in jvm.exception()
+    jvm.clear()
+    jvm.fail_next_pins(0)
+    assert jvm.live_pins() == 0 and jvm.critical_violations() == 0
+    r = f(jvm.env, None, jb, js, n, 1, 0)                    # the context is usable again
+    assert r and O.G1.equals(O.unpack_g1(jvm.read(r), stride=64)[0], exp)
+    # fixed-base and field natives never pin
+    p0 = jvm.pin_calls()
+    h = jvm.fn("libAlgebraMSMFixedBaseMSM.so", "Java_algebra_msm_FixedBaseMSM_fieldBatchMSMNativeHelper", [vp, i32, i32])
+    r = h(jvm.env, None, jvm.bytes_(O.pack_scalars([1, 2, 3]) + O.le32(5)), 3, 0)
+    out = jvm.read(r)
+    assert [int.from_bytes(out[64 * i:64 * i + 64], "big") for i in range(3)] == [5, 10, 15]
+    assert jvm.pin_calls() == p0 and jvm.critical_violations() == 0
+
+
+def test_stale_key_handles_throw(jvm):
+    """A jlong that is not a live handle of uploadBasesDirect (freed, or garbage) is a RuntimeException, not a wild pointer."""
+    i64 = ctypes.c_int64
+    up = jvm.fn("libAlgebraMSMVariableBaseMSM.so", "Java_algebra_msm_VariableBaseMSM_uploadBasesDirect", [vp, i32, i32, i32], i64)
+    keyed = jvm.fn("libAlgebraMSMVariableBaseMSM.so", "Java_algebra_msm_VariableBaseMSM_variableBaseMSMKeyedDirect",
+                   [i64, i64, vp, i32, i32, i32, i32, vp], i32)
+    free = jvm.fn("libAlgebraMSMVariableBaseMSM.so", "Java_algebra_msm_VariableBaseMSM_freeBases", [i64, i32], None)
+    pts = [O.G1.mul(O.G1.generator, k) for k in (3, 4)]
+    k1 = up(jvm.env, None, jvm.direct(O.pack_g1(pts)), 2, 1, 0)
+    assert k1
+    ob = jvm.direct(size=96)
+    sc = jvm.direct(O.pack_scalars([5, 6]))
+    assert keyed(jvm.env, None, k1, 0, sc, 0, 2, 1, 0, ob) == 0
+    assert O.G1.equals(O.unpack_g1(jvm.read(ob))[0], O.G1.mul(O.G1.generator, 39))
+    free(jvm.env, None, k1, 0)
+    assert jvm.exception() is None
+    assert keyed(jvm.env, None, k1, 0, sc, 0, 2, 1, 0, ob) == -1           # freed handle
+    assert "live handle" in jvm.exception()
+    jvm.clear()
+    assert keyed(jvm.env, None, 0x1234, 0, sc, 0, 2, 1, 0, ob) == -1       # garbage
+    assert "live handle" in jvm.exception()
+    jvm.clear()
+    free(jvm.env, None, k1, 0)                                             # double free
+    assert "live handle" in jvm.exception()
+    jvm.clear()

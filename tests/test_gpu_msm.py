@@ -112,17 +112,28 @@ def test_paired_matches_separate(ctx):
 
 @pytest.mark.parametrize("gname,log_n", [("G1", 14), ("G1", 16), ("G1", 18), ("G1", 20), ("G2", 14), ("G2", 16)])
 def test_large_known_dlog(ctx, gname, log_n):
-    """Sizes the oracle cannot add point by point: bases are tiled from 64 points with known discrete logs, so the
-    exact answer is (sum_i s_i k_{i mod 64}) G."""
+    """Sizes the oracle cannot add point by point: n DISTINCT bases P_i = k_i G made on the GPU (fixed-base path, every
+    point with its own Jacobian Z; sampled entries re-checked by the oracle) and scalars uniform in [0, r) with the edge
+    values forced in, so the exact answer is (sum_i s_i k_i mod r) G.  An error in any bit of a point
+    index -- a truncated index, a mis-strided slice -- changes the result."""
     G = O.G1 if gname == "G1" else O.G2
     n = 1 << log_n
-    ks, pool = util.known_dlog_points(G, 64, seed=log_n, random_z=True)
-    raw = util.rand_scalars_bytes(n, seed=log_n)
-    bases = util.tiled_bases_bytes(G, pool, n)
+    d_b, ks = util.gpu_distinct_bases(ctx, G, n, seed=log_n, keep_z=True)
+    raw = util.force_edge_scalars(util.rand_scalars_full_range(n, seed=log_n))
     fn = ctx.msm_g1 if G is O.G1 else ctx.msm_g2
-    out = fn(raw.tobytes(), bases.tobytes(), n)
-    exp = util.expected_from_dlogs(G, ks, util.column_sums(raw, 64))
-    assert G.equals(util.unpack_point(G, out), exp)
+    out = fn(raw, d_b.cpu().numpy(), n)                       # host-pointer entry point (pageable numpy buffers)
+    assert G.equals(util.unpack_point(G, out), util.expected_from_dot(G, raw, ks))
+
+
+def test_large_tiled_random_z_pool(ctx):
+    """The previous form of the large-size check, kept for the normalisation path with adversarial Z values: bases tiled from
+    64 oracle-made points with random Z."""
+    n = 1 << 16
+    ks, pool = util.known_dlog_points(O.G1, 64, seed=16, random_z=True)
+    raw = util.rand_scalars_full_range(n, seed=16)
+    bases = util.tiled_bases_bytes(O.G1, pool, n)
+    out = ctx.msm_g1(raw.tobytes(), bases.tobytes(), n)
+    assert O.G1.equals(O.unpack_g1(out)[0], util.expected_from_dlogs(O.G1, ks, util.column_sums(raw, 64)))
 
 
 def test_profiler_distribution_identical_bases(ctx):
@@ -266,21 +277,70 @@ def test_sum_of_wire_points(ctx):
 
 @pytest.mark.timeout(900)
 def test_headline_size_2_24_known_dlog(ctx):
-    """BASELINE.json configs[1] at its headline size: 2^24 (scalar, point) pairs, bases tiled from 64 points with known
-    discrete logs (random Z), exact answer (sum_i s_i k_{i mod 64}) G; device-resident entry point, then the same through a
-    persistent key with half of the pairs at an offset."""
+    """BASELINE.json configs[1] at its headline size: 2^24 (scalar, point) pairs, 2^24 DISTINCT bases k_i G generated on the
+    GPU (unnormalised Jacobian, every point its own Z), scalars uniform in [0, r) with forced edge values; exact answer
+    (sum_i s_i k_i mod r) G.  Device-resident entry point, then the same through a persistent key with half of the pairs at
+    an offset, then the paired G1+G2 call at 2^20 on distinct G2 bases."""
     import torch
     n = 1 << 24
-    ks, pool = util.known_dlog_points(O.G1, 64, seed=24, random_z=True)
-    raw = util.rand_scalars_bytes(n, seed=24)
+    d_b, ks = util.gpu_distinct_bases(ctx, O.G1, n, seed=24, keep_z=True)
+    raw = util.force_edge_scalars(util.rand_scalars_full_range(n, seed=24))
     d_s = torch.from_numpy(raw).cuda()
-    d_b = torch.from_numpy(np.ascontiguousarray(util.tiled_bases_bytes(O.G1, pool, n))).cuda()
     out = ctx.msm_g1_dev(d_s, d_b, n)
-    exp = util.expected_from_dlogs(O.G1, ks, util.column_sums(raw, 64))
-    assert O.G1.equals(O.unpack_g1(out)[0], exp)
+    assert O.G1.equals(O.unpack_g1(out)[0], util.expected_from_dot(O.G1, raw, ks))
     key = ctx.upload_bases(1, d_b, n, device=True)
     half = n // 2
     out = ctx.msm_keyed(d_s[half:].contiguous(), key, half, first=half, device=True)
-    exp = util.expected_from_dlogs(O.G1, ks, util.column_sums(raw[half:], 64))
+    assert O.G1.equals(O.unpack_g1(out)[0], util.expected_from_dot(O.G1, raw[half:], ks[half:]))
+    key.free()
+    del d_b, key
+    torch.cuda.empty_cache()
+    m = 1 << 20
+    d_b1, k1 = util.gpu_distinct_bases(ctx, O.G1, m, seed=25, keep_z=False)
+    d_b2, k2 = util.gpu_distinct_bases(ctx, O.G2, m, seed=26, keep_z=True)
+    out = ctx.msm_g1g2_dev(d_s[:m].contiguous(), d_b1, d_b2, m)
+    assert O.G1.equals(O.unpack_g1(out[:96])[0], util.expected_from_dot(O.G1, raw[:m], k1))
+    assert O.G2.equals(O.unpack_g2(out[96:])[0], util.expected_from_dot(O.G2, raw[:m], k2))
+
+
+def test_streaming_begin_feed_end(ctx):
+    """ozk_msm_begin / _feed / _end: ragged feeds (also a single pair, and empty ones) into one MSM equal the whole-array call;
+    paired groups; a persistent key for one group; misuse is an error, not a crash."""
+    from octopuszk_b200 import OzkError
+    rng = random.Random(71)
+    n = 70001
+    k1, p1 = util.known_dlog_points(O.G1, 64, seed=71, random_z=True)
+    k2, p2 = util.known_dlog_points(O.G2, 64, seed=72, random_z=True)
+    raw = util.rand_scalars_bytes(n, seed=71)
+    b1 = np.ascontiguousarray(util.tiled_bases_bytes(O.G1, p1, n))
+    b2 = np.ascontiguousarray(util.tiled_bases_bytes(O.G2, p2, n))
+    sums = util.column_sums(raw, 64)
+    e1, e2 = util.expected_from_dlogs(O.G1, k1, sums), util.expected_from_dlogs(O.G2, k2, sums)
+    cuts = [0, 1, 1, 4097, 30000, 30000, 69999, n]
+    ctx.msm_begin(3, n, max_slice=40000)
+    for lo, hi in zip(cuts, cuts[1:]):
+        ctx.msm_feed(raw[lo:hi], b1[lo:hi], b2[lo:hi], hi - lo)
+    out = ctx.msm_end(3)
+    assert O.G1.equals(O.unpack_g1(out[:96])[0], e1) and O.G2.equals(O.unpack_g2(out[96:])[0], e2)
+    # G1 from a persistent key at an offset, scalars streamed
+    key = ctx.upload_bases(1, b1, n)
+    first = 64 * 100
+    m = n - first
+    ctx.msm_begin(1, m, key1=key, first=first)
+    ctx.msm_feed(raw[:m // 2], None, None, m // 2)
+    ctx.msm_feed(raw[m // 2:m], None, None, m - m // 2)
+    out = ctx.msm_end(1)
+    exp = util.expected_from_dlogs(O.G1, k1, util.column_sums(raw[:m], 64))     # key[first + i] = pool[i mod 64] since 64 | first
     assert O.G1.equals(O.unpack_g1(out)[0], exp)
     key.free()
+    with pytest.raises(OzkError):
+        ctx.msm_feed(raw[:1], b1[:1], None, 1)               # nothing in progress
+    ctx.msm_begin(1, 10)
+    ctx.msm_feed(raw[:4], b1[:4], None, 4)
+    with pytest.raises(OzkError):
+        ctx.msm_end(1)                                       # fewer pairs than announced
+    ctx.msm_begin(1, 4)
+    with pytest.raises(OzkError):
+        ctx.msm_feed(raw[:5], b1[:5], None, 5)               # more than announced
+    out = ctx.msm_g1(raw[:100], b1[:100], 100)               # the context still works
+    assert O.G1.equals(O.unpack_g1(out)[0], util.expected_from_dlogs(O.G1, k1, util.column_sums(raw[:100], 64)))

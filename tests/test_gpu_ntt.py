@@ -72,9 +72,8 @@ def test_ntt_large_spot_check_and_roundtrip(ctx, log_n):
     import numpy as np
     rng = random.Random(200 + log_n)
     n = 1 << log_n
-    raw = np.frombuffer(rng.randbytes(n * 32), dtype=np.uint8).reshape(n, 32).copy()
-    raw[:, 31] &= 0x1F                      # < 2^253 < r : canonical
-    x_bytes = raw.tobytes()
+    from tests import util
+    x_bytes = util.rand_scalars_full_range(n, seed=200 + log_n).tobytes()      # uniform in [0, r)
     omega = O.root_of_unity(n)
     y_bytes = ctx.ntt(x_bytes, O.le32(omega))
     ks = [0, 1, n - 1, n // 2] + [rng.randrange(n) for _ in range(2)]
@@ -93,6 +92,63 @@ def test_ntt_large_spot_check_and_roundtrip(ctx, log_n):
     yd = ctx.ntt(bytes(d), O.le32(omega))
     for k in ks:
         assert O.from_le(yd[32 * k:32 * k + 32]) == pow(omega, j * k, O.R)
+
+
+@pytest.mark.parametrize("log_n", [19, 20, 22])
+def test_ntt_three_pass_full_compare_c_oracle(ctx, log_n):
+    """The three-pass sizes (2^19 and up; the headline 2^26 runs the same kernels) compared ELEMENT FOR ELEMENT with the C
+    restatement of FFTAuxiliary.serialRadix2FFT (oracle/dizk_oracle.c, itself checked against the Python oracle in
+    tests/test_oracle_c.py): forward, inverse (SerialFFT.radix2InverseFFT) and coset forward (radix2CosetFFT) on inputs
+    uniform in [0, r) with the edge values 0, 1, r - 1 forced in (full compare up to 2^22)."""
+    import numpy as np
+    import torch
+    from oracle import c_oracle as C
+    from tests import util
+    n = 1 << log_n
+    raw = util.rand_scalars_full_range(n, seed=300 + log_n)
+    for pos, v in enumerate([0, 1, O.R - 1, O.R - 2, 1 << 253]):
+        raw[pos] = np.frombuffer(O.le32(v), dtype=np.uint8)
+    x_bytes = raw.tobytes()
+    omega = O.root_of_unity(n)
+    w, winv = O.le32(omega), O.le32(pow(omega, -1, O.R))
+    g = O.FR_MULT_GEN
+    d_in = torch.from_numpy(raw).cuda()
+    d_out = torch.empty_like(d_in)
+
+    def gpu(**kw):
+        ctx.ntt_ex_dev(d_in, d_out, n, **kw)
+        ctx.sync()
+        return d_out.cpu().numpy().tobytes()
+
+    assert gpu(omega=w) == C.fft_fr(x_bytes, w), "forward"
+    exp = C.fr_scale(C.fft_fr(x_bytes, winv), O.le32(pow(n, -1, O.R)))
+    assert gpu(omega=winv, post_scale=O.le32(pow(n, -1, O.R))) == exp, "inverse"
+    assert gpu(omega=w, pre_coset=O.le32(g)) == C.fft_fr(C.fr_coset_scale(x_bytes, g), w), "coset forward"
+    # the host-pointer entry point (what the JNI shim calls) on the same input
+    assert ctx.ntt(x_bytes, w) == C.fft_fr(x_bytes, w)
+
+
+@pytest.mark.timeout(1200)
+@pytest.mark.parametrize("log_n", [24, 26])
+def test_ntt_headline_sizes_horner_spots(ctx, log_n):
+    """2^24 and the headline 2^26 on inputs uniform in [0, r): K = 64 outputs (fixed corner indices and random ones) against
+    the definition out[k] = sum_j in[j] omega^(jk), evaluated by the C oracle's Horner loop over the whole input
+    (SerialFFTTest.java:168-190 compares with naive evaluation)."""
+    import torch
+    from oracle import c_oracle as C
+    from tests import util
+    n = 1 << log_n
+    raw = util.rand_scalars_full_range(n, seed=400 + log_n)
+    omega = O.root_of_unity(n)
+    d_in = torch.from_numpy(raw).cuda()
+    d_out = torch.empty_like(d_in)
+    ctx.ntt_dev(d_in, d_out, n, O.le32(omega))
+    ctx.sync()
+    rng = random.Random(log_n)
+    ks = [0, 1, 2, n - 1, n // 2, n // 2 + 1, (1 << 9) - 1, 1 << 9, 1 << 18, (1 << 18) + 1] + [rng.randrange(n) for _ in range(54)]
+    got = [O.from_le(d_out[k].cpu().numpy().tobytes()) for k in ks]
+    exp = C.fr_horner(raw, n, [pow(omega, k, O.R) for k in ks])
+    assert got == exp
 
 
 def test_ntt_rejects_bad_omega(ctx):
