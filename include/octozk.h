@@ -94,12 +94,25 @@ OZK_API int ozk_fr_lagrange_dev(ozk_ctx* ctx, void* d_out, size_t m, const uint8
  * R1CStoQAP.java:143-160, LinearCombination.evaluate).  At most 4096 rows may have more than 64 terms.  SURVEY.md 8f row 4. */
 OZK_API int ozk_fr_spmv_dev(ozk_ctx* ctx, const void* d_row_ptr, const void* d_col, const void* d_coeff, const void* d_z, size_t rows,
                             void* d_out);
+/* Same with the length of z given: a column index >= z_len is reported as OZK_ERR_ARG instead of being dereferenced (the form
+ * above trusts the matrix).  d_coeff == NULL: every coefficient is 1 (the reference's synthetic circuit,
+ * src/main/java/profiler/generation/R1CSConstruction.java:48-104, has no other), which also serves the transposed products of
+ * R1CStoQAP.R1CStoQAPRelation (At[j] = sum_i L_i(t) A[i][j], R1CStoQAP.java:62-80) with z = the Lagrange coefficients. */
+OZK_API int ozk_fr_spmv_ex_dev(ozk_ctx* ctx, const void* d_row_ptr, const void* d_col, const void* d_coeff, const void* d_z, size_t z_len,
+                               size_t rows, void* d_out);
+/* out[i] = ca * a[i] + cb * b[i] + cc * c[i] mod r (d_b / d_c may be NULL; out may alias an input): the vector combinations of
+ * SerialSetup.generate (beta At + alpha Bt + Ct and the divisions by gamma / delta,
+ * src/main/java/zk_proof_systems/zkSNARK/SerialSetup.java:66-85) on device-resident vectors. */
+OZK_API int ozk_fr_lincomb_dev(ozk_ctx* ctx, void* d_out, size_t n, const void* d_a, const uint8_t ca[32], const void* d_b,
+                               const uint8_t cb[32], const void* d_c, const uint8_t cc[32]);
 
 /* ---- radix-2 NTT over Fr ---------------------------------------------------------------------------------
  * out[k] = sum_j in[j] * omega^(j k), natural order in and out, n a power of two <= 2^28, omega a primitive n-th
  * root of unity.  Replaces FFTAuxiliary.serialRadix2FFT (src/main/java/algebra/fft/FFTAuxiliary.java:60-124) and the
  * dormant Java_algebra_fft_FFTAuxiliary_serialRadix2FFTNativeHelper / best_fft (algebra_fft_FFTAuxiliary.cu:167-260).
- * d_in == d_out is allowed. */
+ * d_in == d_out is allowed.  Elements must be reduced mod r: the host-pointer entry points (ozk_ntt_fr, ozk_fr_scale) check it
+ * and return OZK_ERR_DOMAIN; the "_dev" entry points only enqueue work and do not (unreduced elements give unspecified
+ * values there, never a memory fault). */
 OZK_API int ozk_ntt_fr(ozk_ctx* ctx, uint8_t* data, size_t n, const uint8_t omega[32]);
 OZK_API int ozk_ntt_fr_dev(ozk_ctx* ctx, const void* d_in, void* d_out, size_t n, const uint8_t omega[32]);
 /* Fused wrappers of src/main/java/algebra/fft/SerialFFT.java:75-115,157-162:

@@ -29,7 +29,11 @@
 
 namespace ozk {
 
-static constexpr int kMaxLogT = 9;          // largest in-CTA transform: 512 points
+static constexpr int kMaxLogT = 9;          // largest in-CTA transform: 512 points ...
+// ... except for transforms of more than 2^27 points, which would need a fourth pass (2^28 = 7+7+7+7): there the first pass takes
+// 1024 points per CTA (one column per tile, 16 KB of twiddles, four CTAs per SM) so that 2^28 = 10+9+9 stays at three passes.
+static constexpr int kMaxLogTBig = 10;
+static inline int max_log_t_for(int log_n) { return log_n > 3 * kMaxLogT ? kMaxLogTBig : kMaxLogT; }
 // Tile of 1024 elements (32 KB) per 128-thread CTA, five CTAs per SM (__launch_bounds__(128, 5): 96 registers, ~100 bytes of
 // spills) whose load / transform / store phases interleave (measured 2^26: 16.3 ms with 2048-element tiles and two CTAs per SM,
 // 15.9 ms with 1024-element tiles and four, 14.7 ms with five together with the direct twiddle tables below).
@@ -57,7 +61,38 @@ struct NttPlan {
     Fr* thi = nullptr;            // omega_n^(e 2^H), e < 2^(log_n - H)
     Fr* tdir[kMaxPasses] = {};    // per pass: direct inter-pass twiddles omega_n^(outer * col * k) at [k][col], when n_j * inner is small enough
     void* block = nullptr;
+    size_t bytes = 0;             // size of `block`
+    unsigned long long last_use = 0;
 };
+
+// The plan cache is bounded: a plan with direct tables is up to 2 GiB per (n, omega), the prover uses four of them per domain,
+// and a JNI host keeps one context per executor thread for the thread's lifetime.  Least-recently-used plans are dropped when
+// a new one would push the context over the budget (OZK_NTT_CACHE_MB, default 16 GiB); a dropped plan is simply rebuilt on its
+// next use (a few ms).
+static size_t plan_budget_bytes() {
+    static const size_t b = (size_t)env_int("OZK_NTT_CACHE_MB", 16384, 64, 1 << 20) << 20;
+    return b;
+}
+static unsigned long long g_plan_clock = 0;
+static int plan_cache_make_room(ozk_ctx* ctx, size_t incoming) {
+    size_t total = incoming;
+    for (auto& kv : ctx->ntt_plans) total += kv.second->bytes;
+    bool synced = false;
+    while (total > plan_budget_bytes() && !ctx->ntt_plans.empty()) {
+        auto victim = ctx->ntt_plans.begin();
+        for (auto it = ctx->ntt_plans.begin(); it != ctx->ntt_plans.end(); ++it)
+            if (it->second->last_use < victim->second->last_use) victim = it;
+        if (!synced) {
+            OZK_CUDA(cudaStreamSynchronize(ctx->stream));      // kernels reading the victim's tables may still be in flight
+            synced = true;
+        }
+        total -= victim->second->bytes;
+        if (victim->second->block) cudaFree(victim->second->block);
+        delete victim->second;
+        ctx->ntt_plans.erase(victim);
+    }
+    return OZK_OK;
+}
 
 // ---- small helpers -----------------------------------------------------------------------------------------
 __device__ __forceinline__ Fr load_fr(const uint4* p) {
@@ -208,6 +243,16 @@ __device__ __forceinline__ void sts_fr(uint4* lo, uint4* hi, uint32_t s, const F
     hi[s] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
 }
 
+// Asynchronous 16-byte global -> shared copies (LDGSTS): the tile load issues all of a thread's copies back to back and waits once,
+// instead of one load-to-register / store-to-shared round trip per 16 bytes (16 dependent DRAM latencies per thread and tile).
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
 // Q decimation-in-frequency stages on 2^Q registers.  Element u sits at index base + u*m of the transform; stage a
 // pairs u with u + 2^(Q-1-a).  The twiddle of a pair depends only on (u mod half) and j = index mod m.
 // M_IS_ONE (the final step, m == 1): exponents with u_local == 0 are zero, those multiplications are skipped.
@@ -298,7 +343,7 @@ __global__ void __launch_bounds__(128, 5) ntt_pass_kernel(PassArgs a) {
 
     // ---- twiddles of the in-CTA transform
     for (uint32_t i = threadIdx.x; i < T; i += blockDim.x) {     // T/2 entries of two uint4 each
-        reinterpret_cast<uint4*>(wtab)[i] = reinterpret_cast<const uint4*>(a.wsub)[i];
+        cp_async16(reinterpret_cast<uint4*>(wtab) + i, reinterpret_cast<const uint4*>(a.wsub) + i);
     }
 
     // ---- load the tile (16 bytes per thread per step, fastest index = the contiguous one in global memory)
@@ -308,8 +353,7 @@ __global__ void __launch_bounds__(128, 5) ntt_pass_kernel(PassArgs a) {
         for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
             uint32_t t = i >> (log_c + 1), r = i & (per_row - 1);
             uint32_t c = r >> 1, h = r & 1;
-            uint4 v = a.in[(in_base + ((size_t)t << a.log_inner) + c) * 2 + h];
-            (h ? hi : lo)[Layout<LAST>::slot(t, c, LOGT, log_c)] = v;
+            cp_async16(&(h ? hi : lo)[Layout<LAST>::slot(t, c, LOGT, log_c)], &a.in[(in_base + ((size_t)t << a.log_inner) + c) * 2 + h]);
         }
     } else {
         const uint32_t log_rho = a.log_outer - a.log_n1;
@@ -318,10 +362,10 @@ __global__ void __launch_bounds__(128, 5) ntt_pass_kernel(PassArgs a) {
         for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
             uint32_t c = i >> (LOGT + 1), r = i & (per_row - 1);
             uint32_t t = r >> 1, h = r & 1;
-            uint4 v = a.in[(in_base + ((((size_t)c << log_rho)) << LOGT) + t) * 2 + h];
-            (h ? hi : lo)[Layout<LAST>::slot(t, c, LOGT, log_c)] = v;
+            cp_async16(&(h ? hi : lo)[Layout<LAST>::slot(t, c, LOGT, log_c)], &a.in[(in_base + ((((size_t)c << log_rho)) << LOGT) + t) * 2 + h]);
         }
     }
+    cp_async_wait_all();
     __syncthreads();
 
     // ---- DIF stages from half-size T/2 down to 1: (LOGT mod 3) single stages first, then radix-8 steps.  (Merging two leftover
@@ -345,38 +389,54 @@ __global__ void __launch_bounds__(128, 5) ntt_pass_kernel(PassArgs a) {
         }
     }
 
-    // ---- store: element k of the transform sits at bit-reversed position; lanes run along the contiguous output index
+    // ---- store: element k of the transform sits at bit-reversed position; lanes run along the contiguous output index.
+    // kStoreBatch elements per thread are handled together: their inter-pass twiddles (one 32-byte global read each, no reuse) are
+    // requested first, so the DRAM latencies of a batch overlap instead of adding up.
     const uint32_t total = T << log_c;
-    for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
-        const uint32_t c = i & (C - 1);
-        const uint32_t k = i >> log_c;
-        const uint32_t pos = LOGT ? (__brev(k) >> (32 - LOGT)) : 0;
-        Fr v = lds_fr(lo, hi, Layout<LAST>::slot(pos, c, LOGT, log_c));
+    constexpr int kStoreBatch = 4;
+    for (uint32_t i0 = threadIdx.x; i0 < total; i0 += blockDim.x * kStoreBatch) {
+        Fr w[kStoreBatch];
         if (!LAST) {
-            // inter-pass twiddle omega_n^(outer * column * k)
-            const uint32_t ek = (col0 + c) * k;
-            if (ek != 0) {
-                if (a.tdir) {
-                    v = Fr::mul(v, a.tdir[((size_t)k << a.log_inner) + col0 + c]);
-                } else {
-                    const uint32_t e = ek << a.log_outer;
-                    Fr w = Fr::mul(a.tlo[e & ((1u << a.H) - 1)], a.thi[e >> a.H]);
-                    v = Fr::mul(v, w);
+#pragma unroll
+            for (int u = 0; u < kStoreBatch; u++) {
+                const uint32_t i = i0 + u * blockDim.x;
+                const uint32_t c = i & (C - 1), k = i >> log_c;
+                const uint32_t ek = (col0 + c) * k;
+                if (i < total && ek != 0) {
+                    if (a.tdir) {
+                        w[u] = a.tdir[((size_t)k << a.log_inner) + col0 + c];
+                    } else {
+                        const uint32_t e = ek << a.log_outer;
+                        w[u] = Fr::mul(a.tlo[e & ((1u << a.H) - 1)], a.thi[e >> a.H]);
+                    }
                 }
             }
-            store_fr(a.out + (out_base + ((size_t)k << a.log_inner) + c) * 2, v);
-        } else {
-            const size_t idx = out_base + ((size_t)k << a.log_outer) + c;
-            if (a.npeers) {
-                if (idx != 0 && a.my_rank != 0) {
-                    const Fr w = Fr::mul(a.ptlo[idx & ((1u << a.pH) - 1)], a.pthi[idx >> a.pH]);
-                    v = Fr::mul(v, w);
-                }
-                const uint32_t dest = (uint32_t)(idx >> a.log_chunk);
-                const size_t local = ((size_t)a.my_rank << a.log_chunk) + (idx & (((size_t)1 << a.log_chunk) - 1));
-                store_fr(a.peer[dest] + local * 2, v);       // peer memory over NVLink (or this GPU's own buffer)
+        }
+#pragma unroll
+        for (int u = 0; u < kStoreBatch; u++) {
+            const uint32_t i = i0 + u * blockDim.x;
+            if (i >= total) break;
+            const uint32_t c = i & (C - 1);
+            const uint32_t k = i >> log_c;
+            const uint32_t pos = LOGT ? (__brev(k) >> (32 - LOGT)) : 0;
+            Fr v = lds_fr(lo, hi, Layout<LAST>::slot(pos, c, LOGT, log_c));
+            if (!LAST) {
+                // inter-pass twiddle omega_n^(outer * column * k)
+                if ((col0 + c) * k != 0) v = Fr::mul(v, w[u]);
+                store_fr(a.out + (out_base + ((size_t)k << a.log_inner) + c) * 2, v);
             } else {
-                store_fr(a.out + idx * 2, v);
+                const size_t idx = out_base + ((size_t)k << a.log_outer) + c;
+                if (a.npeers) {
+                    if (idx != 0 && a.my_rank != 0) {
+                        const Fr wp = Fr::mul(a.ptlo[idx & ((1u << a.pH) - 1)], a.pthi[idx >> a.pH]);
+                        v = Fr::mul(v, wp);
+                    }
+                    const uint32_t dest = (uint32_t)(idx >> a.log_chunk);
+                    const size_t local = ((size_t)a.my_rank << a.log_chunk) + (idx & (((size_t)1 << a.log_chunk) - 1));
+                    store_fr(a.peer[dest] + local * 2, v);       // peer memory over NVLink (or this GPU's own buffer)
+                } else {
+                    store_fr(a.out + idx * 2, v);
+                }
             }
         }
     }
@@ -499,13 +559,22 @@ __global__ void __launch_bounds__(256) fr_lagrange_unit(uint4* __restrict__ out,
 static constexpr uint32_t kSpmvShort = 64;
 static constexpr uint32_t kSpmvLongCap = 4096;
 
-__device__ __forceinline__ Fr spmv_term(const uint4* coeff, const uint4* z, const uint32_t* col, size_t k) {
-    return Fr::mul(Fr::to_mont(load_fr(coeff + k * 2)), load_fr(z + (size_t)col[k] * 2));     // canonical coeff * z
+// coeff == nullptr: every coefficient is 1 (the reference's synthetic circuit, R1CSConstruction.java:48-104, and most gates of
+// real circuits).  A column index >= z_len sets flag bit 0 and contributes nothing, so a malformed matrix cannot read out of bounds.
+__device__ __forceinline__ Fr spmv_term(const uint4* coeff, const uint4* z, const uint32_t* col, size_t k, size_t z_len, uint32_t* flag) {
+    const size_t c = col[k];
+    if (c >= z_len) {
+        atomicOr(flag, 1u);
+        return Fr::zero();
+    }
+    const Fr zv = load_fr(z + c * 2);
+    if (!coeff) return zv;
+    return Fr::mul(Fr::to_mont(load_fr(coeff + k * 2)), zv);     // canonical coeff * z
 }
 
 __global__ void __launch_bounds__(256) fr_spmv_short(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col, const uint4* __restrict__ coeff,
-                                                     const uint4* __restrict__ z, size_t rows, uint4* __restrict__ out, uint32_t* __restrict__ long_rows,
-                                                     uint32_t* __restrict__ long_count) {
+                                                     const uint4* __restrict__ z, size_t z_len, size_t rows, uint4* __restrict__ out,
+                                                     uint32_t* __restrict__ long_rows, uint32_t* __restrict__ long_count, uint32_t* __restrict__ flag) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows) return;
     const uint32_t lo = row_ptr[i], hi = row_ptr[i + 1];
@@ -515,29 +584,86 @@ __global__ void __launch_bounds__(256) fr_spmv_short(const uint32_t* __restrict_
         return;
     }
     Fr acc = Fr::zero();
-    for (uint32_t k = lo; k < hi; k++) acc = Fr::add(acc, spmv_term(coeff, z, col, k));
+    for (uint32_t k = lo; k < hi; k++) acc = Fr::add(acc, spmv_term(coeff, z, col, k, z_len, flag));
     store_fr(out + i * 2, acc);
 }
 
+// Long rows are cut into segments of kSpmvSeg terms; blocks walk the (row, segment) pairs, each leaving one partial sum, and
+// fr_spmv_long_finish adds the partials of every row (a row over all 2^24 variables -- the last constraint of the synthetic
+// circuit -- is 1024 segments spread over all SMs instead of one block's 65 536 serial steps).
+static constexpr uint32_t kSpmvSeg = 1u << 14;
+static constexpr uint32_t kSpmvMaxSegs = 1u << 17;        // partial sums available (4 MB of scratch)
 __global__ void __launch_bounds__(256) fr_spmv_long(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col, const uint4* __restrict__ coeff,
-                                                    const uint4* __restrict__ z, uint4* __restrict__ out, const uint32_t* __restrict__ long_rows,
-                                                    const uint32_t* __restrict__ long_count) {
+                                                    const uint4* __restrict__ z, size_t z_len, uint4* __restrict__ partial,
+                                                    const uint32_t* __restrict__ long_rows, const uint32_t* __restrict__ long_count,
+                                                    uint32_t* __restrict__ flag) {
     __shared__ Fr part[256];
     const uint32_t total = min(*long_count, kSpmvLongCap);
-    for (uint32_t q = blockIdx.x; q < total; q += gridDim.x) {
+    uint32_t seg_base = 0;                                  // index of the first segment of row q among all segments
+    for (uint32_t q = 0; q < total; q++) {
         const uint32_t i = long_rows[q];
         const uint32_t lo = row_ptr[i], hi = row_ptr[i + 1];
-        Fr acc = Fr::zero();
-        for (uint32_t k = lo + threadIdx.x; k < hi; k += blockDim.x) acc = Fr::add(acc, spmv_term(coeff, z, col, k));
-        part[threadIdx.x] = acc;
-        __syncthreads();
-        for (uint32_t s = 128; s >= 1; s >>= 1) {
-            if (threadIdx.x < s) part[threadIdx.x] = Fr::add(part[threadIdx.x], part[threadIdx.x + s]);
+        const uint32_t nseg = (hi - lo + kSpmvSeg - 1) / kSpmvSeg;
+        // segments of this row taken by this block: those whose global segment index is congruent to blockIdx.x
+        uint32_t first = (blockIdx.x + gridDim.x - seg_base % gridDim.x) % gridDim.x;
+        for (uint32_t sg = first; sg < nseg; sg += gridDim.x) {
+            if (seg_base + sg >= kSpmvMaxSegs) {
+                if (threadIdx.x == 0) atomicOr(flag, 2u);
+                break;
+            }
+            const uint32_t a = lo + sg * kSpmvSeg, b = min(hi, a + kSpmvSeg);
+            Fr acc = Fr::zero();
+            for (uint32_t k = a + threadIdx.x; k < b; k += blockDim.x) acc = Fr::add(acc, spmv_term(coeff, z, col, k, z_len, flag));
+            part[threadIdx.x] = acc;
+            __syncthreads();
+            for (uint32_t s = 128; s >= 1; s >>= 1) {
+                if (threadIdx.x < s) part[threadIdx.x] = Fr::add(part[threadIdx.x], part[threadIdx.x + s]);
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) store_fr(partial + (size_t)(seg_base + sg) * 2, part[0]);
             __syncthreads();
         }
-        if (threadIdx.x == 0) store_fr(out + (size_t)i * 2, part[0]);
-        __syncthreads();
+        seg_base += nseg;
     }
+}
+__global__ void __launch_bounds__(128) fr_spmv_long_finish(const uint32_t* __restrict__ row_ptr, const uint4* __restrict__ partial, uint4* __restrict__ out,
+                                                           const uint32_t* __restrict__ long_rows, const uint32_t* __restrict__ long_count) {
+    const uint32_t total = min(*long_count, kSpmvLongCap);
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= total) return;
+    uint32_t seg_base = 0;
+    for (uint32_t p = 0; p < q; p++) {
+        const uint32_t ip = long_rows[p];
+        seg_base += (row_ptr[ip + 1] - row_ptr[ip] + kSpmvSeg - 1) / kSpmvSeg;
+    }
+    const uint32_t i = long_rows[q];
+    const uint32_t nseg = (row_ptr[i + 1] - row_ptr[i] + kSpmvSeg - 1) / kSpmvSeg;
+    Fr acc = Fr::zero();
+    for (uint32_t sg = 0; sg < nseg && seg_base + sg < kSpmvMaxSegs; sg++) acc = Fr::add(acc, load_fr(partial + (size_t)(seg_base + sg) * 2));
+    store_fr(out + (size_t)i * 2, acc);
+}
+
+// out[i] = ca * a[i] + cb * b[i] + cc * c[i] (b, c optional): the linear combinations of the setup, beta*At + alpha*Bt + Ct and
+// their division by gamma / delta (SerialSetup.java:66-85), on vectors that stay on the device.  Constants canonical.
+__global__ void __launch_bounds__(256) fr_lincomb_kernel(uint4* __restrict__ out, size_t n, const uint4* __restrict__ a, Fr ca_canon,
+                                                         const uint4* __restrict__ b, Fr cb_canon, const uint4* __restrict__ c, Fr cc_canon) {
+    const Fr ca = Fr::to_mont(ca_canon), cb = Fr::to_mont(cb_canon), cc = Fr::to_mont(cc_canon);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        Fr v = Fr::mul(ca, load_fr(a + i * 2));                      // Montgomery constant * canonical value = canonical product
+        if (b) v = Fr::add(v, Fr::mul(cb, load_fr(b + i * 2)));
+        if (c) v = Fr::add(v, Fr::mul(cc, load_fr(c + i * 2)));
+        store_fr(out + i * 2, v);
+    }
+}
+
+// flag |= 4 when some element of in[0..n) is not reduced mod r (the host-pointer entry points reject such input; Fr::add / sub
+// rely on operands below the modulus)
+__global__ void __launch_bounds__(256) fr_check_canonical_kernel(const uint4* __restrict__ in, size_t n, uint32_t* __restrict__ flag) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) bad |= !load_fr(in + i * 2).is_canonical();
+    if (bad) atomicOr(flag, 4u);
 }
 
 // ---- small cross-shard DFT (the second step of the multi-GPU transform) ---------------------------------------------------
@@ -602,6 +728,7 @@ static int ntt_get_plan(ozk_ctx* ctx, int log_n, const uint8_t omega[32], NttPla
     key.push_back((char)log_n);
     auto it = ctx->ntt_plans.find(key);
     if (it != ctx->ntt_plans.end()) {
+        it->second->last_use = ++g_plan_clock;
         *out = it->second;
         return OZK_OK;
     }
@@ -619,7 +746,8 @@ static int ntt_get_plan(ozk_ctx* ctx, int log_n, const uint8_t omega[32], NttPla
     }
     NttPlan* p = new NttPlan();
     p->log_n = log_n;
-    p->npass = log_n <= kMaxLogT ? 1 : (log_n + kMaxLogT - 1) / kMaxLogT;
+    const int max_t = env_int("OZK_NTT_MAX_LOGT", max_log_t_for(log_n), 7, kMaxLogTBig);
+    p->npass = log_n <= max_t ? 1 : (log_n + max_t - 1) / max_t;
     {
         int rem = log_n;
         for (int j = 0; j < p->npass; j++) {
@@ -654,7 +782,14 @@ static int ntt_get_plan(ozk_ctx* ctx, int log_n, const uint8_t omega[32], NttPla
             log_outer += p->logt[j];
         }
     }
-    OZK_CUDA(cudaMalloc(&p->block, count * sizeof(Fr)));
+    p->bytes = count * sizeof(Fr);
+    p->last_use = ++g_plan_clock;
+    if (plan_cache_make_room(ctx, p->bytes) != OZK_OK || cudaMalloc(&p->block, p->bytes) != cudaSuccess) {
+        cudaGetLastError();
+        delete p;
+        set_error("ozk_ntt_fr: out of device memory for the twiddle tables of a 2^%d-point transform", log_n);
+        return OZK_ERR_CUDA;
+    }
     Fr* base = (Fr*)p->block;
     for (int j = 0; j < p->npass; j++) {
         p->wsub[j] = base + off_w[j];
@@ -745,7 +880,7 @@ static int ntt_run(ozk_ctx* ctx, const void* d_in, void* d_out, int log_n, const
         a.log_outer = log_n - lt - log_inner;
         a.log_t = lt;
         if (!last) {
-            int lc = env_int("OZK_NTT_TILE_LOG", kTileLogDefault, 9, 10) - lt;
+            int lc = std::max(0, env_int("OZK_NTT_TILE_LOG", kTileLogDefault, 9, 10) - lt);
             if (lc > log_inner) lc = log_inner;
             a.log_c = lc;
             uint32_t grid = 1u << (log_n - lt - lc);
@@ -755,7 +890,7 @@ static int ntt_run(ozk_ctx* ctx, const void* d_in, void* d_out, int log_n, const
             a.nmid = p->npass > 2 ? p->npass - 2 : 0;
             a.logmid0 = a.nmid > 0 ? p->logt[1] : 0;
             a.logmid1 = a.nmid > 1 ? p->logt[2] : 0;
-            int lc = env_int("OZK_NTT_TILE_LOG", kTileLogDefault, 9, 10) - lt;
+            int lc = std::max(0, env_int("OZK_NTT_TILE_LOG", kTileLogDefault, 9, 10) - lt);
             if (lc > (int)a.log_n1) lc = a.log_n1;
             a.log_c = lc;
             if (sc) {
@@ -804,6 +939,7 @@ static int get_pow_table(ozk_ctx* ctx, const uint8_t base[32], int log_range, Nt
     key.push_back((char)log_range);
     auto it = ctx->ntt_plans.find(key);
     if (it != ctx->ntt_plans.end()) {
+        it->second->last_use = ++g_plan_clock;
         *out = it->second;
         return OZK_OK;
     }
@@ -811,7 +947,9 @@ static int get_pow_table(ozk_ctx* ctx, const uint8_t base[32], int log_range, Nt
     tw->log_n = log_range;
     tw->H = (log_range + 1) / 2;
     const size_t nlo = (size_t)1 << tw->H, nhi = (size_t)1 << (log_range - tw->H);
-    if (cudaMalloc(&tw->block, (nlo + nhi) * sizeof(Fr)) != cudaSuccess) {
+    tw->bytes = (nlo + nhi) * sizeof(Fr);
+    tw->last_use = ++g_plan_clock;
+    if (plan_cache_make_room(ctx, tw->bytes) != OZK_OK || cudaMalloc(&tw->block, tw->bytes) != cudaSuccess) {
         delete tw;
         set_error("twiddle table: out of device memory");
         cudaGetLastError();
@@ -858,6 +996,27 @@ static int scale_powers(ozk_ctx* ctx, const void* d_in, void* d_out, size_t n, c
     return OZK_OK;
 }
 
+// Range check of the host-pointer entry points (they synchronise for the download anyway): one HBM-bound pass over the uploaded
+// input that raises a flag, read back after the download.  The "_dev" entry points only enqueue and state the precondition.
+static int check_canonical_begin(ozk_ctx* ctx, const void* d_in, size_t n) {
+    OZK_TRY(ctx->io_out.reserve(512 + (size_t)kSpmvLongCap * 4, ctx->stream));
+    uint32_t* flag = (uint32_t*)((char*)ctx->io_out.p + 400);
+    OZK_CUDA(cudaMemsetAsync(flag, 0, 4, ctx->stream));
+    size_t blocks = std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 16);
+    fr_check_canonical_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>((const uint4*)d_in, n, flag);
+    ctx->launches += 1;
+    OZK_CUDA(cudaMemcpyAsync((char*)ctx->pinned + 2048, flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    return OZK_OK;
+}
+static int check_canonical_end(ozk_ctx* ctx, const char* who) {
+    OZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (*(const uint32_t*)((const char*)ctx->pinned + 2048) & 4u) {
+        set_error("%s: an input element is not reduced mod r", who);
+        return OZK_ERR_DOMAIN;
+    }
+    return OZK_OK;
+}
+
 }  // namespace ozk
 
 using namespace ozk;
@@ -896,8 +1055,10 @@ int ozk_ntt_fr(ozk_ctx* ctx, uint8_t* data, size_t n, const uint8_t omega[32]) {
     const size_t bytes = n * 32;
     OZK_TRY(ctx->io_a.reserve(bytes, ctx->stream));
     OZK_TRY(upload_any(ctx, ctx->io_a.p, data, bytes, ctx->stream));
+    OZK_TRY(check_canonical_begin(ctx, ctx->io_a.p, n));
     OZK_TRY(ntt_run(ctx, ctx->io_a.p, ctx->io_a.p, log_n, omega));
-    return download_any(ctx, data, ctx->io_a.p, bytes, ctx->stream);
+    OZK_TRY(download_any(ctx, data, ctx->io_a.p, bytes, ctx->stream));
+    return check_canonical_end(ctx, "ozk_ntt_fr");
 }
 
 int ozk_fr_scale_dev(ozk_ctx* ctx, const void* d_a, void* d_out, size_t n, const uint8_t b[32]) {
@@ -1039,29 +1200,76 @@ int ozk_ntt_fr_scatter_dev(ozk_ctx* ctx, const void* d_in, void* const* peer_out
     return ntt_run(ctx, d_in, nullptr, log_m, omega_local, &sc);
 }
 
-int ozk_fr_spmv_dev(ozk_ctx* ctx, const void* d_row_ptr, const void* d_col, const void* d_coeff, const void* d_z, size_t rows, void* d_out) {
-    OZK_TRY(ctx_enter(ctx));
-    OZK_ARG(rows == 0 || (d_row_ptr && d_col && d_coeff && d_z && d_out), "ozk_fr_spmv_dev: null pointer");
-    OZK_ARG(rows < ((size_t)1 << 31), "ozk_fr_spmv_dev: too many rows");
+static int spmv_run(ozk_ctx* ctx, const void* d_row_ptr, const void* d_col, const void* d_coeff, const void* d_z, size_t z_len, size_t rows,
+                    void* d_out, const char* who) {
     if (rows == 0) return OZK_OK;
     cudaStream_t st = ctx->stream;
     OZK_TRY(ctx->io_out.reserve(512 + (size_t)kSpmvLongCap * 4, st));
     uint32_t* long_count = (uint32_t*)((char*)ctx->io_out.p + 384);
+    uint32_t* flag = long_count + 1;
     uint32_t* long_rows = (uint32_t*)((char*)ctx->io_out.p + 512);
-    OZK_CUDA(cudaMemsetAsync(long_count, 0, 4, st));
+    OZK_CUDA(cudaMemsetAsync(long_count, 0, 8, st));
     fr_spmv_short<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>((const uint32_t*)d_row_ptr, (const uint32_t*)d_col, (const uint4*)d_coeff,
-                                                                  (const uint4*)d_z, rows, (uint4*)d_out, long_rows, long_count);
-    fr_spmv_long<<<ctx->sm_count, 256, 0, st>>>((const uint32_t*)d_row_ptr, (const uint32_t*)d_col, (const uint4*)d_coeff, (const uint4*)d_z,
-                                                (uint4*)d_out, long_rows, long_count);
-    ctx->launches += 2;
+                                                                  (const uint4*)d_z, z_len, rows, (uint4*)d_out, long_rows, long_count, flag);
+    OZK_TRY(ctx->work.reserve((size_t)kSpmvMaxSegs * 32, st));            // partial sums of the long rows (the NTT scratch, same stream)
+    fr_spmv_long<<<ctx->sm_count * 4, 256, 0, st>>>((const uint32_t*)d_row_ptr, (const uint32_t*)d_col, (const uint4*)d_coeff, (const uint4*)d_z, z_len,
+                                                    (uint4*)ctx->work.p, long_rows, long_count, flag);
+    fr_spmv_long_finish<<<(kSpmvLongCap + 127) / 128, 128, 0, st>>>((const uint32_t*)d_row_ptr, (const uint4*)ctx->work.p, (uint4*)d_out, long_rows,
+                                                                   long_count);
+    ctx->launches += 3;
     OZK_CUDA(cudaGetLastError());
     uint32_t* pin = (uint32_t*)ctx->pinned;
-    OZK_CUDA(cudaMemcpyAsync(pin, long_count, 4, cudaMemcpyDeviceToHost, st));
+    OZK_CUDA(cudaMemcpyAsync(pin, long_count, 8, cudaMemcpyDeviceToHost, st));
     OZK_CUDA(cudaStreamSynchronize(st));
     if (pin[0] > kSpmvLongCap) {
-        set_error("ozk_fr_spmv_dev: more than %u rows with over %u terms", kSpmvLongCap, kSpmvShort);
+        set_error("%s: more than %u rows with over %u terms", who, kSpmvLongCap, kSpmvShort);
         return OZK_ERR_ARG;
     }
+    if (pin[1] & 1u) {
+        set_error("%s: a column index is outside the assignment (>= %zu)", who, z_len);
+        return OZK_ERR_ARG;
+    }
+    if (pin[1] & 2u) {
+        set_error("%s: the rows with over %u terms hold more than %u x %u terms in total", who, kSpmvShort, kSpmvMaxSegs, kSpmvSeg);
+        return OZK_ERR_ARG;
+    }
+    return OZK_OK;
+}
+
+int ozk_fr_spmv_dev(ozk_ctx* ctx, const void* d_row_ptr, const void* d_col, const void* d_coeff, const void* d_z, size_t rows, void* d_out) {
+    OZK_TRY(ctx_enter(ctx));
+    OZK_ARG(rows == 0 || (d_row_ptr && d_col && d_coeff && d_z && d_out), "ozk_fr_spmv_dev: null pointer");
+    OZK_ARG(rows < ((size_t)1 << 31), "ozk_fr_spmv_dev: too many rows");
+    return spmv_run(ctx, d_row_ptr, d_col, d_coeff, d_z, ~(size_t)0, rows, d_out, "ozk_fr_spmv_dev");
+}
+
+int ozk_fr_spmv_ex_dev(ozk_ctx* ctx, const void* d_row_ptr, const void* d_col, const void* d_coeff, const void* d_z, size_t z_len, size_t rows,
+                       void* d_out) {
+    OZK_TRY(ctx_enter(ctx));
+    OZK_ARG(rows == 0 || (d_row_ptr && d_col && d_z && d_out), "ozk_fr_spmv_ex_dev: null pointer");
+    OZK_ARG(rows < ((size_t)1 << 31), "ozk_fr_spmv_ex_dev: too many rows");
+    return spmv_run(ctx, d_row_ptr, d_col, d_coeff, d_z, z_len, rows, d_out, "ozk_fr_spmv_ex_dev");
+}
+
+int ozk_fr_lincomb_dev(ozk_ctx* ctx, void* d_out, size_t n, const void* d_a, const uint8_t ca[32], const void* d_b, const uint8_t cb[32],
+                       const void* d_c, const uint8_t cc[32]) {
+    OZK_TRY(ctx_enter(ctx));
+    OZK_ARG(n == 0 || (d_out && d_a && ca && (!d_b || cb) && (!d_c || cc)), "ozk_fr_lincomb_dev: null pointer");
+    if (n == 0) return OZK_OK;
+    Fr fa, fb, fc;
+    memset(&fb, 0, sizeof fb);
+    memset(&fc, 0, sizeof fc);
+    if (!fr_bytes_canonical(ca) || (d_b && !fr_bytes_canonical(cb)) || (d_c && !fr_bytes_canonical(cc))) {
+        set_error("ozk_fr_lincomb_dev: a constant is not reduced mod r");
+        return OZK_ERR_DOMAIN;
+    }
+    fr_from_bytes(fa, ca);
+    if (d_b) fr_from_bytes(fb, cb);
+    if (d_c) fr_from_bytes(fc, cc);
+    size_t blocks = std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 16);
+    fr_lincomb_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>((uint4*)d_out, n, (const uint4*)d_a, fa, (const uint4*)d_b, fb, (const uint4*)d_c, fc);
+    ctx->launches += 1;
+    OZK_CUDA(cudaGetLastError());
     return OZK_OK;
 }
 
@@ -1109,8 +1317,10 @@ int ozk_fr_scale(ozk_ctx* ctx, const uint8_t* a, size_t n, const uint8_t b[32], 
     const size_t bytes = n * 32;
     OZK_TRY(ctx->io_a.reserve(bytes, ctx->stream));
     OZK_TRY(upload_any(ctx, ctx->io_a.p, a, bytes, ctx->stream));
+    OZK_TRY(check_canonical_begin(ctx, ctx->io_a.p, n));
     OZK_TRY(scale_powers(ctx, ctx->io_a.p, ctx->io_a.p, n, b, nullptr));
-    return download_any(ctx, out, ctx->io_a.p, bytes, ctx->stream);
+    OZK_TRY(download_any(ctx, out, ctx->io_a.p, bytes, ctx->stream));
+    return check_canonical_end(ctx, "ozk_fr_scale");
 }
 
 }  // extern "C"

@@ -78,6 +78,16 @@ class GpuOps:
     def to_device(self, b: bytes):
         return torch.frombuffer(bytearray(b), dtype=torch.uint8).to(self.device)
 
+    def fixed(self, base: bytes, scalars, n, outerc, window, g2=False):
+        out = torch.empty((n, 192 if g2 else 96), dtype=torch.uint8, device=self.device)
+        (self.ctx.fixed_g2_dev if g2 else self.ctx.fixed_g1_dev)(base, scalars, n, outerc, window, out)
+        return out
+
+    def fr_scale(self, a, n, b: int):
+        out = torch.empty_like(a)
+        self.ctx.fr_scale_dev(a, out, n, _le32(b))
+        return out
+
 
 def _world(group):
     return dist.get_world_size(group) if dist.is_initialized() else 1
@@ -104,6 +114,43 @@ def msm_distributed(ops, scalars_local, bases_local, n_local: int, g2: bool = Fa
     for r in range(world):
         ones[32 * r] = 1
     return fn(ops.to_device(bytes(ones)), gathered, world)
+
+
+def _gather_equal(local, group):
+    """all ranks' equally sized shards, concatenated in rank order, on every rank"""
+    world = _world(group)
+    if world == 1:
+        return local
+    out = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out.view(-1), local.contiguous().view(-1), group=group)
+    return out.view((world * local.shape[0],) + tuple(local.shape[1:]))
+
+
+def fixed_batch_distributed(ops, base: bytes, scalars_local, n_local: int, outerc: int, window: int, g2: bool = False, gather: bool = False,
+                            group=None):
+    """FixedBaseMSM.distributedBatchMSM (src/main/java/algebra/msm/FixedBaseMSM.java:446-472: mapPartitions over the scalar
+    partitions against the broadcast window table), used by DistributedSetup.generate for queryA / queryH / deltaABC
+    (zk_proof_systems/zkSNARK/DistributedSetup.java:69-99,137-164): out[i] = scalars[i] * base for this rank's slice.  Embarrassingly
+    parallel: every rank walks its own slice against its own cached window table (built once per rank; nothing is broadcast), and
+    the outputs STAY SHARDED, in input order, where the sharded prover consumes them.  gather=True returns the whole vector on
+    every rank instead (equal slices required)."""
+    out = ops.fixed(base, scalars_local, n_local, outerc, window, g2)
+    return _gather_equal(out, group) if gather else out
+
+
+def fixed_double_batch_distributed(ops, base1: bytes, base2: bytes, scalars_local, n_local: int, outerc1: int, window1: int, outerc2: int,
+                                   window2: int, gather: bool = False, group=None):
+    """FixedBaseMSM.distributedDoubleBatchMSM (FixedBaseMSM.java:712-741; queryB of DistributedSetup, :110-135): the pairs
+    (s_i * base1 in G1, s_i * base2 in G2) of this rank's slice, as two sharded vectors."""
+    return (fixed_batch_distributed(ops, base1, scalars_local, n_local, outerc1, window1, False, gather, group),
+            fixed_batch_distributed(ops, base2, scalars_local, n_local, outerc2, window2, True, gather, group))
+
+
+def field_batch_distributed(ops, scalars_local, n_local: int, b: int, gather: bool = False, group=None):
+    """FixedBaseMSM.distributedFieldBatchMSM (FixedBaseMSM.java:880-900; DistributedSetup.java:69-76,169): a_i * b mod r on this
+    rank's slice."""
+    out = ops.fr_scale(scalars_local, n_local, b)
+    return _gather_equal(out, group) if gather else out
 
 
 class PeerExchange:

@@ -44,6 +44,8 @@ SIGNATURES = {
     "ozk_fr_scale_powers_dev": (_int, [_vp, _vp, _vp, _sz, _c_u8p, _c_u8p, ctypes.c_uint64]),
     "ozk_fr_mul_sub_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _sz]),
     "ozk_fr_spmv_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ozk_fr_spmv_ex_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _sz, _vp]),
+    "ozk_fr_lincomb_dev": (_int, [_vp, _vp, _sz, _vp, _c_u8p, _vp, _c_u8p, _vp, _c_u8p]),
     "ozk_fr_lagrange_dev": (_int, [_vp, _vp, _sz, _c_u8p, _c_u8p]),
     "ozk_ntt_fr_scatter_dev": (_int, [_vp, _vp, ctypes.POINTER(_vp), _sz, _sz, _sz, _c_u8p, _c_u8p]),
     "ozk_fr_dft_small_scatter_dev": (_int, [_vp, _vp, ctypes.POINTER(_vp), _sz, _sz, _sz, _c_u8p, _c_u8p]),
@@ -241,6 +243,15 @@ class Context:
 
     def fr_spmv_dev(self, d_row_ptr, d_col, d_coeff, d_z, rows: int, d_out):
         self._check(self.lib.ozk_fr_spmv_dev(self._h, self._dp(d_row_ptr), self._dp(d_col), self._dp(d_coeff), self._dp(d_z), rows, self._dp(d_out)))
+
+    def fr_spmv_ex_dev(self, d_row_ptr, d_col, d_coeff, d_z, z_len: int, rows: int, d_out):
+        """d_coeff None: unit coefficients; column indices are checked against z_len."""
+        self._check(self.lib.ozk_fr_spmv_ex_dev(self._h, self._dp(d_row_ptr), self._dp(d_col), self._dp(d_coeff) if d_coeff is not None else None,
+                                                self._dp(d_z), z_len, rows, self._dp(d_out)))
+
+    def fr_lincomb_dev(self, d_out, n: int, d_a, ca: bytes, d_b=None, cb: bytes = None, d_c=None, cc: bytes = None):
+        self._check(self.lib.ozk_fr_lincomb_dev(self._h, self._dp(d_out), n, self._dp(d_a), ca, self._dp(d_b) if d_b is not None else None, cb,
+                                                self._dp(d_c) if d_c is not None else None, cc))
 
     def fr_lagrange_dev(self, d_out, m: int, t: bytes, omega: bytes):
         self._check(self.lib.ozk_fr_lagrange_dev(self._h, self._dp(d_out), m, t, omega))

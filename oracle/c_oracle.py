@@ -30,6 +30,7 @@ def load():
     lib.oracle_fr_horner.argtypes = [vp, sz, vp, sz, i, vp]
     lib.oracle_fr_lagrange_eval.argtypes = [vp, sz, vp, vp, i, vp]
     lib.oracle_r1cs_chain.argtypes = [sz, vp, vp, vp]
+    lib.oracle_r1cs_synth_eval.argtypes = [sz, sz, vp, sz, sz, vp, vp, vp]
     _lib = lib
     return lib
 
@@ -129,3 +130,12 @@ def fr_coset_scale(a, g: int) -> bytes:
     out = ctypes.create_string_buffer(32 * n)
     load().oracle_fr_coset_scale(_addr(a), n, int(g).to_bytes(32, "little"), out)
     return out.raw
+
+
+def r1cs_synth_eval(nc: int, ni: int, z, col_limit: int, n_dom: int):
+    """(a, b, c) evaluation vectors ((n_dom, 32) uint8 each) of the synthetic circuit at assignment z, columns < col_limit only."""
+    import numpy as np
+    a, b, c = (np.empty((n_dom, 32), dtype=np.uint8) for _ in range(3))
+    rc = load().oracle_r1cs_synth_eval(nc, ni, _addr(z), col_limit, n_dom, a.ctypes.data, b.ctypes.data, c.ctypes.data)
+    assert rc == 0, rc
+    return a, b, c

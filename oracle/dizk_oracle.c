@@ -520,17 +520,38 @@ int oracle_fr_horner(const uint8_t* coeffs, size_t n, const uint8_t* xs, size_t 
     fe* c = (fe*)malloc((n ? n : 1) * sizeof(fe));
 #pragma omp parallel for num_threads(threads) schedule(static)
     for (long j = 0; j < (long)n; j++) load_fe(&FR, &c[j], coeffs + 32 * (size_t)j);
+    /* every point's polynomial is cut into chunks so that all threads have work: P(x) = sum_k x^(k L) P_k(x) */
+    size_t nchunks = npts ? ((size_t)threads * 2 + npts - 1) / npts : 1;
+    if (nchunks < 1) nchunks = 1;
+    if (nchunks > n / 1024 + 1) nchunks = n / 1024 + 1;
+    const size_t L = (n + nchunks - 1) / nchunks;
+    fe* part = (fe*)malloc((npts * nchunks + 1) * sizeof(fe));
 #pragma omp parallel for num_threads(threads) schedule(dynamic, 1)
-    for (long q = 0; q < (long)npts; q++) {
+    for (long item = 0; item < (long)(npts * nchunks); item++) {
+        const size_t q = (size_t)item / nchunks, k = (size_t)item % nchunks;
+        const size_t lo = k * L, hi = (lo + L < n) ? lo + L : n;
         fe x, acc;
-        load_fe(&FR, &x, xs + 32 * (size_t)q);
+        load_fe(&FR, &x, xs + 32 * q);
         memset(&acc, 0, sizeof acc);
-        for (size_t j = n; j-- > 0;) {
+        for (size_t j = hi; j-- > lo;) {
             fe_mul(&FR, &acc, &acc, &x);
             fe_add(&FR, &acc, &acc, &c[j]);
         }
-        store_fe(&FR, out + 32 * (size_t)q, &acc);
+        part[item] = acc;
     }
+    for (size_t q = 0; q < npts; q++) {
+        fe x, xl, acc;
+        load_fe(&FR, &x, xs + 32 * q);
+        uint64_t e[4] = {(uint64_t)L, 0, 0, 0};
+        fe_pow(&FR, &xl, &x, e);
+        memset(&acc, 0, sizeof acc);
+        for (size_t k = nchunks; k-- > 0;) {                  /* Horner over the chunks in x^L */
+            fe_mul(&FR, &acc, &acc, &xl);
+            fe_add(&FR, &acc, &acc, &part[q * nchunks + k]);
+        }
+        store_fe(&FR, out + 32 * q, &acc);
+    }
+    free(part);
     free(c);
     return 0;
 }
@@ -647,6 +668,59 @@ int oracle_fr_coset_scale(const uint8_t* a, size_t n, const uint8_t g_b[32], uin
         store_fe(&FR, out + 32 * i, &x);
         fe_mul(&FR, &u, &u, &g);
     }
+    return 0;
+}
+
+/* Evaluation vectors of R1CStoQAP.R1CStoQAPWitness (src/main/java/reductions/r1cs_to_qap/R1CStoQAP.java:143-160) for the
+ * reference's synthetic circuit (R1CSConstruction.serialConstruct, R1CSConstruction.java:48-104): a_j = <A_j, z>, b_j, c_j for
+ * every constraint j, the primary inputs appended to a at num_constraints + i (:151-153), zero up to the domain size n_dom.
+ * Only variables with index < col_limit contribute (col_limit = numVariables: the full vectors; col_limit = numInputs: the
+ * part of every row that belongs to the primary input, used to split sum_i z_i A_i(t) into its primary and auxiliary halves).
+ * z: numConstraints + 3 canonical elements; outputs n_dom canonical elements each. */
+int oracle_r1cs_synth_eval(size_t nc, size_t ni, const uint8_t* z, size_t col_limit, size_t n_dom, uint8_t* out_a, uint8_t* out_b,
+                           uint8_t* out_c) {
+    init_once();
+    const size_t nv = nc + 3;
+    if (n_dom < nc + ni || col_limit > nv) return -1;
+    memset(out_a, 0, 32 * n_dom);
+    memset(out_b, 0, 32 * n_dom);
+    memset(out_c, 0, 32 * n_dom);
+#define ZV(idx, dst) do { if ((size_t)(idx) < col_limit) load_fe(&FR, (dst), z + 32 * (size_t)(idx)); else memset((dst), 0, sizeof(fe)); } while (0)
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)nc - 1; i++) {
+        fe a, b, c, t;
+        if (i % 2 != 0) {                       /* A = x_{i+1}, B = x_{i+2}, C = x_{i+3} */
+            ZV(i + 1, &a);
+            ZV(i + 2, &b);
+        } else {                                /* A = x_{i+1} + x_{i+2}, B = x_0, C = x_{i+3} */
+            ZV(i + 1, &a);
+            ZV(i + 2, &t);
+            fe_add(&FR, &a, &a, &t);
+            ZV(0, &b);
+        }
+        ZV(i + 3, &c);
+        store_fe(&FR, out_a + 32 * (size_t)i, &a);
+        store_fe(&FR, out_b + 32 * (size_t)i, &b);
+        store_fe(&FR, out_c + 32 * (size_t)i, &c);
+    }
+    {                                           /* last constraint: A = B = sum_{1 <= j <= nv-2} x_j, C = x_{nv-1} */
+        fe sum, v;
+        memset(&sum, 0, sizeof sum);
+        for (size_t j = 1; j + 1 < nv; j++) {
+            ZV(j, &v);
+            fe_add(&FR, &sum, &sum, &v);
+        }
+        store_fe(&FR, out_a + 32 * (nc - 1), &sum);
+        store_fe(&FR, out_b + 32 * (nc - 1), &sum);
+        ZV(nv - 1, &v);
+        store_fe(&FR, out_c + 32 * (nc - 1), &v);
+    }
+    for (size_t i = 0; i < ni; i++) {
+        fe v;
+        ZV(i, &v);
+        store_fe(&FR, out_a + 32 * (nc + i), &v);
+    }
+#undef ZV
     return 0;
 }
 

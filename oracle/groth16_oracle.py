@@ -270,3 +270,44 @@ def proof_exponents(setup, primary, auxiliary, H) -> Tuple[int, int, int]:
     assert a * b % R == (alpha * beta + x_gamma * setup["gamma"] + c * delta) % R, "oracle proof does not verify"
     assert num_inputs == len(setup["gammaABC"])
     return a, b, c
+
+
+def proof_exponents_synthetic(num_constraints: int, num_inputs: int, threads: int = 0) -> Tuple[int, int, int]:
+    """The same (a, b, c) as `proof_exponents` for the reference's synthetic circuit, at ANY size, without building the QAP:
+    with L_j(t) the Lagrange coefficients of the domain at the setup point t (FFTAuxiliary.java:249-302),
+        sum_i z_i At_i = sum_j L_j(t) a_j        (a_j = <A_j, z>, inputs appended: R1CStoQAP.java:54-80 against :143-160)
+    and likewise for B and C, and H(t) Z(t) = A(t) B(t) - C(t) because the circuit is satisfied (QAPRelation.isSatisfied), so
+        a = alpha + A(t) + r delta,   b = beta + B(t) + s delta,
+        c = [beta A_aux(t) + alpha B_aux(t) + C_aux(t) + H(t) Z(t)] / delta + s a + r b - r s delta
+    where X_aux(t) = X(t) - (the same sum over the primary variables only).  Everything is O(domain) field work in the C oracle
+    (oracle_r1cs_chain, oracle_r1cs_synth_eval, oracle_fr_lagrange_eval); no group operation and no GPU result enters."""
+    from . import c_oracle as C
+    t = alpha = beta = gamma = delta = r = s = seed10()
+    nc, ni = num_constraints, num_inputs
+    n = O.SerialFFT(nc + ni).domain_size
+    omega = O.root_of_unity(n)
+    z = C.r1cs_chain(nc, seed10(), seed10())
+    nv = nc + 3
+    full = [C.fr_lagrange_eval(v, n, omega, t, threads) for v in C.r1cs_synth_eval(nc, ni, z, nv, n)]
+    prim = [C.fr_lagrange_eval(v, n, omega, t, threads) for v in C.r1cs_synth_eval(nc, ni, z, ni, n)]
+    at, bt, ct = full
+    hz = (at * bt - ct) % R
+    abc_aux = (beta * (at - prim[0]) + alpha * (bt - prim[1]) + (ct - prim[2])) % R
+    a = (alpha + at + r * delta) % R
+    b = (beta + bt + s * delta) % R
+    c = ((abc_aux + hz) * pow(delta, -1, R) + s * a + r * b - r * s * delta) % R
+    # the verification equation in the exponent (Verifier.java:36-51): the primary part of abc is what gammaABC carries
+    x_gamma = (beta * prim[0] + alpha * prim[1] + prim[2]) % R          # (sum_i x_i gammaABC_i) * gamma
+    assert a * b % R == (alpha * beta + x_gamma + c * delta) % R, "oracle proof does not verify"
+    return a, b, c
+
+
+def expected_proof_synthetic(num_constraints: int, num_inputs: int, threads: int = 0):
+    """The proof points SerialProver.prove must output for the synthetic circuit, as affine-normalised Jacobian triples:
+    (a g1, b g2, c g1) with g1 = BNG1.random(seed 10) = seed10 * G1one, g2 = seed10 * G2one (BNG1.java:125-127)."""
+    a, b, c = proof_exponents_synthetic(num_constraints, num_inputs, threads)
+    rho = seed10()
+    A = O.G1.to_affine(O.G1.mul(O.G1.generator, rho * a % R))
+    B = O.G2.to_affine(O.G2.mul(O.G2.generator, rho * b % R))
+    Cp = O.G1.to_affine(O.G1.mul(O.G1.generator, rho * c % R))
+    return A, B, Cp

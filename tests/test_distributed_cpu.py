@@ -54,6 +54,16 @@ class OracleOps:
     def msm_g1(self, scalars, bases, n):
         return C.msm_g1(scalars.numpy().tobytes(), bases.numpy().tobytes(), n, 1)
 
+    def fixed(self, base, scalars, n, outerc, window, g2=False):
+        assert not g2
+        sc = [O.from_le(bytes(scalars.reshape(-1)[32 * i:32 * i + 32].tolist())) for i in range(n)]
+        pts = [O.G1.mul(O.unpack_g1(base)[0], s % (1 << (outerc * window))) for s in sc]
+        return torch.frombuffer(bytearray(O.pack_g1(pts)), dtype=torch.uint8).view(n, 96)
+
+    def fr_scale(self, a, n, b):
+        out = C.fr_scale(a.numpy().tobytes(), O.le32(b))
+        return torch.frombuffer(bytearray(out), dtype=torch.uint8).view(a.shape)
+
 
 def _free_port():
     s = socket.socket()
@@ -90,6 +100,19 @@ def _worker(rank, world, port, q):
     ev = [[rng.randrange(O.R) for _ in range(n)] for _ in range(3)]
     sh = [torch.frombuffer(bytearray(D.ntt_scatter_cyclic(O.pack_scalars(v), world, rank)), dtype=torch.uint8) for v in ev]
     h = D.witness_map_distributed(ops, sh[0], sh[1], sh[2], n)
+    # ---- fixed-base batch and field batch over scalar slices (FixedBaseMSM.distributedBatchMSM / distributedFieldBatchMSM)
+    fsc = [rng.randrange(O.R) for _ in range(12)]
+    flo, fhi = rank * 12 // world, (rank + 1) * 12 // world
+    fs = torch.frombuffer(bytearray(O.pack_scalars(fsc[flo:fhi])), dtype=torch.uint8).view(-1, 32)
+    gbase = O.pack_g1([O.G1.random(10)])
+    f_sharded = D.fixed_batch_distributed(ops, gbase, fs, fhi - flo, 23, 11)
+    f_all = D.fixed_batch_distributed(ops, gbase, fs, fhi - flo, 23, 11, gather=True)
+    fld = D.field_batch_distributed(ops, fs, fhi - flo, 12345, gather=True)
+    assert f_sharded.shape == (fhi - flo, 96) and f_all.shape == (12, 96)
+    got = O.unpack_g1(f_all.numpy().tobytes())
+    assert all(O.G1.equals(a, b) for a, b in zip(got, O.fixed_batch_msm(O.G1, 253, 11, O.G1.random(10), fsc)))
+    fb = fld.numpy().tobytes()
+    assert [O.from_le(fb[32 * i:32 * i + 32]) for i in range(12)] == O.field_batch_msm(fsc, 12345)
     q.put((rank, out.numpy().tobytes(), res, x, scalars, bases, back.numpy().tobytes(), ev, h.numpy().tobytes()))
     dist.barrier()
     dist.destroy_process_group()
@@ -152,3 +175,31 @@ def test_scatter_gather_layouts_single_process():
     for d in range(world):
         outs.append(b"".join(x[(k1 * m + d * c + t) * 32:(k1 * m + d * c + t) * 32 + 32] for k1 in range(world) for t in range(c)))
     assert D.ntt_gather_natural(outs, n) == x
+
+
+def test_prover_shards_partition_everything():
+    """ProverShards (octopuszk_b200/prover.py): over all ranks the variable slices, the auxiliary slices and the H blocks cover every
+    index exactly once, the H blocks are the blocked layout witness_map_distributed leaves, and the rows that carry the primary
+    inputs are found on the right rank at the right local row."""
+    from octopuszk_b200.prover import ProverShards, domain_size
+    for nc, ni, world in ((64, 7, 1), (64, 7, 2), (61, 6, 4), (1 << 10, 50, 8), (1 << 15, 1023, 8)):
+        nv = nc + 3
+        n = domain_size(nc, ni)
+        seen_v, seen_a, seen_h, seen_in = [], [], [], {}
+        for rank in range(world):
+            sh = ProverShards(world, rank, n, ni, nv)
+            seen_v += list(range(*sh.var_range))
+            seen_a += list(range(*sh.aux_range))
+            for first, cnt in sh.h_blocks():
+                seen_h += list(range(first, first + cnt))
+            if world > 1:
+                m, c = n // world, n // world // world
+                assert sh.h_blocks() == [(k1 * m + rank * c, c) for k1 in range(world)]
+            ir = sh.input_rows(nc)
+            if ir is not None:
+                row0, var0, count, step = ir
+                for k in range(count):
+                    g_row = rank + world * (row0 + k)          # global domain index of local row row0 + k
+                    seen_in[g_row] = var0 + k * step
+        assert seen_v == list(range(nv)) and seen_a == list(range(nv - ni)) and sorted(seen_h) == list(range(n))
+        assert seen_in == {nc + i: i for i in range(ni)}

@@ -209,6 +209,33 @@ def _nccl_worker(rank, world, port, q):
     n_dom = len(sH) - 1
     m_dom, c_dom = n_dom // world, n_dom // world // world
     assert dH == [sH[k1 * m_dom + rank * c_dom + t] for k1 in range(world) for t in range(c_dom)]
+    # device-resident sharded setup + prover (octopuszk_b200/prover.py): each rank encodes only its slices of the query vectors,
+    # the proof equals the expected points (and hence the one-GPU proof) bit for bit after affine normalisation
+    from octopuszk_b200.groth16 import fr_random
+    from octopuszk_b200.prover import DeviceGroth16, synthetic_r1cs
+    from oracle import c_oracle as C
+    from oracle import groth16_oracle as GO
+    for nc_, ni_ in ((240, 15), (1 << 12, 100)):
+        dgz = DeviceGroth16(ctx, exchange=ex)
+        dpk, _ = dgz.setup(synthetic_r1cs(nc_, ni_, torch.device("cuda", rank)), keep_vk=False)
+        d_z = torch.from_numpy(C.r1cs_chain(nc_, fr_random(), fr_random())).cuda()
+        pA, pB, pC = dgz.prove(dpk, synthetic_r1cs(nc_, ni_, torch.device("cuda", rank), world, rank), d_z)
+        assert (O.G1.to_affine(pA), O.G2.to_affine(pB), O.G1.to_affine(pC)) == GO.expected_proof_synthetic(nc_, ni_, 2)
+        dpk.free()
+    # fixed-base batch over scalar slices, outputs sharded / gathered (FixedBaseMSM.distributedBatchMSM, distributedDoubleBatchMSM)
+    ftot = 1 << 10
+    fraw = util.rand_scalars_bytes(ftot, seed=8)
+    flo, fhi = rank * ftot // world, (rank + 1) * ftot // world
+    fsl = torch.from_numpy(fraw[flo:fhi].copy()).cuda()
+    b1, b2 = O.pack_g1([O.G1.random(10)]), O.pack_g2([O.G2.random(10)])
+    o1, o2 = D.fixed_double_batch_distributed(ops, b1, b2, fsl, fhi - flo, 20, 13, 22, 12, gather=True)
+    torch.cuda.synchronize()
+    sums = util.column_sums(fraw, 1)[0] % O.R
+    tot1 = ctx.sum_points_dev(1, o1, ftot)
+    tot2 = ctx.sum_points_dev(2, o2, ftot)
+    assert O.G1.equals(O.unpack_g1(tot1)[0], O.G1.mul(O.G1.random(10), sums)) and O.G2.equals(O.unpack_g2(tot2)[0], O.G2.mul(O.G2.random(10), sums))
+    i_ = 777
+    assert O.G1.equals(O.unpack_g1(o1[i_].cpu().numpy().tobytes())[0], O.G1.mul(O.G1.random(10), O.from_le(fraw[i_].tobytes())))
     ex.close()
     ks, pool = util.known_dlog_points(O.G1, 16, seed=4)
     total = 1 << 12

@@ -34,3 +34,18 @@ def test_literal_setup_and_prover_verify_in_the_exponent():
     assert O.G2.equals(B, O.G2.mul(setup["g2"], b))
     assert O.G1.equals(C, O.G1.mul(setup["g1"], c))
     assert setup["scalarSizeG1"] == 253 and setup["scalarSizeG2"] == 254
+
+
+def test_exponent_shortcut_at_scale_matches_the_literal_flow():
+    """proof_exponents_synthetic (C oracle, O(domain), used to check proofs at 2^20..2^24 constraints) gives the same exponents as
+    the literal restatement of setup + witness map, and the same proof points as SerialSetup + SerialProver restated."""
+    for nc, ni in ((8, 3), (64, 7), (300, 20)):
+        cons, _, na, prim, aux = G.serial_construct(nc, ni)
+        setup = G.setup_scalars(cons, ni, ni + na)
+        H = G.r1cs_to_qap_witness(cons, ni, prim, aux)
+        assert G.proof_exponents_synthetic(nc, ni, 2) == G.proof_exponents(setup, prim, aux, H)
+    cons, ni, na, prim, aux = G.serial_construct(8, 3)
+    _, pk, _ = G.setup_literal(cons, ni, ni + na)
+    (A, B, C), _ = G.prove_literal(pk, cons, ni, prim, aux)
+    eA, eB, eC = G.expected_proof_synthetic(8, 3, 2)
+    assert O.G1.to_affine(A) == eA and O.G2.to_affine(B) == eB and O.G1.to_affine(C) == eC

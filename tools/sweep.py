@@ -1,7 +1,7 @@
 """Sweep of BASELINE.json configs[1..3] on one GPU, device-resident, CUDA-event timed (median of 5 after 2 warm-ups):
 G1 / G2 variable-base MSM, NTT, fixed-base batch MSM.  Prints one JSON line per point; used for profiles/rNN_sweep.jsonl.
 
-    python tools/sweep.py [msm|msm2|skew|ntt|fixed|fixed2 ...]   (OZK_SWEEP_LOGS=24,26 restricts the G1 MSM sizes)"""
+    python tools/sweep.py [msm|cfg1|msm2|skew|ntt|fixed|fixed2 ...]   (OZK_SWEEP_LOGS=24,26 restricts the G1 MSM sizes)"""
 import json
 import os
 import sys
@@ -15,6 +15,7 @@ from oracle import dizk_oracle as O  # noqa: E402
 from tests import util  # noqa: E402
 
 ctx = Context(0, stream=torch.cuda.current_stream().cuda_stream)
+IMAD_PEAK = ctx.imad_peak()          # measured integer-pipe peak (G multiply-adds / s) for the roofline fractions
 what = [a for a in sys.argv[1:] if not a.startswith("-")] or ["msm", "msm2", "ntt", "fixed", "fixed2"]
 
 
@@ -33,22 +34,27 @@ def timeit(fn, reps=5, warm=2):
     return sorted(ts)[len(ts) // 2]
 
 
-def msm_sweep(G, logs, name):
-    ks, pool = util.known_dlog_points(G, 64, seed=1, random_z=False)
-    pool = [G.to_affine(p) for p in pool]
-    for log_n in logs:
-        n = 1 << log_n
-        raw = util.rand_scalars_bytes(n, seed=log_n)
-        d_s = torch.from_numpy(raw).cuda()
-        d_b = torch.from_numpy(np.ascontiguousarray(util.tiled_bases_bytes(G, pool, n))).cuda()
+def msm_sweep(G, sizes, name):
+    """sizes: pair counts.  n DISTINCT bases k_i G made on the GPU, scalars uniform in [0, r): exact answer (sum s_i k_i) G."""
+    for n in sizes:
+        d_b, ks = util.gpu_distinct_bases(ctx, G, n, seed=n & 0xFFFF, keep_z=False, verify=3)
+        raw = util.force_edge_scalars(util.rand_scalars_full_range(n, seed=n & 0xFFFF)) if n <= (1 << 22) else None
+        if raw is None:
+            d_s = util.gpu_rand_scalars(n, n & 0xFFFF, torch.device("cuda"))
+            raw = d_s.cpu().numpy()
+        else:
+            d_s = torch.from_numpy(raw).cuda()
         fn = ctx.msm_g1_dev if G is O.G1 else ctx.msm_g2_dev
         out = fn(d_s, d_b, n)
-        ok = G.equals(util.unpack_point(G, out), util.expected_from_dlogs(G, ks, util.column_sums(raw, 64)))
+        ok = G.equals(util.unpack_point(G, out), util.expected_from_dot(G, raw, ks))
         ms = timeit(lambda: fn(d_s, d_b, n))
         st = ctx.msm_last_stats()
-        print(json.dumps({"op": name, "log_n": log_n, "ok": ok, "ms": ms, "Mpairs_per_s": n / ms / 1e3, "window_bits": st[0],
+        imad = n * 21760 * (1 if G is O.G1 else 3) / (ms * 1e-3) / 1e9
+        print(json.dumps({"op": name, "n": n, "log_n": round(np.log2(n), 3), "ok": ok, "ms": ms, "Mpairs_per_s": n / ms / 1e3, "window_bits": st[0],
+                          "imad_frac": imad / IMAD_PEAK,
                           "phases_ms": {"sort": st[5], "convert": st[6], "accumulate": st[7], "merge": st[8], "reduce_final": st[9]}}), flush=True)
         del d_s, d_b
+        torch.cuda.empty_cache()
 
 
 def profiler_scalars(n, seed):
@@ -89,9 +95,12 @@ if "skew" in what:
         del d_s, d_b
 
 if "msm" in what:
-    msm_sweep(O.G1, [int(x) for x in os.environ.get("OZK_SWEEP_LOGS", "16,18,20,22,24,26").split(",")], "varmsm_g1")
+    msm_sweep(O.G1, [1 << int(x) for x in os.environ.get("OZK_SWEEP_LOGS", "16,18,20,22,24,26").split(",")], "varmsm_g1")
+if "cfg1" in what:
+    # the MSM sizes of BASELINE.json configs[0] (2^15 constraints, 1023 inputs: SURVEY.md section 8 a1)
+    msm_sweep(O.G1, [1023, 31748, 65537], "varmsm_g1_cfg1")
 if "msm2" in what:
-    msm_sweep(O.G2, [16, 18, 20, 22], "varmsm_g2")
+    msm_sweep(O.G2, [1 << k for k in (16, 18, 20, 22, 24)], "varmsm_g2")
 if "ntt" in what or "ntt26" in what:
     for log_n in ([26] if "ntt26" in what else [16, 18, 20, 22, 24, 26, 28]):
         n = 1 << log_n
@@ -100,9 +109,10 @@ if "ntt" in what or "ntt26" in what:
         o = torch.empty_like(d)
         omega = O.le32(O.root_of_unity(n))
         ms = timeit(lambda: ctx.ntt_dev(d, o, n, omega))
-        print(json.dumps({"op": "ntt_fr", "log_n": log_n, "ms": ms, "alg_GBps": n * 128 / ms / 1e6, "Gmodmul_per_s_alg": n * log_n / 2 / ms / 1e6}), flush=True)
+        print(json.dumps({"op": "ntt_fr", "log_n": log_n, "ms": ms, "alg_GBps": n * 128 / ms / 1e6, "Gmodmul_per_s_alg": n * log_n / 2 / ms / 1e6,
+                          "imad_frac": n * 68 * log_n / (ms * 1e-3) / 1e9 / IMAD_PEAK}), flush=True)
         del d, o
-for key, G, logs in (("fixed", O.G1, [20, 22, 24]), ("fixed2", O.G2, [20, 22])):
+for key, G, logs in (("fixed", O.G1, [20, 22, 24]), ("fixed2", O.G2, [20, 22, 24])):
     if key not in what:
         continue
     base_pt = G.random(10)
@@ -122,6 +132,10 @@ for key, G, logs in (("fixed", O.G1, [20, 22, 24]), ("fixed2", O.G2, [20, 22])):
         pts = O.unpack_g1(outb) if G is O.G1 else O.unpack_g2(outb)
         sc = util.scalars_from_bytes(raw[:3])
         ok = all(G.equals(p, e) for p, e in zip(pts, O.fixed_batch_msm(G, ss, w, base_pt, sc)))
+        imad = n * outerc * 1360 * (1 if G is O.G1 else 3) / (ms * 1e-3) / 1e9      # outerc x 10 x 136 IMAD per scalar, x3 for G2
+        # size-independent exact check: sum_i out_i == (sum_i s_i) * B
+        tot = ctx.sum_points_dev(1 if G is O.G1 else 2, d_o[:4096].contiguous(), 4096)
+        ok = ok and G.equals(util.unpack_point(G, tot), G.mul(base_pt, util.column_sums(raw[:4096], 1)[0] % O.R))
         print(json.dumps({"op": "fixed_" + ("g1" if G is O.G1 else "g2"), "log_n": log_n, "window": w, "outerc": outerc, "ok": ok, "ms": ms,
-                          "Mscalars_per_s": n / ms / 1e3}), flush=True)
+                          "Mscalars_per_s": n / ms / 1e3, "imad_frac": imad / IMAD_PEAK}), flush=True)
         del d_s, d_o
