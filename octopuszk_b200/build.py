@@ -24,8 +24,12 @@ NVCC_FLAGS = [
     "-I", os.path.join(ROOT, "include"),
 ]
 
-CU_SOURCES = ["capi.cu", "ntt.cu", "msm.cu", "msm_g1.cu", "msm_g2.cu", "fixed_base.cu", "stage.cu"]
+CU_SOURCES = ["capi.cu", "ntt.cu", "msm.cu", "msm_g1.cu", "msm_g2.cu", "msm_ba_g1.cu", "fixed_base.cu", "stage.cu"]
 HEADERS = ["common.h", "consts.cuh", "chains.cuh", "curve.cuh", "fp256.cuh", "ptx_arith.cuh", "msm_impl.cuh", "fixed_impl.cuh", os.path.join(ROOT, "include", "octozk.h")]
+
+
+# headers only some translation units include (a change must not rebuild the slow msm_g2.cu)
+EXTRA_DEPS = {"msm.cu": ["msm_ba_impl.cuh"], "msm_ba_g1.cu": ["msm_ba_impl.cuh"]}
 
 
 def _newer(target: str, deps) -> bool:
@@ -54,7 +58,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         src = os.path.join(CSRC, s)
         obj = os.path.join(OBJDIR, s.replace(".cu", ".o"))
         objs.append(obj)
-        if force or not _newer(obj, [src] + hdrs):
+        if force or not _newer(obj, [src] + hdrs + [os.path.join(CSRC, h) for h in EXTRA_DEPS.get(s, [])]):
             extra = ["-Xptxas", "-v"] if verbose else []
             jobs.append([NVCC] + NVCC_FLAGS + extra + ["-c", src, "-o", obj])
     with concurrent.futures.ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as ex:

@@ -9,6 +9,7 @@
 #include <cstring>
 
 #include "common.h"
+#include "msm_ba_impl.cuh"
 #include "msm_impl.cuh"
 
 namespace ozk {
@@ -45,7 +46,7 @@ __device__ __forceinline__ bool scalar_lt_r(const uint32_t (&s)[8]) {
 // a top window with one or two significant bits -- the dominant bucket of a window is in nearly every warp's first lane
 // group, which turns up to 32 same-address atomics into one and the group's stores into one coalesced run.
 template <int MODE>
-__global__ void __launch_bounds__(256) msm_digits(const uint4* __restrict__ scalars, size_t n, uint32_t c, uint32_t nwin,
+__global__ void __launch_bounds__(256) msm_digits(const uint4* __restrict__ scalars, size_t n, size_t wstride, uint32_t c, uint32_t nwin,
                                                   uint32_t win_lo, uint32_t win_hi,
                                                   uint32_t* __restrict__ count_or_cursor, uint32_t* __restrict__ sorted,
                                                   uint32_t* flag) {
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(256) msm_digits(const uint4* __restrict__ scal
             if (!in_group) atomicAdd(&count_or_cursor[slot], 1u);
         } else {
             const uint32_t pos = in_group ? base + __popc(group & ((1u << lane) - 1u)) : atomicAdd(&count_or_cursor[slot], 1u);
-            sorted[(size_t)w * n + pos] = (uint32_t)i | (neg << 31);
+            sorted[(size_t)w * wstride + pos] = (uint32_t)i | (neg << 31);
         }
     }
 }
@@ -102,7 +103,8 @@ static constexpr int kScanPer = 8;
 __global__ void __launch_bounds__(1024) msm_scan(const uint32_t* __restrict__ count, uint32_t nb, uint32_t* __restrict__ start,
                                                  uint32_t* __restrict__ cursor, OvfTask* __restrict__ ovf_tasks,
                                                  uint32_t* __restrict__ ovf_task_count, OvfBucket* __restrict__ ovf_buckets,
-                                                 uint32_t* __restrict__ ovf_bucket_count, uint32_t ovf_task_cap, uint32_t ovf_bucket_cap, uint32_t seg_len) {
+                                                 uint32_t* __restrict__ ovf_bucket_count, uint32_t ovf_task_cap, uint32_t ovf_bucket_cap, uint32_t seg_len,
+                                                 uint32_t align_mask) {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t carry_s;
     const uint32_t w = blockIdx.x;
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(1024) msm_scan(const uint32_t* __restrict__ co
 #pragma unroll
         for (int k = 0; k < kScanPer; k++) {
             v[k] = (b0 + k) < nb ? cnt[b0 + k] : 0;
-            tsum += v[k];
+            tsum += (v[k] + align_mask) & ~align_mask;          // bucket runs start at multiples of 2^rounds (batch-affine pre-reduction)
         }
         // block-wide exclusive scan of the per-thread sums
         uint32_t x = tsum;
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(1024) msm_scan(const uint32_t* __restrict__ co
                     }
                 }
             }
-            excl += v[k];
+            excl += (v[k] + align_mask) & ~align_mask;
         }
         __syncthreads();
         if (threadIdx.x == 1023) carry_s = excl;
@@ -268,7 +270,20 @@ struct MsmShape {
     uint32_t c, nwin, nb, log_nb;
     uint32_t seg;                      // longest run one accumulate task handles
     uint32_t ovf_task_cap, ovf_bucket_cap;
+    uint32_t ba;                       // batch-affine pre-reduction rounds (msm_ba_impl.cuh); 0: off
+    size_t wstride;                    // entries per window in the sorted index array (len, plus the alignment padding when ba > 0)
 };
+
+// Batch-affine pre-reduction (G1): rounds by slice length.  Each round halves the runs at ~6.6 instead of ~9.5 products per
+// addition but costs a pass over HBM, so it pays only while the runs are long.  OZK_MSM_BA = 0..3 overrides.
+static uint32_t ba_rounds_for(size_t len, uint32_t c) {
+    if (const char* e = getenv("OZK_MSM_BA")) {
+        int r = atoi(e);
+        if (r >= 0 && r <= 3) return (uint32_t)r;
+    }
+    (void)len; (void)c;
+    return 0;
+}
 
 // n_total fixes the window shape (slices of one MSM share their buckets); len is the number of pairs sorted and
 // accumulated at a time and fixes the task length and the overflow capacities.
@@ -286,12 +301,16 @@ static MsmShape msm_shape(size_t n_total, size_t len) {
     size_t cap = ((size_t)s.nwin * len) / s.seg + 1;
     s.ovf_task_cap = (uint32_t)std::min<size_t>(cap, 0x7fffffffu);
     s.ovf_bucket_cap = s.ovf_task_cap;
+    s.ba = ba_rounds_for(len, s.c);
+    if (len >= ((size_t)1 << 31) - 1) s.ba = 0;           // the sentinel must not be a valid entry
+    const size_t a = (size_t)1 << s.ba;
+    s.wstride = s.ba ? ((len + (size_t)s.nb * (a - 1) + 63) & ~(size_t)63) : len;
     return s;
 }
 static MsmShape msm_shape(size_t n) { return msm_shape(n, n); }
 
 // buffers in ctx->msm[]
-enum { B_AFF1 = 0, B_AFF2, B_COUNT, B_START, B_CURSOR, B_SORTED, B_BUCKETS, B_OVFTASK, B_OVFBUCKET, B_OVFPART, B_SCRATCH, B_MISC, B_ORDER, B_BUCKETS2 };
+enum { B_AFF1 = 0, B_AFF2, B_COUNT, B_START, B_CURSOR, B_SORTED, B_BUCKETS, B_OVFTASK, B_OVFBUCKET, B_OVFPART, B_SCRATCH, B_MISC, B_ORDER, B_BUCKETS2, B_PAIR0, B_PAIR1 };
 static constexpr int kMiscOhist = 64, kMiscOcursor = 2048, kMiscWords = 4096;   // word offsets inside B_MISC
 
 // sort phase shared by G1 / G2 / paired calls: fills start/count/sorted and the overflow lists
@@ -301,11 +320,12 @@ static int msm_sort(ozk_ctx* ctx, const void* d_scalars, size_t n, const MsmShap
     OZK_TRY(ctx->msm[B_COUNT].reserve(nbt * 4, st));
     OZK_TRY(ctx->msm[B_START].reserve(nbt * 4, st));
     OZK_TRY(ctx->msm[B_CURSOR].reserve(nbt * 4, st));
-    OZK_TRY(ctx->msm[B_SORTED].reserve((size_t)sh.nwin * n * 4, st));
+    OZK_TRY(ctx->msm[B_SORTED].reserve((size_t)sh.nwin * sh.wstride * 4, st));
     OZK_TRY(ctx->msm[B_OVFTASK].reserve((size_t)sh.ovf_task_cap * sizeof(OvfTask), st));
     OZK_TRY(ctx->msm[B_OVFBUCKET].reserve((size_t)sh.ovf_bucket_cap * sizeof(OvfBucket), st));
     OZK_TRY(ctx->msm[B_MISC].reserve(kMiscWords * 4, st));
     OZK_TRY(ctx->msm[B_ORDER].reserve(nbt * 4, st));
+    if (sh.ba) OZK_CUDA(cudaMemsetAsync(ctx->msm[B_SORTED].p, 0xff, (size_t)sh.nwin * sh.wstride * 4, st));     // padding = sentinel
     uint32_t* misc = (uint32_t*)ctx->msm[B_MISC].p;      // [0] flag (cleared by the caller), [1] ovf task count, [2] ovf bucket count, run-length histogram
     OZK_CUDA(cudaMemsetAsync(misc + 1, 0, (kMiscWords - 1) * 4, st));
     OZK_CUDA(cudaMemsetAsync(ctx->msm[B_COUNT].p, 0, nbt * 4, st));
@@ -315,13 +335,14 @@ static int msm_sort(ozk_ctx* ctx, const void* d_scalars, size_t n, const MsmShap
     if (const char* e = getenv("OZK_MSM_WPL")) wpl = (uint32_t)std::max(1, atoi(e));
     uint32_t nlaunch = 0;
     for (uint32_t w0 = 0; w0 < sh.nwin; w0 += wpl, nlaunch++)
-        msm_digits<0><<<grid, 256, 0, st>>>((const uint4*)d_scalars, n, sh.c, sh.nwin, w0, std::min(sh.nwin, w0 + wpl),
+        msm_digits<0><<<grid, 256, 0, st>>>((const uint4*)d_scalars, n, sh.wstride, sh.c, sh.nwin, w0, std::min(sh.nwin, w0 + wpl),
                                             (uint32_t*)ctx->msm[B_COUNT].p, nullptr, misc);
     msm_scan<<<sh.nwin, 1024, 0, st>>>((const uint32_t*)ctx->msm[B_COUNT].p, sh.nb, (uint32_t*)ctx->msm[B_START].p,
                                        (uint32_t*)ctx->msm[B_CURSOR].p, (OvfTask*)ctx->msm[B_OVFTASK].p, misc + 1,
-                                       (OvfBucket*)ctx->msm[B_OVFBUCKET].p, misc + 2, sh.ovf_task_cap, sh.ovf_bucket_cap, sh.seg);
+                                       (OvfBucket*)ctx->msm[B_OVFBUCKET].p, misc + 2, sh.ovf_task_cap, sh.ovf_bucket_cap, sh.seg,
+                                       (1u << sh.ba) - 1u);
     for (uint32_t w0 = 0; w0 < sh.nwin; w0 += wpl, nlaunch++)
-        msm_digits<1><<<grid, 256, 0, st>>>((const uint4*)d_scalars, n, sh.c, sh.nwin, w0, std::min(sh.nwin, w0 + wpl),
+        msm_digits<1><<<grid, 256, 0, st>>>((const uint4*)d_scalars, n, sh.wstride, sh.c, sh.nwin, w0, std::min(sh.nwin, w0 + wpl),
                                             (uint32_t*)ctx->msm[B_CURSOR].p, (uint32_t*)ctx->msm[B_SORTED].p, misc);
     {
         const unsigned og = (unsigned)((nbt + 255) / 256);
@@ -361,9 +382,34 @@ static int msm_accumulate_phase(ozk_ctx* ctx, const MsmLaunch& L, const BaseSrc&
         ctx->launches += 1;
     }
     OZK_CUDA(cudaEventRecord(ctx->evs[2], st));
-    if (L.accumulate(st, aff, (const uint32_t*)ctx->msm[B_SORTED].p, (const uint32_t*)ctx->msm[B_START].p,
+    if (sh.ba && &L == &kMsmG1) {
+        // batch-affine pre-reduction: rounds of pairwise affine additions over all bucket runs, then the XYZZ walk over the short runs
+        const MsmBaLaunch& B = kMsmBaG1;
+        const size_t pairs0 = (size_t)sh.nwin * sh.wstride / 2;
+        OZK_TRY(ctx->msm[B_PAIR0].reserve(pairs0 * B.affine_bytes, st));
+        if (sh.ba > 1) OZK_TRY(ctx->msm[B_PAIR1].reserve(pairs0 / 2 * B.affine_bytes, st));
+        auto batch_for = [&](size_t total) {
+            int M = 32;
+            if (const char* e = getenv("OZK_MSM_BA_M")) M = std::max(8, std::min(kBaMaxM, atoi(e)));
+            else while (M < kBaMaxM && total / ((size_t)M * 2) >= (size_t)ctx->sm_count * 512 * 2) M *= 2;     // keep >= 2 waves of threads
+            return M;
+        };
+        if (B.round0(st, aff, (const uint32_t*)ctx->msm[B_SORTED].p, pairs0, ctx->msm[B_PAIR0].p, batch_for(pairs0))) { set_error("msm: pair round launch failed"); return OZK_ERR_CUDA; }
+        const void* cur = ctx->msm[B_PAIR0].p;
+        size_t total = pairs0;
+        for (uint32_t r = 1; r < sh.ba; r++) {
+            total /= 2;
+            void* dst = (r & 1) ? ctx->msm[B_PAIR1].p : ctx->msm[B_PAIR0].p;
+            if (B.round(st, cur, total, dst, batch_for(total))) { set_error("msm: pair round launch failed"); return OZK_ERR_CUDA; }
+            cur = dst;
+        }
+        ctx->launches += sh.ba;
+        if (B.accumulate_pre(st, cur, (const uint32_t*)ctx->msm[B_START].p, (const uint32_t*)ctx->msm[B_COUNT].p, (const OvfTask*)ctx->msm[B_OVFTASK].p,
+                             misc + 1, (const uint32_t*)ctx->msm[B_ORDER].p, (uint32_t)nbt, sh.log_nb, sh.wstride, sh.seg, sh.ba, resume ? 1u : 0u,
+                             sh.ovf_task_cap, ctx->msm[bkt_slot].p, ctx->msm[B_OVFPART].p)) { set_error("msm: accumulate launch failed"); return OZK_ERR_CUDA; }
+    } else if (L.accumulate(st, aff, (const uint32_t*)ctx->msm[B_SORTED].p, (const uint32_t*)ctx->msm[B_START].p,
                      (const uint32_t*)ctx->msm[B_COUNT].p, (const OvfTask*)ctx->msm[B_OVFTASK].p, misc + 1, (const uint32_t*)ctx->msm[B_ORDER].p,
-                     (uint32_t)nbt, sh.log_nb, n, sh.seg, resume ? 1u : 0u,
+                     (uint32_t)nbt, sh.log_nb, sh.wstride, sh.seg, resume ? 1u : 0u,
                      sh.ovf_task_cap, ctx->msm[bkt_slot].p, ctx->msm[B_OVFPART].p)) { set_error("msm: accumulate launch failed"); return OZK_ERR_CUDA; }
     OZK_CUDA(cudaEventRecord(ctx->evs[3], st));
     if (L.merge(st, (const OvfBucket*)ctx->msm[B_OVFBUCKET].p, misc + 2, std::min<uint32_t>(sh.ovf_bucket_cap, (uint32_t)nbt),
@@ -523,7 +569,7 @@ static MsmStream& stream_of(ozk_ctx* ctx) {
 static int msm_reserve_slices(ozk_ctx* ctx, size_t n_total, size_t len, bool g1, bool g2, bool conv1, bool conv2) {
     cudaStream_t st = ctx->stream;
     const MsmShape sh = msm_shape(n_total, len);
-    OZK_TRY(ctx->msm[B_SORTED].reserve((size_t)sh.nwin * len * 4, st));
+    OZK_TRY(ctx->msm[B_SORTED].reserve((size_t)sh.nwin * sh.wstride * 4, st));
     OZK_TRY(ctx->msm[B_OVFTASK].reserve((size_t)sh.ovf_task_cap * sizeof(OvfTask), st));
     OZK_TRY(ctx->msm[B_OVFBUCKET].reserve((size_t)sh.ovf_bucket_cap * sizeof(OvfBucket), st));
     const size_t part = (size_t)sh.ovf_task_cap * (g2 ? kMsmG2.xyzz_bytes : kMsmG1.xyzz_bytes);

@@ -29,11 +29,12 @@
 
 namespace ozk {
 
-static constexpr int kMaxLogT = 9;          // largest in-CTA transform: 512 points ...
-// ... except for transforms of more than 2^27 points, which would need a fourth pass (2^28 = 7+7+7+7): there the first pass takes
-// 1024 points per CTA (one column per tile, 16 KB of twiddles, four CTAs per SM) so that 2^28 = 10+9+9 stays at three passes.
+static constexpr int kMaxLogT = 9;          // largest in-CTA transform by default: 512 points
+// 1024-point in-CTA transforms (one column per tile, 16 KB of twiddles, four CTAs per SM) are supported and would keep 2^28 at
+// three passes (10+9+9) instead of four (7+7+7+7), but measured slower on B200: 72.7 ms against 67.6 ms -- the first pass then
+// needs the two-level inter-pass twiddle (one more product per element) and runs one column per tile.  OZK_NTT_MAX_LOGT=10 selects it.
 static constexpr int kMaxLogTBig = 10;
-static inline int max_log_t_for(int log_n) { return log_n > 3 * kMaxLogT ? kMaxLogTBig : kMaxLogT; }
+static inline int max_log_t_for(int) { return kMaxLogT; }
 // Tile of 1024 elements (32 KB) per 128-thread CTA, five CTAs per SM (__launch_bounds__(128, 5): 96 registers, ~100 bytes of
 // spills) whose load / transform / store phases interleave (measured 2^26: 16.3 ms with 2048-element tiles and two CTAs per SM,
 // 15.9 ms with 1024-element tiles and four, 14.7 ms with five together with the direct twiddle tables below).

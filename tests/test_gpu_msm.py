@@ -344,3 +344,55 @@ def test_streaming_begin_feed_end(ctx):
         ctx.msm_feed(raw[:5], b1[:5], None, 5)               # more than announced
     out = ctx.msm_g1(raw[:100], b1[:100], 100)               # the context still works
     assert O.G1.equals(O.unpack_g1(out)[0], util.expected_from_dlogs(O.G1, k1, util.column_sums(raw[:100], 64)))
+
+
+# ---- batch-affine pre-reduction of the bucket runs (csrc/msm_ba_impl.cuh), forced on through OZK_MSM_BA ---------------------
+@pytest.mark.parametrize("rounds", [1, 2, 3])
+def test_batch_affine_rounds_match_oracle(ctx, rounds, monkeypatch):
+    """Same results with 1, 2 or 3 rounds of pairwise affine additions before the XYZZ walk: small random inputs with every
+    special case (infinity bases, P with -P, repeated points = doublings inside a pair, zero / one / r-1 scalars), ragged and tiny
+    batch sizes, the profiler's all-identical-bases input (every pair is a doubling, dense buckets), distinct bases at 2^18,
+    slices sharing buckets, and the paired call (G2 keeps the classic path on the padded index layout)."""
+    monkeypatch.setenv("OZK_MSM_BA", str(rounds))
+    rng = random.Random(900 + rounds)
+    for n, m in ((1, None), (2, None), (17, "8"), (100, None), (1023, "16"), (5000, "512")):
+        if m:
+            monkeypatch.setenv("OZK_MSM_BA_M", m)
+        else:
+            monkeypatch.delenv("OZK_MSM_BA_M", raising=False)
+        ks, pool = util.known_dlog_points(O.G1, min(n, 12), seed=n, random_z=True)
+        bases = [pool[rng.randrange(len(pool))] for _ in range(n)]
+        scalars = [rng.randrange(O.R) for _ in range(n)]
+        if n >= 17:
+            bases[0] = O.G1.zero()
+            bases[1] = (pool[0][0], pool[0][1], 0)
+            scalars[2], scalars[3], scalars[4] = 0, 1, O.R - 1
+            bases[5], bases[6] = pool[1], O.G1.negate(pool[1])
+            scalars[5] = scalars[6] = rng.randrange(O.R)
+            bases[7] = bases[8] = bases[9] = pool[2]
+            scalars[7] = scalars[8] = scalars[9] = 12345
+        assert O.G1.equals(_run(ctx, O.G1, scalars, bases), O.pippenger_msm(O.G1, scalars, bases)), (rounds, n)
+    monkeypatch.delenv("OZK_MSM_BA_M", raising=False)
+    # profiler distribution: N copies of one base
+    n = 1 << 16
+    jr = O.JavaRandom(10)
+    g = O.G1.random(10)
+    scalars = [jr.next_long() % O.R for _ in range(n)]
+    out = ctx.msm_g1(O.pack_scalars(scalars), O.pack_g1([g]) * n, n)
+    assert O.G1.equals(O.unpack_g1(out)[0], O.G1.mul(g, sum(scalars) % O.R))
+    # distinct bases, full-range scalars, host path in slices
+    monkeypatch.setenv("OZK_HOST_SLICES", "3")
+    n = 1 << 18
+    d_b, ks = util.gpu_distinct_bases(ctx, O.G1, n, seed=77, keep_z=True)
+    raw = util.force_edge_scalars(util.rand_scalars_full_range(n, seed=77))
+    out = ctx.msm_g1(raw, d_b.cpu().numpy(), n)
+    assert O.G1.equals(O.unpack_g1(out)[0], util.expected_from_dot(O.G1, raw, ks))
+    # paired call
+    m = 3000
+    k1, p1 = util.known_dlog_points(O.G1, 64, seed=5)
+    k2, p2 = util.known_dlog_points(O.G2, 64, seed=6)
+    rw = util.rand_scalars_bytes(m, seed=7)
+    out = ctx.msm_g1g2(rw.tobytes(), util.tiled_bases_bytes(O.G1, p1, m).tobytes(), util.tiled_bases_bytes(O.G2, p2, m).tobytes(), m)
+    sums = util.column_sums(rw, 64)
+    assert O.G1.equals(O.unpack_g1(out[:96])[0], util.expected_from_dlogs(O.G1, k1, sums))
+    assert O.G2.equals(O.unpack_g2(out[96:])[0], util.expected_from_dlogs(O.G2, k2, sums))

@@ -102,7 +102,8 @@ if "cfg1" in what:
 if "msm2" in what:
     msm_sweep(O.G2, [1 << k for k in (16, 18, 20, 22, 24)], "varmsm_g2")
 if "ntt" in what or "ntt26" in what:
-    for log_n in ([26] if "ntt26" in what else [16, 18, 20, 22, 24, 26, 28]):
+    ntt_logs = [int(x) for x in os.environ.get("OZK_SWEEP_NTT_LOGS", "16,18,20,22,24,26,28").split(",")]
+    for log_n in ([26] if "ntt26" in what else ntt_logs):
         n = 1 << log_n
         d = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device="cuda")
         d[:, 31] &= 0x1F
