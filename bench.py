@@ -14,6 +14,7 @@ One "step" = one pass of the hot path (ozk_msm_g1*) over one batch of synthetic 
   cpu_baseline: the C restatement of the reference's CPU algorithm (oracle/dizk_oracle.c, "port": the Java itself
            cannot run, no JVM in the image) on all host cores, on a bounded sample.
   msm_strong: the same MSM with a FIXED total (2^24 and 2^26 pairs) split over the N GPUs (strong scaling).
+  fixed_multi: fixed-base batch MSM (G1 and G2, BASELINE.json configs[3]) over a fixed total of 2^24 scalars split over the N GPUs.
   ntt_multi (N > 1): the four-step transform over all GPUs at 2^26 and 2^28, exchange fused into the kernels (peer stores over
            NVLink) and as an NCCL all_to_all, checked on the box against the single-GPU transform (2^22) and against Horner
            evaluation of the gathered input (full size).
@@ -338,6 +339,28 @@ def run_ours(args):
         assert O.G1.equals(O.unpack_g1(o)[0], exp_t)
         msm_strong.append({"total_log_n": t, "pairs_per_gpu": cnt, "ms_per_step": ms_t, "value": (1 << t) / (ms_t * 1e-3), "unit": "points/s",
                            "imad_frac": cnt * IMAD_PER_PAIR / (ms_t * 1e-3) / 1e9 / imad_peak, "checked": True})
+    # ---- fixed-base batch, a FIXED total of 2^24 scalars split over the GPUs (FixedBaseMSM.distributedBatchMSM; outputs stay sharded) --
+    fixed_multi = []
+    if not args.no_strong:
+        cnt = (1 << 24) // world
+        for grp, pt_bytes, w, oc, gen in ((1, 96, 20, 13, gen_packed), (2, 192, 20, 13, O.pack_g2([O.G2.generator]))):
+            d_o = torch.empty((cnt, pt_bytes), dtype=torch.uint8, device=dev)
+            fn = ctx.fixed_g1_dev if grp == 1 else ctx.fixed_g2_dev
+            for _ in range(2):
+                fn(gen, d_s[:cnt], cnt, oc, w, d_o)
+            ms_f, _, _ = timed(lambda: fn(gen, d_s[:cnt], cnt, oc, w, d_o), 3)
+            ms_f /= 3
+            # exact, size-independent: the sum of the first 4096 outputs is (sum of the first 4096 scalars) * B
+            G = O.G1 if grp == 1 else O.G2
+            tot = ctx.sum_points_dev(grp, d_o[:4096].contiguous(), 4096)
+            want = G.mul(G.generator, util.column_sums(h_sraw[:4096], 1)[0] % O.R)
+            got = O.unpack_g1(tot)[0] if grp == 1 else O.unpack_g2(tot)[0]
+            assert G.equals(got, want), "bench: fixed-base batch outputs do not sum to (sum s_i) B"
+            fixed_multi.append({"group": "G1" if grp == 1 else "G2", "total_log_n": 24, "scalars_per_gpu": cnt, "window": w, "outerc": oc, "ms": ms_f,
+                                "value": (1 << 24) / (ms_f * 1e-3), "unit": "scalars/s",
+                                "imad_frac": cnt * oc * 1360 * (1 if grp == 1 else 3) / (ms_f * 1e-3) / 1e9 / imad_peak, "checked": True})
+            del d_o
+        torch.cuda.empty_cache()
     del h_k, h_sraw
     if n_gen > n:
         d_s, d_b = d_s[:n].clone(), d_b[:n].clone()
@@ -463,6 +486,7 @@ def run_ours(args):
             "phases_ms": {"sort": phase[5], "convert": phase[6], "accumulate": phase[7], "merge": phase[8], "reduce_final": phase[9]},
             "msm_shape": {"window_bits": phase[0], "windows": phase[1], "buckets_per_window": phase[2]},
             "msm_strong": msm_strong,
+            "fixed_multi": fixed_multi,
             "ntt": ntt,
             "ntt_multi": ntt_multi,
             "groth16": groth16,

@@ -1,4 +1,6 @@
 // Context management, error reporting and the integer-pipe microbenchmarks of liboctozk.so.
+#include <cstdlib>
+
 #include "common.h"
 #include "fp256.cuh"
 
@@ -158,24 +160,41 @@ int ozk_device_count(void) {
     return n;
 }
 
+void ozk_ctx_destroy(ozk_ctx* c);
+
 int ozk_ctx_create(int device, ozk_ctx** out) {
     OZK_ARG(out != nullptr, "ozk_ctx_create: out is null");
     int n = 0;
     OZK_CUDA(cudaGetDeviceCount(&n));
     OZK_ARG(device >= 0 && device < n, "ozk_ctx_create: device index out of range");
     OZK_CUDA(cudaSetDevice(device));
+    if (const char* e = getenv("OZK_L2_FETCH")) {
+        // experiment: L2 fill granularity for the 64-byte random gathers of the MSM (a device-wide hint: 32, 64 or 128 bytes)
+        const int g = atoi(e);
+        if (g == 32 || g == 64 || g == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g);
+        cudaGetLastError();
+    }
     ozk_ctx* c = new ozk_ctx();
     c->device = device;
-    cudaDeviceProp prop;
-    OZK_CUDA(cudaGetDeviceProperties(&prop, device));
-    c->sm_count = prop.multiProcessorCount;
-    OZK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    OZK_CUDA(cudaEventCreate(&c->ev0));
-    OZK_CUDA(cudaEventCreate(&c->ev1));
-    for (auto& e : c->evs) OZK_CUDA(cudaEventCreate(&e));
-    OZK_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    for (auto& e : c->copy_ev) OZK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    OZK_CUDA(cudaMallocHost(&c->pinned, 4096));
+    // anything that fails below must not leak the half-built context
+    auto build = [&]() -> int {
+        cudaDeviceProp prop;
+        OZK_CUDA(cudaGetDeviceProperties(&prop, device));
+        c->sm_count = prop.multiProcessorCount;
+        OZK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        OZK_CUDA(cudaEventCreate(&c->ev0));
+        OZK_CUDA(cudaEventCreate(&c->ev1));
+        for (auto& e : c->evs) OZK_CUDA(cudaEventCreate(&e));
+        OZK_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (auto& e : c->copy_ev) OZK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        OZK_CUDA(cudaMallocHost(&c->pinned, 4096));
+        return OZK_OK;
+    };
+    const int rc = build();
+    if (rc != OZK_OK) {
+        ozk_ctx_destroy(c);
+        return rc;
+    }
     *out = c;
     return OZK_OK;
 }
@@ -183,7 +202,7 @@ int ozk_ctx_create(int device, ozk_ctx** out) {
 void ozk_ctx_destroy(ozk_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     ntt_free_plans(c);
     fixed_free_tables(c);
     stager_free(c);

@@ -60,71 +60,119 @@ __device__ __forceinline__ Affine<F> ba_finish(int kind, const Affine<F>& a, con
     return r;
 }
 
-// operand `e` of round 0: entry of the sorted index array (point index | sign << 31, or the sentinel)
-template <class F>
-__device__ __forceinline__ bool ba_load_indexed(const uint4* __restrict__ bases, uint32_t e, Affine<F>& p) {
-    if (e == kBaSentinel) {
-        p = Affine<F>::inf();
-        return false;
-    }
-    p = load_affine<F>(bases, e & 0x7fffffffu);
-    if (p.is_inf()) return false;
-    if (e >> 31) p.y = F::neg(p.y);
-    return true;
-}
-
 // ROUND0: operands come from `bases` through the sorted index array; otherwise from the previous round's array `in`.
+// Both passes are software-pipelined: the index pair of slot k+2 and the operands of slot k+1 are requested before slot k is
+// computed, so the two dependent DRAM latencies of a slot (index, then a random 128-byte line per operand) overlap the
+// arithmetic of the slots before it -- without this the kernel is latency-bound (ncu: 6.3 long-scoreboard stalls per issue,
+// integer pipe 57 % busy).
+template <class F, bool ROUND0>
+struct BaSlot {
+    // where the operands of slot g come from
+    __device__ __forceinline__ static uint2 entry(const uint32_t* __restrict__ sorted, size_t g, size_t total) {
+        if (!ROUND0) return make_uint2(0u, 0u);
+        return g < total ? reinterpret_cast<const uint2*>(sorted)[g] : make_uint2(kBaSentinel, kBaSentinel);
+    }
+    __device__ __forceinline__ static const uint4* addr(const uint4* __restrict__ bases, const uint4* __restrict__ in, uint32_t e, size_t g, int which) {
+        constexpr int U = FieldIO<F>::kU4;
+        if (ROUND0) return bases + (size_t)(e & 0x7fffffffu) * (2 * U);
+        return in + (2 * g + which) * (2 * U);
+    }
+    __device__ __forceinline__ static bool present(uint32_t e, size_t g, size_t total) { return ROUND0 ? e != kBaSentinel : g < total; }
+};
+
 template <class F, bool ROUND0>
 __global__ void __launch_bounds__(128, sizeof(F) == 32 ? 4 : 1) msm_ba_round(const uint4* __restrict__ bases, const uint32_t* __restrict__ sorted,
                                                                          const uint4* __restrict__ in, size_t total, uint4* __restrict__ out, int M) {
+    using S = BaSlot<F, ROUND0>;
     const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     const size_t base = warp * 32 * (size_t)M;
     if (base >= total) return;
     F pre[kBaMaxM];
     F run = F::one();
-    auto load_pair = [&](size_t g, Affine<F>& a, bool& ha, Affine<F>& b, bool& hb) {
-        if (ROUND0) {
-            const uint2 e = reinterpret_cast<const uint2*>(sorted)[g];
-            ha = ba_load_indexed<F>(bases, e.x, a);
-            hb = ba_load_indexed<F>(bases, e.y, b);
-        } else {
-            a = load_affine<F>(in, 2 * g);
-            b = load_affine<F>(in, 2 * g + 1);
+    auto slot_of = [&](int k) { return base + (size_t)k * 32 + lane; };
+    auto load_full = [&](uint2 e, size_t g, Affine<F>& a, bool& ha, Affine<F>& b, bool& hb) {
+        ha = S::present(e.x, g, total);
+        hb = S::present(e.y, g, total);
+        a = Affine<F>::inf();
+        b = Affine<F>::inf();
+        if (ha) {
+            a = load_affine<F>(S::addr(bases, in, e.x, g, 0), 0);
             ha = !a.is_inf();
+            if (ROUND0 && ha && (e.x >> 31)) a.y = F::neg(a.y);
+        }
+        if (hb) {
+            b = load_affine<F>(S::addr(bases, in, e.y, g, 1), 0);
             hb = !b.is_inf();
+            if (ROUND0 && hb && (e.y >> 31)) b.y = F::neg(b.y);
         }
     };
-    // forward: running product of the denominators
-#pragma unroll 1
-    for (int k = 0; k < M; k++) {
-        const size_t g = base + (size_t)k * 32 + lane;
-        F den = F::one();
-        if (g < total) {
-            Affine<F> a, b;
-            bool ha, hb;
-            load_pair(g, a, ha, b, hb);
-            ba_classify(a, ha, b, hb, den);
+    // ---- forward: running product of the denominators.  Only the x coordinates are read here; equal or zero x -- a doubling, a
+    // cancellation, an operand at infinity, rare except for the profiler's input -- takes the full loads.
+    {
+        uint2 e0 = S::entry(sorted, slot_of(0), total);                 // entry of the current slot
+        uint2 e2 = M > 1 ? S::entry(sorted, slot_of(1), total) : make_uint2(kBaSentinel, kBaSentinel);   // of the next one
+        F xa = F::zero(), xb = F::zero();
+        {
+            const size_t g = slot_of(0);
+            if (S::present(e0.x, g, total)) xa = FieldIO<F>::load(S::addr(bases, in, e0.x, g, 0));
+            if (S::present(e0.y, g, total)) xb = FieldIO<F>::load(S::addr(bases, in, e0.y, g, 1));
         }
-        run = F::mul(run, den);
-        pre[k] = run;
+#pragma unroll 1
+        for (int k = 0; k < M; k++) {
+            const size_t g = slot_of(k);
+            // requests for the following slots
+            const uint2 e3 = k + 2 < M ? S::entry(sorted, slot_of(k + 2), total) : make_uint2(kBaSentinel, kBaSentinel);
+            F xa_n = F::zero(), xb_n = F::zero();
+            if (k + 1 < M) {
+                const size_t g1 = slot_of(k + 1);
+                if (S::present(e2.x, g1, total)) xa_n = FieldIO<F>::load(S::addr(bases, in, e2.x, g1, 0));
+                if (S::present(e2.y, g1, total)) xb_n = FieldIO<F>::load(S::addr(bases, in, e2.y, g1, 1));
+            }
+            F den = F::one();
+            const bool ha = S::present(e0.x, g, total), hb = S::present(e0.y, g, total);
+            if (ha && hb && xa != xb && !xa.is_zero() && !xb.is_zero()) {
+                den = F::sub(xb, xa);
+            } else if (ha || hb) {
+                Affine<F> a, b;
+                bool fa, fb;
+                load_full(e0, g, a, fa, b, fb);
+                ba_classify(a, fa, b, fb, den);
+            }
+            run = F::mul(run, den);
+            pre[k] = run;
+            e0 = e2;
+            e2 = e3;
+            xa = xa_n;
+            xb = xb_n;
+        }
     }
     F inv = field_inv_ni(run);
-    // backward: inverse of each denominator, then the addition
+    // ---- backward: inverse of each denominator, then the addition
+    {
+        uint2 e0 = S::entry(sorted, slot_of(M - 1), total);
+        uint2 e2 = M > 1 ? S::entry(sorted, slot_of(M - 2), total) : make_uint2(kBaSentinel, kBaSentinel);
+        Affine<F> a, b;
+        bool ha, hb;
+        load_full(e0, slot_of(M - 1), a, ha, b, hb);
 #pragma unroll 1
-    for (int k = M - 1; k >= 0; k--) {
-        const size_t g = base + (size_t)k * 32 + lane;
-        F den = F::one();
-        Affine<F> a = Affine<F>::inf(), b = Affine<F>::inf();
-        int kind = 0;
-        if (g < total) {
-            bool ha, hb;
-            load_pair(g, a, ha, b, hb);
-            kind = ba_classify(a, ha, b, hb, den);
+        for (int k = M - 1; k >= 0; k--) {
+            const size_t g = slot_of(k);
+            const uint2 e3 = k >= 2 ? S::entry(sorted, slot_of(k - 2), total) : make_uint2(kBaSentinel, kBaSentinel);
+            Affine<F> a_n = Affine<F>::inf(), b_n = Affine<F>::inf();
+            bool ha_n = false, hb_n = false;
+            if (k >= 1) load_full(e2, slot_of(k - 1), a_n, ha_n, b_n, hb_n);
+            F den;
+            const int kind = ba_classify(a, ha, b, hb, den);
+            const F inv_den = k ? F::mul(inv, pre[k - 1]) : inv;
+            inv = F::mul(inv, den);
+            if (g < total) store_affine<F>(out, g, ba_finish(kind, a, b, inv_den));
+            e2 = e3;
+            a = a_n;
+            b = b_n;
+            ha = ha_n;
+            hb = hb_n;
         }
-        const F inv_den = k ? F::mul(inv, pre[k - 1]) : inv;
-        inv = F::mul(inv, den);
-        if (g < total) store_affine<F>(out, g, ba_finish(kind, a, b, inv_den));
     }
 }
 

@@ -47,6 +47,7 @@ static int stager_get(ozk_ctx* ctx, Stager** out) {
         *out = ctx->stager;
         return OZK_OK;
     }
+    if (ctx->stager) stager_free(ctx);              // a half-built one left behind by an earlier failure
     Stager* s = new Stager();
     ctx->stager = s;
     for (int t = 0; t < Stager::kThreads; t++) {

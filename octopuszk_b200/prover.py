@@ -35,7 +35,7 @@ import torch.distributed as dist
 from . import distributed as D
 from .algebra import FR_MODULUS as R
 from .algebra import FR_MULTIPLICATIVE_GENERATOR, FR_ROOT, FixedBaseMSM, VariableBaseMSM, _le32
-from .groth16 import FQ, G1_ONE, G2_ONE, fr_random
+from .groth16 import G1_ONE, G2_ONE, fr_random
 from .lib import Bases, Context
 
 
@@ -374,9 +374,9 @@ class DeviceGroth16:
         ev_b2 = ((v[0], v[1]), (v[2], v[3]), (v[4], v[5]))
         r = s = fr_random()
         msm = self.msm.serialMSM
-        A = msm([1, 1, r], [pk.alphaG1, ev_at, pk.deltaG1])                                                    # SerialProver.java:106-108
-        B1 = msm([1, 1, s], [pk.betaG1, ev_b1, pk.deltaG1])
+        # SerialProver.java:106-114: A = alpha + evAt + r delta, B = beta + evBt + s delta (G1 and G2), C = evABC + s A + r B1 - r s delta.
+        # B1 only enters C, so C is expanded over the independent points (the delta terms add up to + r s delta): three small MSMs.
+        A = msm([1, 1, r], [pk.alphaG1, ev_at, pk.deltaG1])
         B2 = msm([1, 1, s], [pk.betaG2, ev_b2, pk.deltaG2])
-        neg_delta = (pk.deltaG1[0], (-pk.deltaG1[1]) % FQ, pk.deltaG1[2])
-        C = msm([1, 1, s, r, r * s % R], [ev_abc, ev_h, A, B1, neg_delta])                                     # :110-114
+        C = msm([1, 1, s, s, r, r, r * s % R], [ev_abc, ev_h, pk.alphaG1, ev_at, pk.betaG1, ev_b1, pk.deltaG1])
         return A, B2, C
