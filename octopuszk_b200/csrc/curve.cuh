@@ -177,50 +177,93 @@ OZK_HD void xyzz_add(XYZZ<F>& acc, const XYZZ<F>& q) {
     acc.zzz = F::mul(F::mul(acc.zzz, q.zzz), PPP);
 }
 
-// ---- one XYZZ doubling spread over four lanes --------------------------------------------------------------------------
-// The window-combining Horner chain of an MSM is ~255 dependent doublings on ONE value: pure latency.  A doubling has 9
-// products but only 3 dependent levels, so four lanes sharing the value through shared memory finish it in 3 product
-// latencies instead of 9.  All lanes run the same instruction stream (same F::mul, operands picked by lane from a slot
-// table), so there is no divergence; the additions between levels are done by lane 0.  Infinity is all zeros and stays
-// all zeros through the formulas.  (Tested on the CPU by running the lanes one after the other: tests/host_arith_check.cc.)
-template <class F>
-struct CoopDbl {
-    enum { sX, sY, sZZ, sZZZ, sU, sV, sXX, sM, sW, sS, sMM, sVZ, sD, sT1, sT2, sWZ, sX3, sDummy0, sDummy1, sDummy2, sDummy3, kSlots };
-    F s[kSlots];
-    OZK_HD void load(const XYZZ<F>& p) { s[sX] = p.x; s[sY] = p.y; s[sZZ] = p.zz; s[sZZZ] = p.zzz; }
-    OZK_HD XYZZ<F> value() const { return {s[sX], s[sY], s[sZZ], s[sZZZ]}; }
-    // level 0..2: the product lane `lane` (0..3) computes
-    OZK_HD void mul_level(int level, int lane) {
-        int a, b, d;
-        if (level == 0) {
-            a = lane == 0 ? sU : sX; b = a; d = lane == 0 ? sV : lane == 1 ? sXX : sDummy0 + lane;
-        } else if (level == 1) {
-            a = lane == 0 ? sU : lane == 1 ? sM : lane == 2 ? sX : sV;
-            b = lane == 0 ? sV : lane == 1 ? sM : lane == 2 ? sV : sZZ;
-            d = lane == 0 ? sW : lane == 1 ? sMM : lane == 2 ? sS : sVZ;
-        } else {
-            a = lane == 0 ? sM : lane == 1 ? sW : lane == 2 ? sW : sX;
-            b = lane == 0 ? sD : lane == 1 ? sY : lane == 2 ? sZZZ : sX;
-            d = lane == 0 ? sT1 : lane == 1 ? sT2 : lane == 2 ? sWZ : sDummy3;
-        }
-        F r = F::mul(s[a], s[b]);
-        s[d] = r;
+// ---- XYZZ doubling / addition as LEVELS of up to four independent products ----------------------------------------------
+// The tail of an MSM (recombining the windows: ~255 dependent doublings on ONE value, and the last levels of the bucket reduction)
+// is pure latency: a lone warp is bound by the issue rate of the multiplier (one IMAD.WIDE per four cycles), so a thread doing
+// the 9 products of a doubling one after the other takes 9 product times.  The formulas have only 3 (doubling) and 4 (addition)
+// DEPENDENT levels of products, so they are written here once as level schedules over a functor
+//     mul4(A, B, R):  R[i] = A[i] * B[i],  i < 4
+// that the MSM tail kernel implements with the lanes of a warp (msm_impl.cuh, CoopMul4: every lane holds the whole state,
+// lane i computes product i -- for Fq2 three lanes share a product, one Karatsuba term each -- and the results are
+// broadcast with shuffles), and that tests/host_arith_check.cc runs with a plain loop against the oracle.
+// Infinity is all zeros and stays all zeros through the doubling; the addition handles its special cases explicitly, like
+// xyzz_add (all lanes hold the same values, so those branches are uniform).
+template <class F, class Mul4>
+OZK_HD XYZZ<F> xyzz_dbl_levels(const XYZZ<F>& p, Mul4&& mul4) {
+    F A[4], B[4], R[4];
+    const F U = F::dbl(p.y);
+    A[0] = U;   B[0] = U;                // V = U^2
+    A[1] = p.x; B[1] = p.x;              // XX
+    A[2] = F::zero(); B[2] = F::zero();
+    A[3] = F::zero(); B[3] = F::zero();
+    mul4(A, B, R);
+    const F V = R[0];
+    const F M = F::add(F::dbl(R[1]), R[1]);
+    A[0] = U;   B[0] = V;                // W = U V
+    A[1] = M;   B[1] = M;                // M^2
+    A[2] = p.x; B[2] = V;                // S = X V
+    A[3] = V;   B[3] = p.zz;             // ZZ3
+    mul4(A, B, R);
+    const F W = R[0], S = R[2];
+    XYZZ<F> r;
+    r.x = F::sub(R[1], F::dbl(S));
+    r.zz = R[3];
+    A[0] = M;   B[0] = F::sub(S, r.x);   // M (S - X3)
+    A[1] = W;   B[1] = p.y;              // W Y
+    A[2] = W;   B[2] = p.zzz;            // ZZZ3
+    A[3] = F::zero(); B[3] = F::zero();
+    mul4(A, B, R);
+    r.y = F::sub(R[0], R[1]);
+    r.zzz = R[2];
+    return r;
+}
+
+template <class F, class Mul4>
+OZK_HD XYZZ<F> xyzz_add_levels(const XYZZ<F>& p, const XYZZ<F>& q, Mul4&& mul4) {
+    if (q.is_inf()) return p;
+    if (p.is_inf()) return q;
+    F A[4], B[4], R[4];
+    A[0] = p.x; B[0] = q.zz;             // U1
+    A[1] = q.x; B[1] = p.zz;             // U2
+    A[2] = p.y; B[2] = q.zzz;            // S1
+    A[3] = q.y; B[3] = p.zzz;            // S2
+    mul4(A, B, R);
+    const F U1 = R[0], S1 = R[2];
+    const F Pp = F::sub(R[1], U1);
+    const F Rr = F::sub(R[3], S1);
+    if (Pp.is_zero()) {
+        if (Rr.is_zero()) return xyzz_dbl_levels(p, mul4);
+        return XYZZ<F>::inf();
     }
-    // the additions before level `level` (0..2) and after the last one (3); executed by one lane
-    OZK_HD void fix(int level) {
-        if (level == 0) {
-            s[sU] = F::dbl(s[sY]);
-        } else if (level == 1) {
-            s[sM] = F::add(F::dbl(s[sXX]), s[sXX]);
-        } else if (level == 2) {
-            s[sX3] = F::sub(s[sMM], F::dbl(s[sS]));
-            s[sD] = F::sub(s[sS], s[sX3]);
-        } else {
-            s[sY] = F::sub(s[sT1], s[sT2]);
-            s[sX] = s[sX3];
-            s[sZZ] = s[sVZ];
-            s[sZZZ] = s[sWZ];
-        }
+    A[0] = Pp;   B[0] = Pp;              // PP
+    A[1] = Rr;   B[1] = Rr;              // R^2
+    A[2] = p.zz; B[2] = q.zz;
+    A[3] = p.zzz; B[3] = q.zzz;
+    mul4(A, B, R);
+    const F PP = R[0], RR = R[1], ZZ12 = R[2], ZZZ12 = R[3];
+    A[0] = Pp;   B[0] = PP;              // PPP
+    A[1] = U1;   B[1] = PP;              // Q
+    A[2] = ZZ12; B[2] = PP;              // ZZ3
+    A[3] = F::zero(); B[3] = F::zero();
+    mul4(A, B, R);
+    const F PPP = R[0], Q = R[1];
+    XYZZ<F> r;
+    r.zz = R[2];
+    r.x = F::sub(F::sub(RR, PPP), F::dbl(Q));
+    A[0] = Rr;    B[0] = F::sub(Q, r.x); // R (Q - X3)
+    A[1] = S1;    B[1] = PPP;            // S1 PPP
+    A[2] = ZZZ12; B[2] = PPP;            // ZZZ3
+    A[3] = F::zero(); B[3] = F::zero();
+    mul4(A, B, R);
+    r.y = F::sub(R[0], R[1]);
+    r.zzz = R[2];
+    return r;
+}
+// the functor of the CPU-side test (and of any caller without lanes to spare)
+template <class F>
+struct SerialMul4 {
+    OZK_HD void operator()(const F (&A)[4], const F (&B)[4], F (&R)[4]) const {
+        for (int i = 0; i < 4; i++) R[i] = F::mul(A[i], B[i]);
     }
 };
 

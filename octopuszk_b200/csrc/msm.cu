@@ -425,11 +425,16 @@ static int msm_reduce_phase(ozk_ctx* ctx, const MsmLaunch& L, const MsmShape& sh
     cudaStream_t st = ctx->stream;
 
     // hierarchical reduction: one launch per level (msm_reduce_level).  Level l turns A_l (m[l] per window) into run = A_{l+1}
-    // and acc_l (m[l+1] per window each) and carries acc_0 .. acc_{l-1} one summation step further.
-    uint32_t m[9], nlev = 0;
+    // and acc_l (m[l+1] per window each) and carries acc_0 .. acc_{l-1} one summation step further.  Levels with enough inputs
+    // to fill the machine use groups of 8 (a serial chain of 15 additions per thread, fewest bytes moved); below that the chain
+    // is pure latency and groups of 2 -- one addition per thread and level, and fewer additions in total -- finish sooner.
+    uint32_t m[kMaxReduceLevels + 1], logs[kMaxReduceLevels], nlev = 0;
     m[0] = sh.nb;
     while (m[nlev] > 1) {
-        m[nlev + 1] = (m[nlev] + kWsumS - 1) / kWsumS;
+        if (nlev >= (uint32_t)kMaxReduceLevels) { set_error("msm: too many reduction levels"); return OZK_ERR_ARG; }
+        logs[nlev] = ((size_t)m[nlev] * sh.nwin >= kWsumBigMin) ? kWsumLogSBig : kWsumLogSSmall;
+        const uint32_t S = 1u << logs[nlev];
+        m[nlev + 1] = (m[nlev] + S - 1) / S;
         nlev++;
     }
     size_t per_win = 4;
@@ -444,12 +449,13 @@ static int msm_reduce_phase(ozk_ctx* ctx, const MsmLaunch& L, const MsmShape& sh
     FinalArgs fa;
     memset(&fa, 0, sizeof fa);
     const void* level_in = ctx->msm[bkt_slot].p;
-    const void* partial[8] = {};          // partial[k]: current (partially summed) acc array of level k
+    const void* partial[kMaxReduceLevels] = {};          // partial[k]: current (partially summed) acc array of level k
     for (uint32_t l = 0; l < nlev; l++) {
         ReduceArgs ra;
         memset(&ra, 0, sizeof ra);
         ra.m_in = m[l];
         ra.nwin = sh.nwin;
+        ra.s = 1u << logs[l];
         void* run = take(m[l + 1]);
         void* acc = take(m[l + 1]);
         ra.job[0] = {(const uint4*)level_in, (uint4*)run, (uint4*)acc};
@@ -464,13 +470,17 @@ static int msm_reduce_phase(ozk_ctx* ctx, const MsmLaunch& L, const MsmShape& sh
         ctx->launches += 1;
         level_in = run;
     }
-    for (uint32_t l = 0; l < nlev; l++) fa.sum_acc[l] = (const uint4*)partial[l];
+    for (uint32_t l = 0; l < nlev; l++) {
+        fa.sum_acc[l] = (const uint4*)partial[l];
+        fa.log_s[l] = (uint8_t)logs[l];
+    }
     fa.total = (const uint4*)level_in;     // one element per window: the plain sum of all buckets (nb == 1: the bucket itself)
     fa.nlevels = nlev;
     fa.nwin = sh.nwin;
     fa.c = sh.c;
     void* window_vals = take(1);
-    if (L.final(st, fa, window_vals, d_out)) { set_error("msm: final launch failed"); return OZK_ERR_CUDA; }
+    // completion counter of msm_tail: the last word of B_MISC, zeroed when the buffer is first sized and left zero by the kernel
+    if (L.final(st, fa, window_vals, d_out, (uint32_t*)ctx->msm[B_MISC].p + (kMiscWords - 1))) { set_error("msm: final launch failed"); return OZK_ERR_CUDA; }
     ctx->launches += 1;
     OZK_CUDA(cudaEventRecord(ctx->evs[5], st));
     OZK_CUDA(cudaGetLastError());
@@ -671,26 +681,46 @@ static int msm_stream_end(ozk_ctx* ctx, uint8_t* out) {
     return msm_finish(ctx, d_res, bytes, out);
 }
 
-// Slice schedule of a whole-array call: 1 / 2 / 4 / 8 slices by size, lengths growing geometrically (x1.3, the ratio of compute
-// to copy time per pair): the first slice is small, so the GPU starts after ~4 % of the copy instead of 1/8 of it, and every
-// later copy still lands before the compute of the slices before it has finished.  OZK_HOST_SLICE_GROWTH=1 gives equal slices.
+// Slice schedule of a whole-array call.  The compute of a slice starts when its copy has landed, copies run back to back at the
+// PCIe rate, and on one GPU the compute (2.8 ns per G1 pair) is slower than the copy (2.3 ns per pair of 128 bytes), so the
+// schedule wants (i) a small first slice -- the GPU idles while it crosses -- (ii) growth slow enough that copy k+1 always
+// lands before compute k ends: f_k <= f_0 + (t_gpu / t_copy - 1) F_{k-1} + k B / T_copy with B ~ 0.4 ms of fixed cost per slice
+// (bucket set-up of the shared buckets, the sort's small launches), and (iii) a small LAST slice, because when the host link is
+// the bottleneck (several GPUs behind one PCIe switch) the step ends one last-slice compute after the last byte arrives.
+// Round 1 grew the slices geometrically (x1.3: the copy of slice k+1 then takes 1.08x the compute of slice k, the GPU waits a
+// little on every slice, and the step ends a 26 % slice after the copy): 54.7 ms at 2^24; OZK_HOST_SLICE_GROWTH=g restores it.
+static constexpr int kMaxSlices = 16;
 static int msm_plan_slices(size_t n, size_t* bounds, int cap) {
+    static const double plan8[8] = {0.04, 0.07, 0.11, 0.15, 0.19, 0.20, 0.16, 0.08};
+    static const double plan4[4] = {0.10, 0.27, 0.38, 0.25};
+    static const double plan2[2] = {0.35, 0.65};
     int nslices = 1;
     if (n >= ((size_t)1 << 22)) nslices = 8;
     else if (n >= ((size_t)1 << 20)) nslices = 4;
     else if (n >= ((size_t)1 << 18)) nslices = 2;
-    if (const char* e = getenv("OZK_HOST_SLICES")) nslices = std::max(1, std::min(kCopyChunks, atoi(e)));
-    nslices = std::min(nslices, cap);
-    double growth = 1.3;
+    double growth = 0;
+    if (const char* e = getenv("OZK_HOST_SLICES")) {
+        nslices = std::max(1, std::min(kMaxSlices, atoi(e)));
+        growth = 1.3;
+    }
     if (const char* e = getenv("OZK_HOST_SLICE_GROWTH")) growth = std::max(1.0, atof(e));
-    double total = 0, w = 1;
-    for (int k = 0; k < nslices; k++, w *= growth) total += w;
+    nslices = std::min(nslices, cap);
+    double frac[kMaxSlices];
+    const double* tab = nslices == 8 ? plan8 : nslices == 4 ? plan4 : nslices == 2 ? plan2 : nullptr;
+    if (growth == 0 && tab) {
+        for (int k = 0; k < nslices; k++) frac[k] = tab[k];
+    } else {
+        if (growth == 0) growth = 1.3;
+        double total = 0, w = 1;
+        for (int k = 0; k < nslices; k++, w *= growth) total += w;
+        w = 1;
+        for (int k = 0; k < nslices; k++, w *= growth) frac[k] = w / total;
+    }
     double acc = 0;
-    w = 1;
     bounds[0] = 0;
-    for (int k = 0; k < nslices; k++, w *= growth) {
-        acc += w;
-        size_t b = (size_t)((double)n * acc / total);
+    for (int k = 0; k < nslices; k++) {
+        acc += frac[k];
+        size_t b = (size_t)((double)n * acc);
         b = (b + 255) & ~(size_t)255;
         bounds[k + 1] = (k + 1 == nslices) ? n : std::min(b, n);
         if (bounds[k + 1] < bounds[k]) bounds[k + 1] = bounds[k];
@@ -700,8 +730,8 @@ static int msm_plan_slices(size_t n, size_t* bounds, int cap) {
 
 static int msm_run_host(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* b1, const uint8_t* b2, BaseSrc s1, BaseSrc s2, size_t n, uint8_t* out) {
     OZK_ARG(n > 0 && n < ((size_t)1 << 31), "msm: between 1 and 2^31 - 1 points per call");
-    size_t bounds[kCopyChunks + 1];
-    const int nslices = msm_plan_slices(n, bounds, kCopyChunks);
+    size_t bounds[kMaxSlices + 1];
+    const int nslices = msm_plan_slices(n, bounds, kMaxSlices);
     size_t slice = 0;                                    // the longest slice sizes the per-slice scratch
     for (int k = 0; k < nslices; k++) slice = std::max(slice, bounds[k + 1] - bounds[k]);
     OZK_TRY(msm_stream_begin(ctx, b1 || s1.any(), b2 || s2.any(), n, slice, s1.affine, s2.affine));

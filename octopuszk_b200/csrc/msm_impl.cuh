@@ -8,16 +8,20 @@
 //   scatter  : counting-sort the point indices of every window by bucket                     [msm.cu]
 //   accumulate : one thread per (window, bucket) adds its run of points into an XYZZ accumulator (mixed add 8M+2S);
 //                runs longer than SEG are split into extra tasks and merged by a warp-cooperative reduction
-//   reduce   : sum_b (b+1) * B_b per window by an 8-ary hierarchy of running sums (kWsumS; all windows in parallel)
-//   final    : Horner over the windows, conversion to the canonical Jacobian wire format
+//   reduce   : sum_b (b+1) * B_b per window by a hierarchy of running sums (groups of 8 while a level fills the machine,
+//              groups of 2 -- one addition deep -- once it is latency-bound; all windows in parallel)
+//   tail     : per-window recombination of the levels and Horner over the windows, every doubling / addition spread over
+//              the lanes of a warp (level schedules of curve.cuh); conversion to the canonical Jacobian wire format
 #pragma once
 #include "curve.cuh"
 
 namespace ozk {
 
 static constexpr int kSegMax = 1024;     // longest run of points a single accumulate task handles (runtime value <= this)
-static constexpr int kWsumS = 8;         // group size of the hierarchical bucket reduction (log2 = 3): short serial chains
-static constexpr int kWsumLogS = 3;
+static constexpr int kWsumLogSBig = 3;   // bucket reduction: groups of 8 (a serial chain of 15 additions per thread) on levels with enough
+static constexpr int kWsumLogSSmall = 1; // inputs to fill the machine, groups of 2 (ONE addition per thread and level) below that
+static constexpr uint32_t kWsumBigMin = 1u << 18;   // inputs (all windows together) from which a level counts as throughput-bound
+static constexpr int kMaxReduceLevels = 24;
 static constexpr int kConvBatchMax = 64; // most points per thread in the batched normalisations (one inversion per thread)
 // points per thread: large batches amortise the ~380-product inversion, small inputs keep enough threads in flight
 static inline int conv_batch_for(size_t n) {
@@ -298,27 +302,32 @@ struct ReduceJob {
     uint4* out_acc;      // weighted sums of the groups, or null for a plain-sum job
 };
 struct ReduceArgs {
-    ReduceJob job[8];
+    ReduceJob job[kMaxReduceLevels];
     uint32_t njobs;
     uint32_t m_in;       // elements per window in every input of this level
     uint32_t nwin;
+    uint32_t s;          // group size of this level (8 or 2)
 };
 
 template <class F>
 __global__ void __launch_bounds__(128) msm_reduce_level(ReduceArgs a) {
     const ReduceJob jb = a.job[blockIdx.y];
-    const uint32_t groups = (a.m_in + kWsumS - 1) / kWsumS;
+    const uint32_t S = a.s;
+    const uint32_t groups = (a.m_in + S - 1) / S;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= groups * a.nwin) return;
     const uint32_t w = t / groups, g = t % groups;
-    const size_t base = (size_t)w * a.m_in + (size_t)g * kWsumS;
-    const uint32_t len = min((uint32_t)kWsumS, a.m_in - g * kWsumS);
+    const size_t base = (size_t)w * a.m_in + (size_t)g * S;
+    const uint32_t len = min(S, a.m_in - g * S);
     XYZZ<F> run = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
     XYZZ<F> q = load_xyzz<F>(jb.in, base + len - 1);
     for (int j = (int)len - 1; j >= 1; j--) {
         XYZZ<F> qn = load_xyzz<F>(jb.in, base + j - 1);
         xyzz_add(run, q);
-        if (jb.out_acc) xyzz_add(acc, run);
+        if (jb.out_acc) {
+            if (j == (int)len - 1) acc = run;          // inf + run: a copy, not an addition (groups of 2 then cost ONE addition)
+            else xyzz_add(acc, run);
+        }
         q = qn;
     }
     xyzz_add(run, q);
@@ -326,69 +335,116 @@ __global__ void __launch_bounds__(128) msm_reduce_level(ReduceArgs a) {
     if (jb.out_acc) store_xyzz<F>(jb.out_acc, (size_t)w * groups + g, acc);
 }
 
-// ---- final ------------------------------------------------------------------------------------------------------------
+// ---- tail --------------------------------------------------------------------------------------------------------------
 // sum_acc[l][w] (l < nlevels): sum over groups of acc at level l; total[w]: plain sum of all buckets of window w.
-// Window value W_w = total[w] + sum_l S^l * sum_acc[l][w]; result = sum_w 2^(c w) W_w.  Written as canonical Jacobian
-// (X|Y|Z, 32 bytes each per base-field element), (0,1,0) for infinity (what the reference emits,
+// Window value W_w = total[w] + sum_l (prod_{k<l} S_k) * sum_acc[l][w]; result = sum_w 2^(c w) W_w.  Written as canonical
+// Jacobian (X|Y|Z, 32 bytes each per base-field element), (0,1,0) for infinity (what the reference emits,
 // algebra_msm_VariableBaseMSM.cu:1274-1276).
 struct FinalArgs {
-    const uint4* sum_acc[8];
+    const uint4* sum_acc[kMaxReduceLevels];
     const uint4* total;
     uint32_t nlevels;
     uint32_t nwin;
     uint32_t c;
+    uint8_t log_s[kMaxReduceLevels];
 };
 
+// mul4 of the level schedules (curve.cuh) over the lanes of one warp.  Every lane holds the same A, B; lane i (mod 4) computes
+// product i and the four results are broadcast back with shuffles, so one level costs ONE product time whatever the number of
+// products.  Fq2: lane 3 i + k (mod 12) computes Karatsuba term k of product i (a0 b0, a1 b1, (a0 + a1)(b0 + b1)) and the terms
+// are combined after the broadcast -- an Fq2 product in the time of one Fq product.  All 32 lanes run the same instructions
+// (the upper lanes repeat the work of the lower ones), so the whole warp stays converged and holds identical state.
+template <class F> struct CoopMul4;
+template <> struct CoopMul4<Fq> {
+    __device__ __forceinline__ void operator()(const Fq (&A)[4], const Fq (&B)[4], Fq (&R)[4]) const {
+        const int i = threadIdx.x & 3;
+        Fq a = A[0], b = B[0];
+#pragma unroll
+        for (int k = 1; k < 4; k++) {
+            if (i == k) { a = A[k]; b = B[k]; }
+        }
+        const Fq r = Fq::mul(a, b);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+#pragma unroll
+            for (int l = 0; l < 8; l++) R[k].v[l] = __shfl_sync(0xffffffffu, r.v[l], k);
+        }
+    }
+};
+template <> struct CoopMul4<Fq2> {
+    __device__ __forceinline__ void operator()(const Fq2 (&A)[4], const Fq2 (&B)[4], Fq2 (&R)[4]) const {
+        const int idx = (threadIdx.x & 31) % 12;
+        const int i = idx / 3, t = idx - 3 * i;
+        Fq2 a = A[0], b = B[0];
+#pragma unroll
+        for (int k = 1; k < 4; k++) {
+            if (i == k) { a = A[k]; b = B[k]; }
+        }
+        Fq x = Fq::add(a.c0, a.c1), y = Fq::add(b.c0, b.c1);
+        if (t == 0) { x = a.c0; y = b.c0; }
+        if (t == 1) { x = a.c1; y = b.c1; }
+        const Fq r = Fq::mul(x, y);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            Fq v0, v1, v2;
+#pragma unroll
+            for (int l = 0; l < 8; l++) {
+                v0.v[l] = __shfl_sync(0xffffffffu, r.v[l], 3 * k);
+                v1.v[l] = __shfl_sync(0xffffffffu, r.v[l], 3 * k + 1);
+                v2.v[l] = __shfl_sync(0xffffffffu, r.v[l], 3 * k + 2);
+            }
+            R[k].c0 = Fq::sub(v0, v1);
+            R[k].c1 = Fq::sub(Fq::sub(v2, v0), v1);
+        }
+    }
+};
+template <class F> __device__ __noinline__ XYZZ<F> coop_dbl(XYZZ<F> p) { return xyzz_dbl_levels(p, CoopMul4<F>()); }
+template <class F> __device__ __noinline__ XYZZ<F> coop_add(XYZZ<F> p, XYZZ<F> q) { return xyzz_add_levels(p, q, CoopMul4<F>()); }
+
+// One warp per window recombines the levels of that window (nlevels doublings-and-additions: the other latency chain of the
+// tail); the warp that finishes last (a counter in global memory) then runs the Horner chain over the windows -- one launch,
+// no second kernel boundary.  `done` must be zero on entry and is left zero.
 template <class F>
-__global__ void msm_final(FinalArgs a, uint4* __restrict__ window_vals, uint4* __restrict__ out) {
+__global__ void __launch_bounds__(32) msm_tail(FinalArgs a, uint4* __restrict__ window_vals, uint4* __restrict__ out, uint32_t* __restrict__ done) {
     constexpr int U = FieldIO<F>::kU4;
-    const uint32_t w = threadIdx.x;
-    if (w < a.nwin) {
+    const uint32_t w = blockIdx.x;
+    {
         XYZZ<F> T = XYZZ<F>::inf();
         for (int l = (int)a.nlevels - 1; l >= 0; l--) {
-            for (int d = 0; d < kWsumLogS; d++) T = xyzz_dbl(T);
-            XYZZ<F> q = load_xyzz<F>(a.sum_acc[l], w);
-            xyzz_add(T, q);
+            for (int d = 0; d < (int)a.log_s[l]; d++) T = coop_dbl<F>(T);
+            T = coop_add<F>(T, load_xyzz<F>(a.sum_acc[l], w));
         }
-        XYZZ<F> tot = load_xyzz<F>(a.total, w);
-        xyzz_add(T, tot);
-        store_xyzz<F>(window_vals, w, T);
+        T = coop_add<F>(T, load_xyzz<F>(a.total, w));
+        if (threadIdx.x == 0) store_xyzz<F>(window_vals, w, T);
     }
-    __syncthreads();
-    // Horner over the windows: ~nwin * c dependent doublings.  Lanes 0..3 of warp 0 share each doubling (CoopDbl: three
-    // product latencies instead of nine); lane 0 does the nwin additions and the output conversion.
-    __shared__ CoopDbl<F> st;
-    if (threadIdx.x < 4) {
-        const int lane = threadIdx.x;
-        const unsigned mask = 0xfu;
-        if (lane == 0) st.load(XYZZ<F>::inf());
-        __syncwarp(mask);
-        for (int ww = (int)a.nwin - 1; ww >= 0; ww--) {
-            for (uint32_t d = 0; d < a.c; d++) {
-#pragma unroll 1
-                for (int level = 0; level < 3; level++) {
-                    if (lane == 0) st.fix(level);
-                    __syncwarp(mask);
-                    st.mul_level(level, lane);
-                    __syncwarp(mask);
-                }
-                if (lane == 0) st.fix(3);
-                __syncwarp(mask);
-            }
-            if (lane == 0) {
-                XYZZ<F> res = st.value();
-                XYZZ<F> q = load_xyzz<F>(window_vals, ww);
-                xyzz_add(res, q);
-                st.load(res);
-            }
-            __syncwarp(mask);
+    __threadfence();
+    uint32_t last = 0;
+    if (threadIdx.x == 0) last = (atomicAdd(done, 1u) == a.nwin - 1) ? 1u : 0u;
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+    __threadfence();
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (int ww = (int)a.nwin - 1; ww >= 0; ww--) {
+        if (ww != (int)a.nwin - 1) {
+            for (uint32_t d = 0; d < a.c; d++) acc = coop_dbl<F>(acc);
         }
-        if (lane == 0) {
-            Jacobian<F> j = xyzz_to_jacobian(st.value());
-            FieldIO<F>::store(out, F::from_mont(j.x));
-            FieldIO<F>::store(out + U, F::from_mont(j.y));
-            FieldIO<F>::store(out + 2 * U, F::from_mont(j.z));
+        // window values were written by other blocks during this launch: read them around L1
+        XYZZ<F> q;
+        {
+            uint4 raw[4 * U];
+            const uint4* src = window_vals + (size_t)ww * (4 * U);
+#pragma unroll
+            for (int k = 0; k < 4 * U; k++) raw[k] = __ldcg(src + k);
+            q = load_xyzz<F>(raw, 0);
         }
+        acc = coop_add<F>(acc, q);
+    }
+    if (threadIdx.x == 0) {
+        Jacobian<F> j = xyzz_to_jacobian(acc);
+        FieldIO<F>::store(out, F::from_mont(j.x));
+        FieldIO<F>::store(out + U, F::from_mont(j.y));
+        FieldIO<F>::store(out + 2 * U, F::from_mont(j.z));
+        *done = 0;
     }
 }
 
@@ -425,7 +481,7 @@ struct MsmLaunch {
                       uint32_t ovf_cap, void* buckets, void* ovf_partial);
     int (*merge)(cudaStream_t, const OvfBucket* ob, const uint32_t* ob_count, uint32_t ob_cap, const void* ovf_partial, void* buckets);
     int (*reduce_level)(cudaStream_t, const ReduceArgs& a);
-    int (*final)(cudaStream_t, const FinalArgs& a, void* window_vals, void* out);
+    int (*final)(cudaStream_t, const FinalArgs& a, void* window_vals, void* out, uint32_t* done);
     int (*sum_wire)(cudaStream_t, const void* in, uint32_t k, void* out);
     size_t affine_bytes;     // per point
     size_t jac_bytes;        // per point, wire format
@@ -465,13 +521,13 @@ extern const MsmLaunch kMsmG2;
         return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                                     \
     }                                                                                                                          \
     static int NAME##_reduce_level(cudaStream_t s, const ReduceArgs& a) {                                                      \
-        uint32_t groups = (a.m_in + kWsumS - 1) / kWsumS;                                                                      \
+        uint32_t groups = (a.m_in + a.s - 1) / a.s;                                                                            \
         dim3 grid((groups * a.nwin + 127) / 128, a.njobs);                                                                     \
         msm_reduce_level<F><<<grid, 128, 0, s>>>(a);                                                                           \
         return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                                     \
     }                                                                                                                          \
-    static int NAME##_final(cudaStream_t s, const FinalArgs& a, void* window_vals, void* out) {                                \
-        msm_final<F><<<1, 256, 0, s>>>(a, (uint4*)window_vals, (uint4*)out);                                                   \
+    static int NAME##_final(cudaStream_t s, const FinalArgs& a, void* window_vals, void* out, uint32_t* done) {                \
+        msm_tail<F><<<a.nwin, 32, 0, s>>>(a, (uint4*)window_vals, (uint4*)out, done);                                          \
         return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                                     \
     }                                                                                                                          \
     static int NAME##_sum_wire(cudaStream_t s, const void* in, uint32_t k, void* out) {                                        \

@@ -257,7 +257,13 @@ __device__ __forceinline__ void cp_async_wait_all() {
 // Q decimation-in-frequency stages on 2^Q registers.  Element u sits at index base + u*m of the transform; stage a
 // pairs u with u + 2^(Q-1-a).  The twiddle of a pair depends only on (u mod half) and j = index mod m.
 // M_IS_ONE (the final step, m == 1): exponents with u_local == 0 are zero, those multiplications are skipped.
-template <int Q, bool M_IS_ONE>
+// LAZY: values stay in [0, 2r) (inputs may be anywhere in that range): sums are reduced against 2r, the difference goes into the
+// product as p - q + 2r < 4r and the product leaves out its final subtraction; the caller reduces once at the very end
+// (fp256.cuh, "lazy" domain).  2^26: 14.57 -> 13.87 ms.  The products stay INLINED: the kernel is 111 KB of straight-line code
+// that every warp runs through once per tile (15 % of the warp samples are "no instruction" stalls), but calling one shared
+// copy of the product instead (operands and result in registers, 38 KB of code) was slower, 16.6 ms, and two products per call
+// 16.2 ms: a called product cannot be interleaved with the additions of the neighbouring butterflies.
+template <int Q, bool M_IS_ONE, bool LAZY>
 __device__ __forceinline__ void dif_step(Fr (&x)[1 << Q], const Fr* wtab, uint32_t j, uint32_t log_m, uint32_t log_t) {
 #pragma unroll
     for (int a = 0; a < Q; a++) {
@@ -272,10 +278,16 @@ __device__ __forceinline__ void dif_step(Fr (&x)[1 << Q], const Fr* wtab, uint32
             for (int blk = 0; blk < (1 << Q); blk += 2 * half) {
                 Fr& p = x[blk + ul];
                 Fr& q = x[blk + ul + half];
-                Fr s = Fr::add(p, q);
-                Fr d = Fr::sub(p, q);
-                p = s;
-                q = trivial ? d : Fr::mul(d, w);
+                if (LAZY) {
+                    const Fr s = Fr::add_lazy(p, q);
+                    q = trivial ? Fr::sub_lazy(p, q) : Fr::mul_lazy(Fr::sub_lazy_wide(p, q), w);
+                    p = s;
+                } else {
+                    Fr s = Fr::add(p, q);
+                    Fr d = Fr::sub(p, q);
+                    p = s;
+                    q = trivial ? d : Fr::mul(d, w);
+                }
             }
         }
     }
@@ -299,7 +311,7 @@ __device__ __forceinline__ void run_step(uint4* lo, uint4* hi, const Fr* wtab, u
         Fr x[1 << Q];
 #pragma unroll
         for (int u = 0; u < (1 << Q); u++) x[u] = lds_fr(lo, hi, Layout<LAST>::slot(base + ((uint32_t)u << log_m), c, log_t, log_c));
-        dif_step<Q, M_IS_ONE>(x, wtab, j, log_m, log_t);
+        dif_step<Q, M_IS_ONE, true>(x, wtab, j, log_m, log_t);
 #pragma unroll
         for (int u = 0; u < (1 << Q); u++) sts_fr(lo, hi, Layout<LAST>::slot(base + ((uint32_t)u << log_m), c, log_t, log_c), x[u]);
     }
@@ -408,7 +420,7 @@ __global__ void __launch_bounds__(128, 5) ntt_pass_kernel(PassArgs a) {
                         w[u] = a.tdir[((size_t)k << a.log_inner) + col0 + c];
                     } else {
                         const uint32_t e = ek << a.log_outer;
-                        w[u] = Fr::mul(a.tlo[e & ((1u << a.H) - 1)], a.thi[e >> a.H]);
+                        w[u] = Fr::mul_lazy(a.tlo[e & ((1u << a.H) - 1)], a.thi[e >> a.H]);     // < 2r: fine as a factor (v w < 4 r^2)
                     }
                 }
             }
@@ -420,23 +432,24 @@ __global__ void __launch_bounds__(128, 5) ntt_pass_kernel(PassArgs a) {
             const uint32_t c = i & (C - 1);
             const uint32_t k = i >> log_c;
             const uint32_t pos = LOGT ? (__brev(k) >> (32 - LOGT)) : 0;
-            Fr v = lds_fr(lo, hi, Layout<LAST>::slot(pos, c, LOGT, log_c));
+            Fr v = lds_fr(lo, hi, Layout<LAST>::slot(pos, c, LOGT, log_c));      // in [0, 2r)
             if (!LAST) {
-                // inter-pass twiddle omega_n^(outer * column * k)
-                if ((col0 + c) * k != 0) v = Fr::mul(v, w[u]);
+                // inter-pass twiddle omega_n^(outer * column * k); the value stays in [0, 2r) between the passes
+                if ((col0 + c) * k != 0) v = Fr::mul_lazy(v, w[u]);
                 store_fr(a.out + (out_base + ((size_t)k << a.log_inner) + c) * 2, v);
             } else {
                 const size_t idx = out_base + ((size_t)k << a.log_outer) + c;
                 if (a.npeers) {
                     if (idx != 0 && a.my_rank != 0) {
-                        const Fr wp = Fr::mul(a.ptlo[idx & ((1u << a.pH) - 1)], a.pthi[idx >> a.pH]);
-                        v = Fr::mul(v, wp);
+                        const Fr wp = Fr::mul_lazy(a.ptlo[idx & ((1u << a.pH) - 1)], a.pthi[idx >> a.pH]);
+                        v = Fr::mul_lazy(v, wp);
                     }
+                    v = Fr::reduce_lazy(v);                      // canonical on the wire
                     const uint32_t dest = (uint32_t)(idx >> a.log_chunk);
                     const size_t local = ((size_t)a.my_rank << a.log_chunk) + (idx & (((size_t)1 << a.log_chunk) - 1));
                     store_fr(a.peer[dest] + local * 2, v);       // peer memory over NVLink (or this GPU's own buffer)
                 } else {
-                    store_fr(a.out + idx * 2, v);
+                    store_fr(a.out + idx * 2, Fr::reduce_lazy(v));   // the last pass hands out canonical values
                 }
             }
         }
@@ -677,7 +690,7 @@ __global__ void __launch_bounds__(256) fr_dft_small_kernel(const uint4* __restri
     Fr x[1 << Q];
 #pragma unroll
     for (int u = 0; u < (1 << Q); u++) x[u] = load_fr(in + ((size_t)u * len + j) * 2);
-    dif_step<Q, true>(x, wtab, 0, 0, Q);
+    dif_step<Q, true, false>(x, wtab, 0, 0, Q);
 #pragma unroll
     for (int u = 0; u < (1 << Q); u++) {
         const uint32_t k1 = __brev((uint32_t)u) >> (32 - Q);
@@ -701,7 +714,7 @@ __global__ void __launch_bounds__(256) fr_dft_small_scatter_kernel(const uint4* 
     Fr x[1 << Q];
 #pragma unroll
     for (int u = 0; u < (1 << Q); u++) x[u] = load_fr(in + ((size_t)u * len + j) * 2);
-    dif_step<Q, true>(x, wtab, 0, 0, Q);
+    dif_step<Q, true, false>(x, wtab, 0, 0, Q);
     const size_t i2 = (size_t)rank * len + j;
 #pragma unroll
     for (int u = 0; u < (1 << Q); u++) {

@@ -46,6 +46,17 @@ static void field_cmd(const std::string& op, std::istringstream& in) {
     else if (op == "sqr") r = F::sqr(a);
     else if (op == "dbl") r = F::dbl(a);
     else if (op == "canon") { std::cout << (parse<F>(sa).is_canonical() ? 1 : 0) << "\n"; return; }
+    else if (op == "lz") {
+        // lazy-domain butterfly on RAW 256-bit values a, b in [0, 2m) and a canonical twiddle w: prints the raw results of
+        // add_lazy, sub_lazy, mul_lazy(sub_lazy_wide(a, b), w R) and reduce_lazy(add_lazy) -- the test checks ranges and residues
+        std::string sw;
+        in >> sb >> sw;
+        F x = parse<F>(sa), y = parse<F>(sb), w = F::to_mont(parse<F>(sw));
+        F s = F::add_lazy(x, y);
+        std::cout << hex(s) << " " << hex(F::sub_lazy(x, y)) << " " << hex(F::mul_lazy(F::sub_lazy_wide(x, y), w)) << " "
+                  << hex(F::reduce_lazy(s)) << "\n";
+        return;
+    }
     else {
         in >> sb;
         F b = F::to_mont(parse<F>(sb));
@@ -138,21 +149,18 @@ int main() {
                 xyzz_madd(u, a); xyzz_madd(u, b);
                 g1_print(xyzz_dbl(u));
             } else if (op == "coopdbl") {
-                // k doublings with the four-lane cooperative schedule, lanes emulated one after the other
+                // k doublings with the level schedule the MSM tail runs across the lanes of a warp (here: a plain loop per level)
                 int k; in >> k;
                 G1XYZZ u = G1XYZZ::inf();
                 G1Affine a = g1_parse(in), b = g1_parse(in);
                 xyzz_madd(u, a); xyzz_madd(u, b);
-                CoopDbl<Fq> st;
-                st.load(u);
-                for (int i = 0; i < k; i++) {
-                    for (int level = 0; level < 3; level++) {
-                        st.fix(level);
-                        for (int lane = 0; lane < 4; lane++) st.mul_level(level, lane);
-                    }
-                    st.fix(3);
-                }
-                g1_print(st.value());
+                for (int i = 0; i < k; i++) u = xyzz_dbl_levels(u, SerialMul4<Fq>());
+                g1_print(u);
+            } else if (op == "coopadd") {
+                G1XYZZ u = G1XYZZ::inf(), w = G1XYZZ::inf();
+                G1Affine a = g1_parse(in), b = g1_parse(in), c = g1_parse(in), d = g1_parse(in);
+                xyzz_madd(u, a); xyzz_madd(u, b); xyzz_madd(w, c); xyzz_madd(w, d);
+                g1_print(xyzz_add_levels(u, w, SerialMul4<Fq>()));
             }
         } else if (fld == "g2") {
             if (op == "chain") {
@@ -172,20 +180,18 @@ int main() {
                 xyzz_madd(u, a); xyzz_madd(u, b);
                 g2_print(xyzz_dbl(u));
             } else if (op == "coopdbl") {
+                // k doublings with the level schedule the MSM tail runs across the lanes of a warp (here: a plain loop per level)
                 int k; in >> k;
                 G2XYZZ u = G2XYZZ::inf();
                 G2Affine a = g2_parse(in), b = g2_parse(in);
                 xyzz_madd(u, a); xyzz_madd(u, b);
-                CoopDbl<Fq2> st;
-                st.load(u);
-                for (int i = 0; i < k; i++) {
-                    for (int level = 0; level < 3; level++) {
-                        st.fix(level);
-                        for (int lane = 0; lane < 4; lane++) st.mul_level(level, lane);
-                    }
-                    st.fix(3);
-                }
-                g2_print(st.value());
+                for (int i = 0; i < k; i++) u = xyzz_dbl_levels(u, SerialMul4<Fq2>());
+                g2_print(u);
+            } else if (op == "coopadd") {
+                G2XYZZ u = G2XYZZ::inf(), w = G2XYZZ::inf();
+                G2Affine a = g2_parse(in), b = g2_parse(in), c = g2_parse(in), d = g2_parse(in);
+                xyzz_madd(u, a); xyzz_madd(u, b); xyzz_madd(w, c); xyzz_madd(w, d);
+                g2_print(xyzz_add_levels(u, w, SerialMul4<Fq2>()));
             }
         } else {
             std::cout << "bad\n";

@@ -49,6 +49,26 @@ def test_field_ops(checker):
     assert checker(cmds) == exp
 
 
+def test_lazy_domain_butterfly(checker):
+    """The NTT butterflies keep values in [0, 2m): sums reduced against 2m, differences offset by 2m, and a Montgomery product
+    without its final subtraction (fp256.cuh, "lazy" domain).  Inputs cover the whole range including 2m - 1."""
+    rng = random.Random(11)
+    for name, m in (("fr", O.R), ("fq", O.P)):
+        edge = [0, 1, m - 1, m, m + 1, 2 * m - 1, 2 * m - 2]
+        vals = edge + [rng.randrange(2 * m) for _ in range(100)]
+        ws = [0, 1, m - 1] + [rng.randrange(m) for _ in range(20)]
+        cases = [(rng.choice(vals), rng.choice(vals), rng.choice(ws)) for _ in range(600)]
+        cases += [(2 * m - 1, 0, m - 1), (0, 2 * m - 1, m - 1), (2 * m - 1, 2 * m - 1, m - 1)]
+        out = checker([f"{name} lz {h(a)} {h(b)} {h(w)}" for a, b, w in cases])
+        for (a, b, w), line in zip(cases, out):
+            s, d, p, sr = (int(x, 16) for x in line.split())
+            assert s < 2 * m and s % m == (a + b) % m
+            assert d < 2 * m and d % m == (a - b) % m
+            assert p < 2 * m and p % m == (a - b) * w % m
+            assert sr == s % m or (sr < m and sr % m == s % m)
+            assert sr < m or s >= 2 * m
+
+
 def test_fq2_ops(checker):
     rng = random.Random(8)
     F = O.Fq2Field
@@ -118,12 +138,13 @@ def test_curve_ops(checker, gname):
         (pts[2], pts[3], inf, inf),
     ]
     for q in quads:
-        cmds.append(f"{gname} add " + " ".join(_fmt(G, _aff(G, p)) for p in q))
-        exp.append(_out(G, _aff(G, G.add(G.add(q[0], q[1]), G.add(q[2], q[3])))))
+        for op in ("add", "coopadd"):        # coopadd: the four-level schedule of the MSM tail (xyzz_add_levels), same special cases
+            cmds.append(f"{gname} {op} " + " ".join(_fmt(G, _aff(G, p)) for p in q))
+            exp.append(_out(G, _aff(G, G.add(G.add(q[0], q[1]), G.add(q[2], q[3])))))
     for a, b in ((pts[5], pts[6]), (pts[7], inf), (inf, inf)):
         cmds.append(f"{gname} dbl " + " ".join(_fmt(G, _aff(G, p)) for p in (a, b)))
         exp.append(_out(G, _aff(G, G.twice(G.add(a, b)))))
-    # the four-lane cooperative doubling schedule used by the MSM's window-combining Horner chain
+    # the three-level doubling schedule of the MSM tail (xyzz_dbl_levels)
     for k, (a, b) in ((1, (pts[5], pts[6])), (5, (pts[7], pts[8])), (3, (inf, inf)), (2, (pts[9], inf))):
         cmds.append(f"{gname} coopdbl {k} " + " ".join(_fmt(G, _aff(G, p)) for p in (a, b)))
         e = G.add(a, b)
