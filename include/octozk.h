@@ -181,7 +181,8 @@ OZK_API int ozk_msm_g1g2_dev(ozk_ctx* ctx, const void* d_scalars, const void* d_
  *                                      whole MSM (the Java's own 2^23-element chunk loop, VariableBaseMSM.java:211-265, maps
  *                                      onto feeds of one MSM too)
  *   ozk_msm_end(ctx, out)              bucket reduction + window recombination, result as for ozk_msm_*
- *   ozk_msm_plan_slices(n, bounds, cap) the slice schedule the whole-array entry points use: returns k <= cap and fills
+ *   ozk_msm_plan_slices(n, bounds, cap) the slice schedule the whole-array entry points use for pageable host memory (a small
+ *                                      first and last slice: the call is bound by the copies): returns k <= cap and fills
  *                                      bounds[0..k] (bounds[0] = 0, bounds[k] = n)
  * Unreduced inputs are reported by ozk_msm_end.  One MSM in progress per context. */
 OZK_API int ozk_msm_begin(ozk_ctx* ctx, int groups, size_t n_total, size_t max_slice, const ozk_bases* key1, const ozk_bases* key2,

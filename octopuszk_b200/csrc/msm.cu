@@ -311,6 +311,19 @@ static MsmShape msm_shape(size_t n) { return msm_shape(n, n); }
 
 // buffers in ctx->msm[]
 enum { B_AFF1 = 0, B_AFF2, B_COUNT, B_START, B_CURSOR, B_SORTED, B_BUCKETS, B_OVFTASK, B_OVFBUCKET, B_OVFPART, B_SCRATCH, B_MISC, B_ORDER, B_BUCKETS2, B_PAIR0, B_PAIR1 };
+// Which accumulate kernel runs (msm_impl.cuh): bit 0 = G1, bit 1 = G2 use the shared-memory-resident one.  Default: G2 only.
+// Measured at 2^24 (profiles/r2_sweep_g2_called_products.jsonl, r2_sweep_smem_accumulate_experiment.jsonl), accumulate ms:
+//   G2  register-resident, products inlined, 2 CTAs per SM (round 1)   134.0
+//       products called                                                120.3
+//       products called, 168-register cap for 3 CTAs (516 B of spills) 116.8
+//       products called + accumulator in shared memory, 3 CTAs         113.1   <- default
+//   G1  register-resident, 4 CTAs per SM                                37.5   <- default
+//       accumulator in shared memory, 5 CTAs                            37.3   (within noise; not worth a second code path)
+bool msm_use_smem_accumulate(bool g2) {
+    const char* e = getenv("OZK_MSM_SMEM");       // read on every call: the parity test switches it inside one process
+    const int mask = e ? atoi(e) : 2;
+    return (mask >> (g2 ? 1 : 0)) & 1;
+}
 static constexpr int kMiscOhist = 64, kMiscOcursor = 2048, kMiscWords = 4096;   // word offsets inside B_MISC
 
 // sort phase shared by G1 / G2 / paired calls: fills start/count/sorted and the overflow lists
@@ -681,16 +694,18 @@ static int msm_stream_end(ozk_ctx* ctx, uint8_t* out) {
     return msm_finish(ctx, d_res, bytes, out);
 }
 
-// Slice schedule of a whole-array call.  The compute of a slice starts when its copy has landed, copies run back to back at the
-// PCIe rate, and on one GPU the compute (2.8 ns per G1 pair) is slower than the copy (2.3 ns per pair of 128 bytes), so the
-// schedule wants (i) a small first slice -- the GPU idles while it crosses -- (ii) growth slow enough that copy k+1 always
-// lands before compute k ends: f_k <= f_0 + (t_gpu / t_copy - 1) F_{k-1} + k B / T_copy with B ~ 0.4 ms of fixed cost per slice
-// (bucket set-up of the shared buckets, the sort's small launches), and (iii) a small LAST slice, because when the host link is
-// the bottleneck (several GPUs behind one PCIe switch) the step ends one last-slice compute after the last byte arrives.
-// Round 1 grew the slices geometrically (x1.3: the copy of slice k+1 then takes 1.08x the compute of slice k, the GPU waits a
-// little on every slice, and the step ends a 26 % slice after the copy): 54.7 ms at 2^24; OZK_HOST_SLICE_GROWTH=g restores it.
+// Slice schedule of a whole-array call.  The compute of a slice starts when its copy has landed and the copies run back to
+// back, so a step ends at max(first copy + all compute + per-slice overheads, all copies + compute of the LAST slice).  Every
+// slice costs ~0.5 ms of fixed work (each accumulate launch reloads and stores all buckets and starts every run cold).
+//  * pinned memory on one GPU: copy 2.3 ns per 128-byte pair, compute 2.8 ns -- both ends bind at once.  Eight slices growing
+//    x1.3 measured best (profiles/r2_e2e_slice_plans.jsonl: 53.7 ms at 2^24; equal slices 56.3, x1.2 54.6, x1.5 57.8, six or
+//    twelve slices 54.4, a schedule with small first AND last slices 55.0 -- it is then bound by the per-slice overheads).
+//  * pageable memory (what the JNI shims pass; it crosses through the bounce-buffer stager at ~25 GB/s) is bound by the copies,
+//    and the step ends one last-slice compute after the last byte: there the schedule with a small last slice wins
+//    (2^23 pairs through the legacy JNI symbol: 37.7 ms against 43-50 ms).
+// OZK_HOST_SLICES / OZK_HOST_SLICE_GROWTH / OZK_HOST_PLAN override (tools/e2e_plan_sweep.py).
 static constexpr int kMaxSlices = 16;
-static int msm_plan_slices(size_t n, size_t* bounds, int cap) {
+static int msm_plan_slices(size_t n, size_t* bounds, int cap, bool copy_bound) {
     static const double plan8[8] = {0.04, 0.07, 0.11, 0.15, 0.19, 0.20, 0.16, 0.08};
     static const double plan4[4] = {0.10, 0.27, 0.38, 0.25};
     static const double plan2[2] = {0.35, 0.65};
@@ -706,7 +721,30 @@ static int msm_plan_slices(size_t n, size_t* bounds, int cap) {
     if (const char* e = getenv("OZK_HOST_SLICE_GROWTH")) growth = std::max(1.0, atof(e));
     nslices = std::min(nslices, cap);
     double frac[kMaxSlices];
-    const double* tab = nslices == 8 ? plan8 : nslices == 4 ? plan4 : nslices == 2 ? plan2 : nullptr;
+    if (const char* e = getenv("OZK_HOST_PLAN")) {
+        // explicit fractions "0.05,0.1,..." (normalised to 1): the tuning knob tools/e2e_plan_sweep.py turns
+        int k = 0;
+        double total = 0;
+        for (const char* q = e; *q && k < std::min(cap, kMaxSlices);) {
+            char* end = nullptr;
+            const double v = strtod(q, &end);
+            if (end == q) break;
+            if (v > 0) { frac[k++] = v; total += v; }
+            q = (*end == ',') ? end + 1 : end;
+        }
+        if (k > 0 && n >= ((size_t)1 << 18)) {
+            double acc = 0;
+            bounds[0] = 0;
+            for (int i = 0; i < k; i++) {
+                acc += frac[i] / total;
+                size_t b = ((size_t)((double)n * acc) + 255) & ~(size_t)255;
+                bounds[i + 1] = (i + 1 == k) ? n : std::min(b, n);
+                if (bounds[i + 1] < bounds[i]) bounds[i + 1] = bounds[i];
+            }
+            return k;
+        }
+    }
+    const double* tab = !copy_bound ? nullptr : nslices == 8 ? plan8 : nslices == 4 ? plan4 : nslices == 2 ? plan2 : nullptr;
     if (growth == 0 && tab) {
         for (int k = 0; k < nslices; k++) frac[k] = tab[k];
     } else {
@@ -731,7 +769,7 @@ static int msm_plan_slices(size_t n, size_t* bounds, int cap) {
 static int msm_run_host(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* b1, const uint8_t* b2, BaseSrc s1, BaseSrc s2, size_t n, uint8_t* out) {
     OZK_ARG(n > 0 && n < ((size_t)1 << 31), "msm: between 1 and 2^31 - 1 points per call");
     size_t bounds[kMaxSlices + 1];
-    const int nslices = msm_plan_slices(n, bounds, kMaxSlices);
+    const int nslices = msm_plan_slices(n, bounds, kMaxSlices, host_pointer_is_pageable(b1 ? b1 : b2 ? b2 : scalars));
     size_t slice = 0;                                    // the longest slice sizes the per-slice scratch
     for (int k = 0; k < nslices; k++) slice = std::max(slice, bounds[k + 1] - bounds[k]);
     OZK_TRY(msm_stream_begin(ctx, b1 || s1.any(), b2 || s2.any(), n, slice, s1.affine, s2.affine));
@@ -876,7 +914,7 @@ int ozk_msm_end(ozk_ctx* ctx, uint8_t* out) {
 int ozk_msm_plan_slices(size_t n, size_t* bounds, int cap) {
     if (!bounds || cap < 1) return 0;
     if (n == 0) { bounds[0] = 0; return 0; }
-    return msm_plan_slices(n, bounds, std::min(cap, kCopyChunks));
+    return msm_plan_slices(n, bounds, std::min(cap, kCopyChunks), true);     // callers that feed slices themselves hold pageable (JVM heap) arrays
 }
 
 int ozk_bases_upload_g1(ozk_ctx* ctx, const uint8_t* bases, size_t n, ozk_bases** out) {

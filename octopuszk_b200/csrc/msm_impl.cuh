@@ -13,6 +13,8 @@
 //   tail     : per-window recombination of the levels and Horner over the windows, every doubling / addition spread over
 //              the lanes of a warp (level schedules of curve.cuh); conversion to the canonical Jacobian wire format
 #pragma once
+#include <cstdlib>
+
 #include "curve.cuh"
 
 namespace ozk {
@@ -96,16 +98,43 @@ template <class F> __device__ __noinline__ void xyzz_dbl_ni(XYZZ<F>& p) { p = xy
 template <class F> __device__ __noinline__ void xyzz_dbl_affine_ni(XYZZ<F>& acc, const Affine<F>& q) { acc = xyzz_dbl_affine(q); }
 template <class F> __device__ __noinline__ F field_inv_ni(const F& a) { return F::inv(a); }
 
+// Products of the hot loop: inlined for Fq; for Fq2 (CALLS) one called copy of the product / square each (operands and result
+// travel in registers).  The inlined G2 loop body is ~128 KB of code against a 32 KB L1.5 instruction cache, and with only two
+// warps per scheduler (242 registers) 18 % of the warp samples of msm_accumulate<Fq2> were "no instruction" stalls at 66 % pipe
+// utilisation (profiles/r2_ncu_full_msm_accumulate_g2.txt).  An Fq2 product is ~700 instructions with three independent
+// carry-chain streams inside, so nothing is lost by not interleaving it with its neighbours -- unlike the 183-instruction Fr
+// product of the NTT butterflies, where the same change cost 14 % (ntt.cu).  OZK_MSM_G2_INLINE=1 runs the inlined kernel.
+template <class F, bool CALLS>
+struct HotOps {
+    __device__ __forceinline__ static F mul(const F& a, const F& b) { return F::mul(a, b); }
+    __device__ __forceinline__ static F sqr(const F& a) { return F::sqr(a); }
+    __device__ __forceinline__ static F mul_sub(const F& a, const F& b, const F& c, const F& d) { return F::mul_sub(a, b, c, d); }
+};
+static __device__ __noinline__ Fq2 fq2_mul_ni(Fq2 a, Fq2 b) { return Fq2::mul(a, b); }
+static __device__ __noinline__ Fq2 fq2_sqr_ni(Fq2 a) { return Fq2::sqr(a); }
+template <>
+struct HotOps<Fq2, true> {
+    __device__ __forceinline__ static Fq2 mul(const Fq2& a, const Fq2& b) { return fq2_mul_ni(a, b); }
+    __device__ __forceinline__ static Fq2 sqr(const Fq2& a) { return fq2_sqr_ni(a); }
+    __device__ __forceinline__ static Fq2 mul_sub(const Fq2& a, const Fq2& b, const Fq2& c, const Fq2& d) {
+        return Fq2::sub(fq2_mul_ni(a, b), fq2_mul_ni(c, d));
+    }
+};
+
+// default: inlined products for Fq, called ones for Fq2 (G2 accumulate 2^24: 134.0 -> 120.3 ms, profiles/r2_sweep_g2_called_products.jsonl)
+template <class F> struct HotCallsDefault { static constexpr bool value = sizeof(F) != 32; };
+
 // mixed add for the hot loop: the common path is inline, the doubling special case is a call
-template <class F>
+template <class F, bool CALLS = HotCallsDefault<F>::value>
 __device__ __forceinline__ void xyzz_madd_hot(XYZZ<F>& acc, const Affine<F>& q) {
+    using H = HotOps<F, CALLS>;
     if (q.is_inf()) return;
     if (acc.is_inf()) {
         acc = {q.x, q.y, F::one(), F::one()};
         return;
     }
-    F U2 = F::mul(q.x, acc.zz);
-    F S2 = F::mul(q.y, acc.zzz);
+    F U2 = H::mul(q.x, acc.zz);
+    F S2 = H::mul(q.y, acc.zzz);
     F Pp = F::sub(U2, acc.x);
     F Rr = F::sub(S2, acc.y);
     if (Pp.is_zero()) {
@@ -113,14 +142,14 @@ __device__ __forceinline__ void xyzz_madd_hot(XYZZ<F>& acc, const Affine<F>& q) 
         else acc = XYZZ<F>::inf();
         return;
     }
-    F PP = F::sqr(Pp);
-    F PPP = F::mul(Pp, PP);
-    F Q = F::mul(acc.x, PP);
-    F X3 = F::sub(F::sub(F::sqr(Rr), PPP), F::dbl(Q));
-    acc.y = F::mul_sub(Rr, F::sub(Q, X3), acc.y, PPP);       // one reduction for both products (lazy)
+    F PP = H::sqr(Pp);
+    F PPP = H::mul(Pp, PP);
+    F Q = H::mul(acc.x, PP);
+    F X3 = F::sub(F::sub(H::sqr(Rr), PPP), F::dbl(Q));
+    acc.y = H::mul_sub(Rr, F::sub(Q, X3), acc.y, PPP);       // one reduction for both products (lazy)
     acc.x = X3;
-    acc.zz = F::mul(acc.zz, PP);
-    acc.zzz = F::mul(acc.zzz, PPP);
+    acc.zz = H::mul(acc.zz, PP);
+    acc.zzz = H::mul(acc.zzz, PPP);
 }
 
 __device__ __forceinline__ Fq canon_one(Fq*) {
@@ -197,8 +226,8 @@ __global__ void __launch_bounds__(128) msm_convert_bases(const uint4* __restrict
 // task t >= nbuckets_total: overflow task (bucket, seg), entries [seg*seg_len, ...)     -> ovf_partial[t - nbuckets_total]
 // sorted[w * n + pos] = point index | sign << 31 ; start/count are per (window, bucket), start is window-local.
 // G1: four 128-thread CTAs per SM (<= 128 registers per thread); G2 needs ~240 registers and runs two.
-template <class F>
-__global__ void __launch_bounds__(128, sizeof(F) == 32 ? 4 : 1) msm_accumulate(const uint4* __restrict__ bases, const uint32_t* __restrict__ sorted,
+template <class F, bool CALLS = HotCallsDefault<F>::value, int MINB = (sizeof(F) == 32 ? 4 : 1)>
+__global__ void __launch_bounds__(128, MINB) msm_accumulate(const uint4* __restrict__ bases, const uint32_t* __restrict__ sorted,
                                                       const uint32_t* __restrict__ start, const uint32_t* __restrict__ count,
                                                       const OvfTask* __restrict__ ovf_tasks, const uint32_t* __restrict__ ovf_count,
                                                       const uint32_t* __restrict__ order,
@@ -235,13 +264,159 @@ __global__ void __launch_bounds__(128, sizeof(F) == 32 ? 4 : 1) msm_accumulate(c
                 p_next = load_affine<F>(bases, e_next & 0x7fffffffu);
             }
             if (e >> 31) p.y = F::neg(p.y);
-            xyzz_madd_hot(acc, p);
+            xyzz_madd_hot<F, CALLS>(acc, p);
             e = e_next;
             p = p_next;
         }
     }
     if (t < nbuckets_total) store_xyzz<F>(buckets, bucket, acc);
     else store_xyzz<F>(ovf_partial, t - nbuckets_total, acc);
+}
+
+// ---- accumulate, shared-memory-resident variant -----------------------------------------------------------------------
+// The same tasks as msm_accumulate, but the accumulator and the prefetched next point live in shared memory (one column per
+// thread of a [row][thread] array of 16-byte words: conflict-free), so a thread needs registers only for the values in flight
+// inside one addition.  That buys a fifth resident CTA per SM for G1 (96 instead of 128 registers) and a third for G2 (168
+// instead of 242, where the register-resident kernel runs two warps per scheduler).  The next point arrives by cp.async
+// straight into the thread's column, so the prefetch holds no registers either.  Selected by OZK_MSM_SMEM (msm.cu).
+template <class F> struct SmIO;
+template <> struct SmIO<Fq> {
+    __device__ __forceinline__ static Fq ld(const uint4* row) {
+        const uint4 a = row[0], b = row[128];
+        Fq r;
+        r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+        r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+        return r;
+    }
+    __device__ __forceinline__ static void st(uint4* row, const Fq& r) {
+        row[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+        row[128] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+    }
+};
+template <> struct SmIO<Fq2> {
+    __device__ __forceinline__ static Fq2 ld(const uint4* row) { return {SmIO<Fq>::ld(row), SmIO<Fq>::ld(row + 2 * 128)}; }
+    __device__ __forceinline__ static void st(uint4* row, const Fq2& r) {
+        SmIO<Fq>::st(row, r.c0);
+        SmIO<Fq>::st(row + 2 * 128, r.c1);
+    }
+};
+// element `slot` of a thread's column (slot s occupies rows s*U .. s*U + U - 1)
+template <class F> __device__ __forceinline__ F sm_ld(const uint4* col, int slot) { return SmIO<F>::ld(col + slot * FieldIO<F>::kU4 * 128); }
+template <class F> __device__ __forceinline__ void sm_st(uint4* col, int slot, const F& v) { SmIO<F>::st(col + slot * FieldIO<F>::kU4 * 128, v); }
+
+__device__ __forceinline__ void cp_async16_g2s(void* smem_dst, const void* gmem_src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
+}
+
+// acc (slots 0..3 = x, y, zz, zzz of the column; infinity iff zz == 0) += p, same formulas and special cases as xyzz_madd_hot
+template <class F>
+__device__ __forceinline__ void xyzz_madd_sm(uint4* acc, const Affine<F>& p) {
+    using H = HotOps<F, HotCallsDefault<F>::value>;
+    if (p.is_inf()) return;
+    const F zz = sm_ld<F>(acc, 2);
+    if (zz.is_zero()) {
+        sm_st<F>(acc, 0, p.x);
+        sm_st<F>(acc, 1, p.y);
+        sm_st<F>(acc, 2, F::one());
+        sm_st<F>(acc, 3, F::one());
+        return;
+    }
+    const F Pp = F::sub(H::mul(p.x, zz), sm_ld<F>(acc, 0));
+    const F Rr = F::sub(H::mul(p.y, sm_ld<F>(acc, 3)), sm_ld<F>(acc, 1));
+    if (Pp.is_zero()) {
+        if (Rr.is_zero()) {
+            XYZZ<F> d;
+            xyzz_dbl_affine_ni(d, p);
+            sm_st<F>(acc, 0, d.x);
+            sm_st<F>(acc, 1, d.y);
+            sm_st<F>(acc, 2, d.zz);
+            sm_st<F>(acc, 3, d.zzz);
+        } else {
+            sm_st<F>(acc, 2, F::zero());
+        }
+        return;
+    }
+    const F PP = H::sqr(Pp);
+    sm_st<F>(acc, 2, H::mul(sm_ld<F>(acc, 2), PP));
+    const F PPP = H::mul(Pp, PP);
+    const F Q = H::mul(sm_ld<F>(acc, 0), PP);
+    sm_st<F>(acc, 3, H::mul(sm_ld<F>(acc, 3), PPP));
+    const F X3 = F::sub(F::sub(H::sqr(Rr), PPP), F::dbl(Q));
+    sm_st<F>(acc, 0, X3);
+    sm_st<F>(acc, 1, H::mul_sub(Rr, F::sub(Q, X3), sm_ld<F>(acc, 1), PPP));
+}
+
+template <class F>
+__global__ void __launch_bounds__(128, sizeof(F) == 32 ? 5 : 3) msm_accumulate_sm(const uint4* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                                                      const uint32_t* __restrict__ start, const uint32_t* __restrict__ count,
+                                                      const OvfTask* __restrict__ ovf_tasks, const uint32_t* __restrict__ ovf_count,
+                                                      const uint32_t* __restrict__ order,
+                                                      uint32_t nbuckets_total, uint32_t log_nb, size_t n, uint32_t seg_len,
+                                                      uint32_t resume, uint4* __restrict__ buckets, uint4* __restrict__ ovf_partial) {
+    extern __shared__ uint4 sm_acc[];
+    constexpr int U = FieldIO<F>::kU4;
+    uint4* acc = sm_acc + threadIdx.x;                       // rows 0 .. 4U-1
+    uint4* pbuf = sm_acc + 4 * U * 128 + threadIdx.x;        // two point buffers of 2U rows each
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t bucket, seg;
+    if (t < nbuckets_total) {
+        bucket = order[t];
+        seg = 0;
+    } else {
+        const uint32_t k = t - nbuckets_total;
+        if (k >= *ovf_count) return;
+        bucket = ovf_tasks[k].bucket;
+        seg = ovf_tasks[k].seg;
+    }
+    const uint32_t cnt = count[bucket];
+    const uint32_t w = bucket >> log_nb;
+    const uint32_t lo = seg * seg_len;
+    const uint32_t hi = min(cnt, lo + seg_len);
+    const uint32_t* run = sorted + (size_t)w * n + start[bucket];
+    if (resume && t < nbuckets_total) {
+        const XYZZ<F> b = load_xyzz<F>(buckets, bucket);
+        sm_st<F>(acc, 0, b.x);
+        sm_st<F>(acc, 1, b.y);
+        sm_st<F>(acc, 2, b.zz);
+        sm_st<F>(acc, 3, b.zzz);
+    } else {
+        sm_st<F>(acc, 2, F::zero());
+    }
+    if (lo < hi) {
+        uint32_t e = run[lo];
+        {
+            const uint4* src = bases + (size_t)(e & 0x7fffffffu) * (2 * U);
+#pragma unroll
+            for (int k = 0; k < 2 * U; k++) cp_async16_g2s(pbuf + k * 128, src + k);
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+        }
+        for (uint32_t j = lo; j < hi; j++) {
+            uint4* cur = pbuf + ((j - lo) & 1) * (2 * U * 128);
+            uint32_t e_next = 0;
+            if (j + 1 < hi) {
+                e_next = run[j + 1];
+                uint4* nxt = pbuf + ((j + 1 - lo) & 1) * (2 * U * 128);
+                const uint4* src = bases + (size_t)(e_next & 0x7fffffffu) * (2 * U);
+#pragma unroll
+                for (int k = 0; k < 2 * U; k++) cp_async16_g2s(nxt + k * 128, src + k);
+                asm volatile("cp.async.commit_group;\ncp.async.wait_group 1;\n" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+            }
+            Affine<F> p = {sm_ld<F>(cur, 0), sm_ld<F>(cur, 1)};
+            if (e >> 31) p.y = F::neg(p.y);
+            xyzz_madd_sm<F>(acc, p);
+            e = e_next;
+        }
+    }
+    XYZZ<F> r = XYZZ<F>::inf();
+    {
+        const F zz = sm_ld<F>(acc, 2);
+        if (!zz.is_zero()) r = {sm_ld<F>(acc, 0), sm_ld<F>(acc, 1), zz, sm_ld<F>(acc, 3)};
+    }
+    if (t < nbuckets_total) store_xyzz<F>(buckets, bucket, r);
+    else store_xyzz<F>(ovf_partial, t - nbuckets_total, r);
 }
 
 // buckets[b] += sum of the overflow partials of bucket b.  Two launches over the overflow-bucket list:
@@ -490,6 +665,8 @@ struct MsmLaunch {
 
 extern const MsmLaunch kMsmG1;
 extern const MsmLaunch kMsmG2;
+// which accumulate kernel runs (msm.cu: OZK_MSM_SMEM bit 0 = G1, bit 1 = G2)
+bool msm_use_smem_accumulate(bool g2);
 
 #define OZK_DEFINE_MSM_LAUNCH(F, NAME)                                                                                         \
     static int NAME##_convert(cudaStream_t s, const void* in, void* out, size_t n, uint32_t* flag, int sm_count) {             \
@@ -507,6 +684,29 @@ extern const MsmLaunch kMsmG2;
                                  void* buckets, void* ovf_partial) {                                                           \
         size_t total = (size_t)nbt + ovf_cap;                                                                                  \
         unsigned grid = (unsigned)((total + 127) / 128);                                                                       \
+        if (msm_use_smem_accumulate(sizeof(F) != 32)) {                                                                        \
+            const size_t smem = (size_t)8 * FieldIO<F>::kU4 * 128 * 16;                                                        \
+            static bool attr_done = false;                                                                                     \
+            if (!attr_done) {                                                                                                  \
+                if (cudaFuncSetAttribute(msm_accumulate_sm<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1; \
+                attr_done = true;                                                                                              \
+            }                                                                                                                  \
+            msm_accumulate_sm<F><<<grid, 128, smem, s>>>((const uint4*)bases, sorted, start, count, tasks, ovf_count, order, nbt, log_nb, n, \
+                                                         seg_len, resume, (uint4*)buckets, (uint4*)ovf_partial);                       \
+            return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                                 \
+        }                                                                                                                      \
+        if constexpr (sizeof(F) != 32) {                                                                                       \
+            if (getenv("OZK_MSM_G2_INLINE")) {                                                                                 \
+                msm_accumulate<F, false><<<grid, 128, 0, s>>>((const uint4*)bases, sorted, start, count, tasks, ovf_count, order, nbt, log_nb, n, \
+                                                              seg_len, resume, (uint4*)buckets, (uint4*)ovf_partial);                  \
+                return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                             \
+            }                                                                                                                  \
+            if (getenv("OZK_MSM_G2_3CTA")) {                                                                                   \
+                msm_accumulate<F, true, 3><<<grid, 128, 0, s>>>((const uint4*)bases, sorted, start, count, tasks, ovf_count, order, nbt, log_nb, \
+                                                                n, seg_len, resume, (uint4*)buckets, (uint4*)ovf_partial);             \
+                return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                             \
+            }                                                                                                                  \
+        }                                                                                                                      \
         msm_accumulate<F><<<grid, 128, 0, s>>>((const uint4*)bases, sorted, start, count, tasks, ovf_count, order, nbt, log_nb, n, seg_len, \
                                                resume, (uint4*)buckets, (uint4*)ovf_partial);                                          \
         return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                                     \

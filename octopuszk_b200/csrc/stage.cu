@@ -15,8 +15,9 @@
 namespace ozk {
 
 struct Stager {
-    static constexpr int kThreads = 4;
+    static constexpr int kThreads = 8;          // upper bound; `active` of them are used (OZK_STAGE_THREADS, default 4)
     static constexpr int kBufs = 2;
+    int active = 4;
     static constexpr size_t kChunk = (size_t)4 << 20;
     void* pinned[kThreads][kBufs] = {};
     cudaStream_t st[kThreads] = {};
@@ -50,7 +51,8 @@ static int stager_get(ozk_ctx* ctx, Stager** out) {
     if (ctx->stager) stager_free(ctx);              // a half-built one left behind by an earlier failure
     Stager* s = new Stager();
     ctx->stager = s;
-    for (int t = 0; t < Stager::kThreads; t++) {
+    if (const char* e = getenv("OZK_STAGE_THREADS")) s->active = std::max(1, std::min((int)Stager::kThreads, atoi(e)));
+    for (int t = 0; t < s->active; t++) {
         OZK_CUDA(cudaStreamCreateWithFlags(&s->st[t], cudaStreamNonBlocking));
         OZK_CUDA(cudaEventCreateWithFlags(&s->done[t], cudaEventDisableTiming));
         for (int b = 0; b < Stager::kBufs; b++) {
@@ -102,7 +104,7 @@ int staged_h2d(ozk_ctx* ctx, void* dst, const void* src, size_t bytes, cudaEvent
     Stager* s;
     OZK_TRY(stager_get(ctx, &s));
     const size_t nchunks = (bytes + Stager::kChunk - 1) / Stager::kChunk;
-    const int nthreads = (int)std::min<size_t>(Stager::kThreads, nchunks);
+    const int nthreads = (int)std::min<size_t>((size_t)s->active, nchunks);
     cudaError_t err[Stager::kThreads];
     auto work = [&](int t) {
         cudaError_t e = cudaSetDevice(ctx->device);
@@ -139,7 +141,7 @@ int staged_d2h(ozk_ctx* ctx, void* dst, const void* src, size_t bytes, cudaEvent
     Stager* s;
     OZK_TRY(stager_get(ctx, &s));
     const size_t nchunks = (bytes + Stager::kChunk - 1) / Stager::kChunk;
-    const int nthreads = (int)std::min<size_t>(Stager::kThreads, nchunks);
+    const int nthreads = (int)std::min<size_t>((size_t)s->active, nchunks);
     cudaError_t err[Stager::kThreads];
     auto work = [&](int t) {
         cudaError_t e = cudaSetDevice(ctx->device);

@@ -396,3 +396,49 @@ def test_batch_affine_rounds_match_oracle(ctx, rounds, monkeypatch):
     sums = util.column_sums(rw, 64)
     assert O.G1.equals(O.unpack_g1(out[:96])[0], util.expected_from_dlogs(O.G1, k1, sums))
     assert O.G2.equals(O.unpack_g2(out[96:])[0], util.expected_from_dlogs(O.G2, k2, sums))
+
+
+# ---- shared-memory-resident accumulate kernel (csrc/msm_impl.cuh, msm_accumulate_sm), forced on through OZK_MSM_SMEM --------
+@pytest.mark.parametrize("gname,mask", [("G1", "3"), ("G2", "3"), ("G2", "0")])
+def test_smem_accumulate_matches_oracle(ctx, gname, mask, monkeypatch):
+    """Both accumulate kernels of both groups, whatever the default is (G1: registers, G2: shared memory; mask "3" forces the
+    shared-memory kernel, "0" the register-resident one).
+    The accumulate variant that keeps the bucket accumulator and the prefetched point in shared memory gives the same sums:
+    small inputs with every special case of the mixed addition (infinity bases, P with -P, the same point repeatedly = the
+    doubling branch, zero / one / r-1 scalars), the profiler's identical-bases input (dense buckets, overflow tasks), distinct
+    bases at 2^16, and host slices that resume the shared buckets."""
+    import torch
+    monkeypatch.setenv("OZK_MSM_SMEM", mask)
+    G = O.G1 if gname == "G1" else O.G2
+    rng = random.Random(77)
+    for n in (1, 2, 17, 100, 1023 if G is O.G1 else 257):
+        ks, pool = util.known_dlog_points(G, min(n, 12), seed=n, random_z=True)
+        bases = [pool[rng.randrange(len(pool))] for _ in range(n)]
+        scalars = [rng.randrange(O.R) for _ in range(n)]
+        if n >= 17:
+            bases[0] = G.zero()
+            bases[1] = (pool[0][0], pool[0][1], G.F.zero)
+            scalars[2], scalars[3], scalars[4] = 0, 1, O.R - 1
+            bases[5], bases[6] = pool[1], G.negate(pool[1])
+            scalars[5] = scalars[6] = rng.randrange(O.R)
+            bases[7] = bases[8] = bases[9] = pool[2]
+            scalars[7] = scalars[8] = scalars[9] = 12345
+        assert G.equals(_run(ctx, G, scalars, bases), O.pippenger_msm(G, scalars, bases)), (gname, n)
+    # N copies of one base, scalars Fr(random long): one bucket per high window holds N/2 points, every addition is a doubling
+    n = 1 << 14
+    jr = O.JavaRandom(10)
+    g = G.random(10)
+    scalars = [jr.next_long() % O.R for _ in range(n)]
+    assert G.equals(_run(ctx, G, scalars, [g] * n), G.mul(g, sum(scalars) % O.R))
+    # distinct bases k_i G, scalars uniform in [0, r), device-resident and through host slices (resume of the shared buckets)
+    log_n = 16 if G is O.G1 else 14
+    n = 1 << log_n
+    d_b, ksv = util.gpu_distinct_bases(ctx, G, n, seed=5, keep_z=True, verify=2)
+    raw = util.force_edge_scalars(util.rand_scalars_full_range(n, seed=6))
+    exp = util.expected_from_dot(G, raw, ksv)
+    fn = ctx.msm_g1_dev if G is O.G1 else ctx.msm_g2_dev
+    assert G.equals(util.unpack_point(G, fn(torch.from_numpy(raw).cuda(), d_b, n)), exp)
+    monkeypatch.setenv("OZK_HOST_SLICES", "3")
+    hb = d_b.cpu().numpy()
+    out = ctx.msm_g1(raw, hb, n) if G is O.G1 else ctx.msm_g2(raw, hb, n)
+    assert G.equals(util.unpack_point(G, out), exp)

@@ -100,7 +100,7 @@ if "cfg1" in what:
     # the MSM sizes of BASELINE.json configs[0] (2^15 constraints, 1023 inputs: SURVEY.md section 8 a1)
     msm_sweep(O.G1, [1023, 31748, 65537], "varmsm_g1_cfg1")
 if "msm2" in what:
-    msm_sweep(O.G2, [1 << k for k in (16, 18, 20, 22, 24)], "varmsm_g2")
+    msm_sweep(O.G2, [1 << int(x) for x in os.environ.get("OZK_SWEEP_LOGS2", "16,18,20,22,24").split(",")], "varmsm_g2")
 if "ntt" in what or "ntt26" in what:
     ntt_logs = [int(x) for x in os.environ.get("OZK_SWEEP_NTT_LOGS", "16,18,20,22,24,26,28").split(",")]
     for log_n in ([26] if "ntt26" in what else ntt_logs):
