@@ -186,6 +186,11 @@ int ozk_ctx_create(int device, ozk_ctx** out) {
         OZK_CUDA(cudaEventCreate(&c->ev1));
         for (auto& e : c->evs) OZK_CUDA(cudaEventCreate(&e));
         OZK_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        {
+            int lo_prio = 0, hi_prio = 0;
+            OZK_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+            OZK_CUDA(cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, hi_prio));
+        }
         for (auto& e : c->copy_ev) OZK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         OZK_CUDA(cudaMallocHost(&c->pinned, 4096));
         return OZK_OK;
@@ -216,6 +221,7 @@ void ozk_ctx_destroy(ozk_ctx* c) {
     for (auto& e : c->evs) if (e) cudaEventDestroy(e);
     for (auto& e : c->copy_ev) if (e) cudaEventDestroy(e);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    if (c->side_stream) { cudaStreamSynchronize(c->side_stream); cudaStreamDestroy(c->side_stream); }
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }

@@ -79,6 +79,8 @@ struct ozk_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaStream_t copy_stream = nullptr;        // second stream for chunked host->device uploads (host-pointer MSM entry)
     cudaEvent_t copy_ev[20] = {};
+    cudaStream_t side_stream = nullptr;        // high-priority side stream: the normalisation of a slice's bases runs here while the
+    int conv_forked = 0;                       // same slice is sorted on the main stream (msm.cu, msm_convert_fork; bit g = group g forked)
     cudaEvent_t evs[8] = {};                   // phase marks of the last MSM (see ozk_msm_last_stats)
     unsigned long long launches = 0;           // kernels launched through this context
     // scratch

@@ -377,6 +377,31 @@ struct BaseSrc {
     bool any() const { return wire || affine; }
 };
 
+// The normalisation of a slice's bases (wire Jacobian -> affine Montgomery: integer-pipe bound, 1.0 ms per 2^24 points with
+// Z = 1 and 3.7 ms with a Z per point) needs only the bases, the sort of the same slice (L2-atomic bound, 5.9 ms) only the scalars:
+// the conversion is forked onto a high-priority side stream BEFORE the sort is enqueued and joined before the accumulate.
+// The fork event sits behind everything already on the main stream, so the conversion cannot overwrite the affine buffer while
+// the previous slice's accumulate still reads it.  OZK_MSM_CONVERT_FORK=0 keeps everything on one stream.
+static int msm_convert_fork(ozk_ctx* ctx, const MsmLaunch& L, const BaseSrc& src, size_t n, int aff_slot, int group_bit) {
+    if (!src.wire) return OZK_OK;
+    if (const char* e = getenv("OZK_MSM_CONVERT_FORK")) {
+        if (atoi(e) == 0) return OZK_OK;
+    }
+    cudaStream_t st = ctx->stream, side = ctx->side_stream;
+    if (ctx->msm[aff_slot].bytes < n * L.affine_bytes) OZK_CUDA(cudaStreamSynchronize(side));   // a regrow frees the buffer: nothing may be in flight on it
+    OZK_TRY(ctx->msm[aff_slot].reserve(n * L.affine_bytes, st));
+    cudaEvent_t fork = ctx->copy_ev[kCopyChunks], join = ctx->copy_ev[kCopyChunks + 1 + group_bit];
+    if (!(ctx->conv_forked)) {
+        OZK_CUDA(cudaEventRecord(fork, st));
+        OZK_CUDA(cudaStreamWaitEvent(side, fork, 0));
+    }
+    if (L.convert(side, src.wire, ctx->msm[aff_slot].p, n, (uint32_t*)ctx->msm[B_MISC].p, ctx->sm_count)) { set_error("msm: convert launch failed"); return OZK_ERR_CUDA; }
+    OZK_CUDA(cudaEventRecord(join, side));
+    ctx->launches += 1;
+    ctx->conv_forked |= 1 << group_bit;
+    return OZK_OK;
+}
+
 // bucket phase, part 1: convert `n` bases and add them into the buckets of their digits.  resume == false starts from empty
 // buckets; resume == true adds to what earlier slices of the same MSM left there (same shape c / nwin / nb).
 static int msm_accumulate_phase(ozk_ctx* ctx, const MsmLaunch& L, const BaseSrc& src, size_t n, const MsmShape& sh, int aff_slot, int bkt_slot,
@@ -389,10 +414,17 @@ static int msm_accumulate_phase(ozk_ctx* ctx, const MsmLaunch& L, const BaseSrc&
     OZK_CUDA(cudaEventRecord(ctx->evs[1], st));
     const void* aff = src.affine;
     if (!aff) {
-        OZK_TRY(ctx->msm[aff_slot].reserve(n * L.affine_bytes, st));
-        if (L.convert(st, src.wire, ctx->msm[aff_slot].p, n, misc, ctx->sm_count)) { set_error("msm: convert launch failed"); return OZK_ERR_CUDA; }
+        const int group_bit = aff_slot == B_AFF2 ? 1 : 0;
+        if (ctx->conv_forked & (1 << group_bit)) {
+            // converted on the side stream while the sort ran (msm_convert_fork): join
+            OZK_CUDA(cudaStreamWaitEvent(st, ctx->copy_ev[kCopyChunks + 1 + group_bit], 0));
+            ctx->conv_forked &= ~(1 << group_bit);
+        } else {
+            OZK_TRY(ctx->msm[aff_slot].reserve(n * L.affine_bytes, st));
+            if (L.convert(st, src.wire, ctx->msm[aff_slot].p, n, misc, ctx->sm_count)) { set_error("msm: convert launch failed"); return OZK_ERR_CUDA; }
+            ctx->launches += 1;
+        }
         aff = ctx->msm[aff_slot].p;
-        ctx->launches += 1;
     }
     OZK_CUDA(cudaEventRecord(ctx->evs[2], st));
     if (sh.ba && &L == &kMsmG1) {
@@ -544,6 +576,9 @@ static int msm_run(ozk_ctx* ctx, const void* d_scalars, BaseSrc s1, BaseSrc s2, 
     for (size_t lo = 0; lo < n; lo += kDevSliceLen) {
         const size_t len = std::min(kDevSliceLen, n - lo);
         sh = msm_shape(n, len);
+        ctx->conv_forked = 0;
+        if (s1.wire) OZK_TRY(msm_convert_fork(ctx, kMsmG1, BaseSrc{(const char*)s1.wire + lo * kMsmG1.jac_bytes, nullptr}, len, B_AFF1, 0));
+        if (s2.wire) OZK_TRY(msm_convert_fork(ctx, kMsmG2, BaseSrc{(const char*)s2.wire + lo * kMsmG2.jac_bytes, nullptr}, len, B_AFF2, 1));
         OZK_TRY(msm_sort(ctx, (const char*)d_scalars + lo * 32, len, sh));
         if (s1.any()) {
             BaseSrc b = {s1.wire ? (const char*)s1.wire + lo * kMsmG1.jac_bytes : nullptr, s1.affine ? (const char*)s1.affine + lo * kMsmG1.affine_bytes : nullptr};
@@ -658,6 +693,9 @@ static int msm_stream_feed(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* 
     OZK_CUDA(cudaStreamWaitEvent(st, ev, 0));
     if (release_host && any_async) OZK_CUDA(cudaEventSynchronize(ev));
     const MsmShape sh = msm_shape(ms.n_total, len);
+    ctx->conv_forked = 0;
+    if (ms.s1.wire) OZK_TRY(msm_convert_fork(ctx, kMsmG1, BaseSrc{(const char*)ms.s1.wire + lo * kMsmG1.jac_bytes, nullptr}, len, B_AFF1, 0));
+    if (ms.s2.wire) OZK_TRY(msm_convert_fork(ctx, kMsmG2, BaseSrc{(const char*)ms.s2.wire + lo * kMsmG2.jac_bytes, nullptr}, len, B_AFF2, 1));
     OZK_TRY(msm_sort(ctx, (char*)ctx->io_a.p + lo * 32, len, sh));
     if (ms.s1.any()) {
         BaseSrc b = {ms.s1.wire ? (const char*)ms.s1.wire + lo * kMsmG1.jac_bytes : nullptr,
