@@ -103,7 +103,8 @@ template <class F> __device__ __noinline__ F field_inv_ni(const F& a) { return F
 // warps per scheduler (242 registers) 18 % of the warp samples of msm_accumulate<Fq2> were "no instruction" stalls at 66 % pipe
 // utilisation (profiles/r2_ncu_full_msm_accumulate_g2.txt).  An Fq2 product is ~700 instructions with three independent
 // carry-chain streams inside, so nothing is lost by not interleaving it with its neighbours -- unlike the 183-instruction Fr
-// product of the NTT butterflies, where the same change cost 14 % (ntt.cu).  OZK_MSM_G2_INLINE=1 runs the inlined kernel.
+// product of the NTT butterflies, where the same change cost 14 % (ntt.cu).  (The inlined G2 kernel and a 168-register, three-CTA
+// build of the called one were measured and removed again: they cost 4 minutes of build time; numbers in msm.cu.)
 template <class F, bool CALLS>
 struct HotOps {
     __device__ __forceinline__ static F mul(const F& a, const F& b) { return F::mul(a, b); }
@@ -226,8 +227,8 @@ __global__ void __launch_bounds__(128) msm_convert_bases(const uint4* __restrict
 // task t >= nbuckets_total: overflow task (bucket, seg), entries [seg*seg_len, ...)     -> ovf_partial[t - nbuckets_total]
 // sorted[w * n + pos] = point index | sign << 31 ; start/count are per (window, bucket), start is window-local.
 // G1: four 128-thread CTAs per SM (<= 128 registers per thread); G2 needs ~240 registers and runs two.
-template <class F, bool CALLS = HotCallsDefault<F>::value, int MINB = (sizeof(F) == 32 ? 4 : 1)>
-__global__ void __launch_bounds__(128, MINB) msm_accumulate(const uint4* __restrict__ bases, const uint32_t* __restrict__ sorted,
+template <class F, bool CALLS = HotCallsDefault<F>::value>
+__global__ void __launch_bounds__(128, sizeof(F) == 32 ? 4 : 1) msm_accumulate(const uint4* __restrict__ bases, const uint32_t* __restrict__ sorted,
                                                       const uint32_t* __restrict__ start, const uint32_t* __restrict__ count,
                                                       const OvfTask* __restrict__ ovf_tasks, const uint32_t* __restrict__ ovf_count,
                                                       const uint32_t* __restrict__ order,
@@ -694,18 +695,6 @@ bool msm_use_smem_accumulate(bool g2);
             msm_accumulate_sm<F><<<grid, 128, smem, s>>>((const uint4*)bases, sorted, start, count, tasks, ovf_count, order, nbt, log_nb, n, \
                                                          seg_len, resume, (uint4*)buckets, (uint4*)ovf_partial);                       \
             return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                                 \
-        }                                                                                                                      \
-        if constexpr (sizeof(F) != 32) {                                                                                       \
-            if (getenv("OZK_MSM_G2_INLINE")) {                                                                                 \
-                msm_accumulate<F, false><<<grid, 128, 0, s>>>((const uint4*)bases, sorted, start, count, tasks, ovf_count, order, nbt, log_nb, n, \
-                                                              seg_len, resume, (uint4*)buckets, (uint4*)ovf_partial);                  \
-                return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                             \
-            }                                                                                                                  \
-            if (getenv("OZK_MSM_G2_3CTA")) {                                                                                   \
-                msm_accumulate<F, true, 3><<<grid, 128, 0, s>>>((const uint4*)bases, sorted, start, count, tasks, ovf_count, order, nbt, log_nb, \
-                                                                n, seg_len, resume, (uint4*)buckets, (uint4*)ovf_partial);             \
-                return cudaGetLastError() == cudaSuccess ? 0 : -1;                                                             \
-            }                                                                                                                  \
         }                                                                                                                      \
         msm_accumulate<F><<<grid, 128, 0, s>>>((const uint4*)bases, sorted, start, count, tasks, ovf_count, order, nbt, log_nb, n, seg_len, \
                                                resume, (uint4*)buckets, (uint4*)ovf_partial);                                          \
