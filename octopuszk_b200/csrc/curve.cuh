@@ -184,7 +184,7 @@ OZK_HD void xyzz_add(XYZZ<F>& acc, const XYZZ<F>& q) {
 // DEPENDENT levels of products, so they are written here once as level schedules over a functor
 //     mul4(A, B, R):  R[i] = A[i] * B[i],  i < 4
 // that the MSM tail kernel implements with the lanes of a warp (msm_impl.cuh, CoopMul4: every lane holds the whole state,
-// lane i computes product i -- for Fq2 three lanes share a product, one Karatsuba term each -- and the results are
+// lane i computes product i -- for Fq2 four lanes share a product, one schoolbook term each -- and the results are
 // broadcast with shuffles), and that tests/host_arith_check.cc runs with a plain loop against the oracle.
 // Infinity is all zeros and stays all zeros through the doubling; the addition handles its special cases explicitly, like
 // xyzz_add (all lanes hold the same values, so those branches are uniform).

@@ -153,6 +153,36 @@ __device__ __forceinline__ void xyzz_madd_hot(XYZZ<F>& acc, const Affine<F>& q) 
     acc.zzz = H::mul(acc.zzz, PPP);
 }
 
+// full addition for the throughput-bound reduction levels, products through HotOps (Fq2: called)
+template <class F, bool CALLS = HotCallsDefault<F>::value>
+__device__ __forceinline__ void xyzz_add_hot(XYZZ<F>& acc, const XYZZ<F>& q) {
+    using H = HotOps<F, CALLS>;
+    if (q.is_inf()) return;
+    if (acc.is_inf()) {
+        acc = q;
+        return;
+    }
+    F U1 = H::mul(acc.x, q.zz);
+    F U2 = H::mul(q.x, acc.zz);
+    F S1 = H::mul(acc.y, q.zzz);
+    F S2 = H::mul(q.y, acc.zzz);
+    F Pp = F::sub(U2, U1);
+    F Rr = F::sub(S2, S1);
+    if (Pp.is_zero()) {
+        if (Rr.is_zero()) xyzz_dbl_ni(acc);
+        else acc = XYZZ<F>::inf();
+        return;
+    }
+    F PP = H::sqr(Pp);
+    F PPP = H::mul(Pp, PP);
+    F Q = H::mul(U1, PP);
+    F X3 = F::sub(F::sub(H::sqr(Rr), PPP), F::dbl(Q));
+    acc.y = H::mul_sub(Rr, F::sub(Q, X3), S1, PPP);
+    acc.x = X3;
+    acc.zz = H::mul(H::mul(acc.zz, q.zz), PP);
+    acc.zzz = H::mul(H::mul(acc.zzz, q.zzz), PPP);
+}
+
 __device__ __forceinline__ Fq canon_one(Fq*) {
     Fq r = Fq::zero();
     r.v[0] = 1;
@@ -499,14 +529,14 @@ __global__ void __launch_bounds__(128) msm_reduce_level(ReduceArgs a) {
     XYZZ<F> q = load_xyzz<F>(jb.in, base + len - 1);
     for (int j = (int)len - 1; j >= 1; j--) {
         XYZZ<F> qn = load_xyzz<F>(jb.in, base + j - 1);
-        xyzz_add(run, q);
+        xyzz_add_hot<F>(run, q);
         if (jb.out_acc) {
             if (j == (int)len - 1) acc = run;          // inf + run: a copy, not an addition (groups of 2 then cost ONE addition)
-            else xyzz_add(acc, run);
+            else xyzz_add_hot<F>(acc, run);
         }
         q = qn;
     }
-    xyzz_add(run, q);
+    xyzz_add_hot<F>(run, q);
     store_xyzz<F>(jb.out_run, (size_t)w * groups + g, run);
     if (jb.out_acc) store_xyzz<F>(jb.out_acc, (size_t)w * groups + g, acc);
 }
@@ -527,8 +557,8 @@ struct FinalArgs {
 
 // mul4 of the level schedules (curve.cuh) over the lanes of one warp.  Every lane holds the same A, B; lane i (mod 4) computes
 // product i and the four results are broadcast back with shuffles, so one level costs ONE product time whatever the number of
-// products.  Fq2: lane 3 i + k (mod 12) computes Karatsuba term k of product i (a0 b0, a1 b1, (a0 + a1)(b0 + b1)) and the terms
-// are combined after the broadcast -- an Fq2 product in the time of one Fq product.  All 32 lanes run the same instructions
+// products.  Fq2: four lanes share a product, one schoolbook term each (below) -- an Fq2 product in the time of one Fq product.
+// All 32 lanes run the same instructions
 // (the upper lanes repeat the work of the lower ones), so the whole warp stays converged and holds identical state.
 template <class F> struct CoopMul4;
 template <> struct CoopMul4<Fq> {
@@ -548,29 +578,33 @@ template <> struct CoopMul4<Fq> {
     }
 };
 template <> struct CoopMul4<Fq2> {
+    // Four lanes per product, schoolbook: lane 4 i + t computes term t of product i (a0 b0, a1 b1, a0 b1, a1 b0); neighbouring
+    // lanes combine their terms with one shuffle exchange (c0 = a0 b0 - a1 b1 in lane t = 0, c1 = a0 b1 + a1 b0 in lane t = 2) BEFORE
+    // the broadcast, so a level costs one Fq product, one Fq addition and 72 shuffles (the three-lane Karatsuba form needed three
+    // subtractions per product after the broadcast: 12 per level, a third of the level's instructions).
     __device__ __forceinline__ void operator()(const Fq2 (&A)[4], const Fq2 (&B)[4], Fq2 (&R)[4]) const {
-        const int idx = (threadIdx.x & 31) % 12;
-        const int i = idx / 3, t = idx - 3 * i;
+        const int lane = threadIdx.x & 15;
+        const int i = lane >> 2, t = lane & 3;
         Fq2 a = A[0], b = B[0];
 #pragma unroll
         for (int k = 1; k < 4; k++) {
             if (i == k) { a = A[k]; b = B[k]; }
         }
-        Fq x = Fq::add(a.c0, a.c1), y = Fq::add(b.c0, b.c1);
-        if (t == 0) { x = a.c0; y = b.c0; }
-        if (t == 1) { x = a.c1; y = b.c1; }
+        const Fq x = (t == 0 || t == 2) ? a.c0 : a.c1;
+        const Fq y = (t == 0 || t == 3) ? b.c0 : b.c1;
         const Fq r = Fq::mul(x, y);
+        Fq o;
+#pragma unroll
+        for (int l = 0; l < 8; l++) o.v[l] = __shfl_xor_sync(0xffffffffu, r.v[l], 1);
+        if (t == 0) o = Fq::neg(o);                       // lanes t = 1, 3 compute values nobody reads
+        const Fq c = Fq::add(r, o);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            Fq v0, v1, v2;
 #pragma unroll
             for (int l = 0; l < 8; l++) {
-                v0.v[l] = __shfl_sync(0xffffffffu, r.v[l], 3 * k);
-                v1.v[l] = __shfl_sync(0xffffffffu, r.v[l], 3 * k + 1);
-                v2.v[l] = __shfl_sync(0xffffffffu, r.v[l], 3 * k + 2);
+                R[k].c0.v[l] = __shfl_sync(0xffffffffu, c.v[l], 4 * k);
+                R[k].c1.v[l] = __shfl_sync(0xffffffffu, c.v[l], 4 * k + 2);
             }
-            R[k].c0 = Fq::sub(v0, v1);
-            R[k].c1 = Fq::sub(Fq::sub(v2, v0), v1);
         }
     }
 };
