@@ -50,6 +50,23 @@ static int env_int(const char* name, int dflt, int lo, int hi) {
     }
     return dflt;
 }
+// ... and up to 2^28 entries (8 GiB per plan) when the device has the memory to spare: at 2^27 the direct table of the first pass
+// takes the transform from 31.1 to 28.8 ms.  Decided from the free device memory when the first plan is made (the plan-cache
+// budget below grows with it: a forward / inverse pair at 2^28 holds 17 GiB of tables); OZK_NTT_DIRECT_LOG overrides.
+static int direct_log_limit() {
+    static const int lim = [] {
+        if (getenv("OZK_NTT_DIRECT_LOG")) return env_int("OZK_NTT_DIRECT_LOG", kDirectLogDefault, 0, 28);
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
+            cudaGetLastError();
+            return kDirectLogDefault;
+        }
+        if (free_b >= ((size_t)96 << 30)) return 28;
+        if (free_b >= ((size_t)48 << 30)) return 27;
+        return kDirectLogDefault;
+    }();
+    return lim;
+}
 static constexpr int kMaxPasses = 4;
 
 struct NttPlan {
@@ -69,9 +86,9 @@ struct NttPlan {
 // The plan cache is bounded: a plan with direct tables is up to 2 GiB per (n, omega), the prover uses four of them per domain,
 // and a JNI host keeps one context per executor thread for the thread's lifetime.  Least-recently-used plans are dropped when
 // a new one would push the context over the budget (OZK_NTT_CACHE_MB, default 16 GiB); a dropped plan is simply rebuilt on its
-// next use (a few ms).
+// next use (a few ms; ~15 ms for the 8 GiB table of a 2^28-point transform).
 static size_t plan_budget_bytes() {
-    static const size_t b = (size_t)env_int("OZK_NTT_CACHE_MB", 16384, 64, 1 << 20) << 20;
+    static const size_t b = (size_t)env_int("OZK_NTT_CACHE_MB", direct_log_limit() >= 28 ? 40960 : direct_log_limit() == 27 ? 24576 : 16384, 64, 1 << 20) << 20;
     return b;
 }
 static unsigned long long g_plan_clock = 0;
@@ -788,7 +805,7 @@ static int ntt_get_plan(ozk_ctx* ctx, int log_n, const uint8_t omega[32], NttPla
         int log_outer = 0;
         for (int j = 0; j + 1 < p->npass; j++) {
             const int range_log = log_n - log_outer;
-            if (range_log <= env_int("OZK_NTT_DIRECT_LOG", kDirectLogDefault, 0, 27)) {
+            if (range_log <= direct_log_limit()) {
                 off_dir[j] = count;
                 dir_log[j] = range_log;
                 count += (size_t)1 << range_log;

@@ -262,6 +262,49 @@ def test_ntt_headline_sizes_device_resident(ctx, log_n):
         assert (b - a) % O.R == pow(omega, j * k, O.R), (log_n, k)
 
 
+@pytest.mark.parametrize("log_n", [27, 28])
+def test_ntt_beyond_headline_direct_tables(ctx, log_n):
+    """2^27 and 2^28 (the 2-adicity of Fr): on a device with memory to spare the first pass reads a direct inter-pass twiddle table
+    of 2^27 / 2^28 entries (ntt.cu, direct_log_limit).  Same exact properties as above, all on the device -- forward, inverse and
+    n^-1 give the input back bit for bit; the response to a unit vector e_j is omega^(jk) at sampled k -- and at 2^27 three outputs
+    against Horner evaluation of the whole input by the C oracle."""
+    import torch
+    n = 1 << log_n
+    free, _total = torch.cuda.mem_get_info()
+    if free < 9 * n * 32:
+        pytest.skip("not enough free device memory for five 2^%d-element vectors, the scratch and the tables" % log_n)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(log_n)
+    x = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device="cuda", generator=g)
+    x[:, 31] &= 0x0F
+    x[:, 0] &= 0xFE
+    omega = O.root_of_unity(n)
+    y = torch.empty_like(x)
+    ctx.ntt_dev(x, y, n, O.le32(omega))
+    back = torch.empty_like(x)
+    ctx.ntt_ex_dev(y, back, n, O.le32(pow(omega, -1, O.R)), None, O.le32(pow(n, -1, O.R)), None)
+    ctx.sync()
+    assert torch.equal(back, x)
+    del back
+    rng = random.Random(log_n)
+    if log_n == 27:
+        from oracle import c_oracle as C
+        ks = [1, n // 2 + 3, rng.randrange(n)]
+        exp = C.fr_horner(x.cpu().numpy(), n, [pow(omega, k, O.R) for k in ks])
+        assert [O.from_le(y[k].cpu().numpy().tobytes()) for k in ks] == exp
+    j = rng.randrange(n)
+    x[j, 0] |= 1                                      # x + e_j, in place
+    y2 = torch.empty_like(x)
+    ctx.ntt_dev(x, y2, n, O.le32(omega))
+    ctx.sync()
+    for k in [0, 1, n - 1, n // 2, j] + [rng.randrange(n) for _ in range(8)]:
+        a = O.from_le(y[k].cpu().numpy().tobytes())
+        b = O.from_le(y2[k].cpu().numpy().tobytes())
+        assert (b - a) % O.R == pow(omega, j * k, O.R), (log_n, k)
+    del x, y, y2
+    torch.cuda.empty_cache()
+
+
 def test_sparse_rows_times_assignment(ctx):
     """ozk_fr_spmv_dev against LinearCombination.evaluate restated: empty rows, single terms, rows at and above the
     one-thread limit (64 terms), one row over all variables (the last constraint of R1CSConstruction.serialConstruct)."""
