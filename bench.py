@@ -305,6 +305,8 @@ def run_ours(args):
     ms_e2e /= e2e_steps
     assert O.G1.equals(O.unpack_g1(out_e2e)[0], expected_local), "bench: e2e MSM result differs from the known answer"
     e2e_value = world * n / (ms_e2e * 1e-3)
+    _st = ctx.msm_last_stats()
+    e2e_first_slice_gbps = _st[10] if len(_st) > 10 else None      # host-link rate the library measured on the first slice (rank 0)
 
     # the same call with the bases uploaded once as a persistent proving-key vector (ozk_bases_upload_g1, untimed, like
     # the reference's proving key they are the same for every proof): only the scalars cross PCIe in the timed region
@@ -471,7 +473,9 @@ def run_ours(args):
                        "answer_check": "global sum == (sum over ranks of sum_i s_i k_i mod r) G on every rank, for value, e2e, keyed and strong legs"},
             "clocks": _clock_summary(samples),
             "e2e": {"value": e2e_value, "unit": "points/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": n * 128,
-                    "d2h_bytes_per_step": 96},
+                    "d2h_bytes_per_step": 96, "first_slice_h2d_GBps": e2e_first_slice_gbps,
+                    "slice_schedule": ("small last slice (host link below 38 GB/s)" if e2e_first_slice_gbps and e2e_first_slice_gbps < 38.0
+                                       else "x1.3 growth")},
             "e2e_resident_key": {"value": world * n / (ms_key * 1e-3), "unit": "points/s", "ms_per_step": ms_key,
                                  "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 96,
                                  "note": "bases uploaded once with ozk_bases_upload_g1 (persistent proving-key vector); scalars from pinned host memory per step"},

@@ -222,8 +222,9 @@ OZK_API int ozk_sum_g1_dev(ozk_ctx* ctx, const void* d_points, size_t k, uint8_t
 OZK_API int ozk_sum_g2_dev(ozk_ctx* ctx, const void* d_points, size_t k, uint8_t out[192]);
 
 /* last MSM on this context: {window bits, windows, buckets per window, overflow tasks, overflow buckets,
- * ms sort, ms convert, ms accumulate, ms merge, ms reduce+final} (device times from events on the context's stream;
- * for the paired call the per-group phases are those of the G2 half) */
+ * ms sort, ms convert, ms accumulate, ms merge, ms reduce+final, GB/s of the first slice's upload in the last whole-array
+ * host-pointer call from pinned memory (what its slice schedule was chosen by)} (device times from events on the context's
+ * stream; for the paired call the per-group phases are those of the G2 half) */
 OZK_API int ozk_msm_last_stats(ozk_ctx* ctx, double* out, int cap);
 
 /* ---- fixed-base batch MSM -----------------------------------------------------------------------------------

@@ -615,6 +615,7 @@ struct MsmStream {
     BaseSrc s1, s2;                 // device sources of the two groups (wire staging or persistent affine)
     bool host1 = false, host2 = false;
     bool first = true;
+    bool time_first = false;        // bracket the uploads of the first slice with the timing events ev0 / ev1 (msm_run_host)
     int slices = 0;
 };
 static MsmStream& stream_of(ozk_ctx* ctx) {
@@ -685,9 +686,12 @@ static int msm_stream_feed(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* 
         any_async = any_async || !host_pointer_is_pageable(src);
         return OZK_OK;
     };
+    const bool timed = ms.time_first && ms.slices == 0;
+    if (timed) OZK_CUDA(cudaEventRecord(ctx->ev0, cs));
     OZK_TRY(upload((char*)ctx->io_a.p + lo * 32, scalars, len * 32));
     if (ms.host1) OZK_TRY(upload((char*)ctx->io_b.p + lo * 96, b1, len * 96));
     if (ms.host2) OZK_TRY(upload((char*)ctx->io_c.p + lo * 192, b2, len * 192));
+    if (timed) OZK_CUDA(cudaEventRecord(ctx->ev1, cs));      // right behind the copies: host time spent below must not count
     cudaEvent_t ev = ctx->copy_ev[ms.slices % kCopyChunks];
     OZK_CUDA(cudaEventRecord(ev, cs));
     OZK_CUDA(cudaStreamWaitEvent(st, ev, 0));
@@ -807,16 +811,54 @@ static int msm_plan_slices(size_t n, size_t* bounds, int cap, bool copy_bound) {
 static int msm_run_host(ozk_ctx* ctx, const uint8_t* scalars, const uint8_t* b1, const uint8_t* b2, BaseSrc s1, BaseSrc s2, size_t n, uint8_t* out) {
     OZK_ARG(n > 0 && n < ((size_t)1 << 31), "msm: between 1 and 2^31 - 1 points per call");
     size_t bounds[kMaxSlices + 1];
-    const int nslices = msm_plan_slices(n, bounds, kMaxSlices, host_pointer_is_pageable(b1 ? b1 : b2 ? b2 : scalars));
+    const bool pageable = host_pointer_is_pageable(b1 ? b1 : b2 ? b2 : scalars);
+    int nslices = msm_plan_slices(n, bounds, kMaxSlices, pageable);
     size_t slice = 0;                                    // the longest slice sizes the per-slice scratch
     for (int k = 0; k < nslices; k++) slice = std::max(slice, bounds[k + 1] - bounds[k]);
     OZK_TRY(msm_stream_begin(ctx, b1 || s1.any(), b2 || s2.any(), n, slice, s1.affine, s2.affine));
+    // Pinned memory: the schedule assumes the full PCIe rate.  When several GPUs share a host link (4 or 8 ranks on one box each
+    // moving 2 GiB per step: ~21 GB/s per GPU instead of ~54) the copies bind and the step ends one last-slice compute after the
+    // last byte, so the rate of the FIRST slice's copy is measured (two events on the copy stream, one host wait of a millisecond
+    // or two that the GPU does not notice) and a slow link switches the remaining slices to the small-last-slice schedule.
+    const bool adaptive = !pageable && nslices == 8 && b1 && !b2 && !getenv("OZK_HOST_SLICES") && !getenv("OZK_HOST_SLICE_GROWTH") &&
+                          !getenv("OZK_HOST_PLAN") && !getenv("OZK_HOST_NO_ADAPT");
     for (int k = 0; k < nslices; k++) {
         const size_t lo = bounds[k], len = bounds[k + 1] - bounds[k];
+        if (adaptive && k == 0) stream_of(ctx).time_first = true;
         int rc = msm_stream_feed(ctx, scalars + lo * 32, b1 ? b1 + lo * 96 : nullptr, b2 ? b2 + lo * 192 : nullptr, len, false);
         if (rc != OZK_OK) {
             stream_of(ctx).active = false;
             return rc;
+        }
+        if (adaptive && k == 0) {
+            float ms = 0;
+            if (cudaEventSynchronize(ctx->ev1) == cudaSuccess && cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess && ms > 0) {
+                const double gbps = (double)len * 128 / (ms * 1e6);
+                ctx->msm_stats[10] = gbps;
+                double slow = 38.0;                                   // GB/s; OZK_HOST_ADAPT_GBPS moves the threshold (tests force the re-plan with it)
+                if (const char* e = getenv("OZK_HOST_ADAPT_GBPS")) slow = atof(e);
+                if (gbps < slow) {
+                    // re-plan what is left: fractions 7, 11, 15, 19, 20, 16, 8 (% of the whole) behind the first slice
+                    static const double rest[7] = {0.07, 0.11, 0.15, 0.19, 0.20, 0.16, 0.08};
+                    double total = 0, acc = 0;
+                    for (double f : rest) total += f;
+                    const size_t left = n - bounds[1];
+                    for (int q = 0; q < 7; q++) {
+                        acc += rest[q] / total;
+                        size_t b = bounds[1] + (((size_t)((double)left * acc) + 255) & ~(size_t)255);
+                        bounds[q + 2] = (q == 6) ? n : std::min(b, n);
+                        if (bounds[q + 2] - bounds[q + 1] > slice) bounds[q + 2] = bounds[q + 1] + slice;   // never beyond the reserved scratch
+                    }
+                    bounds[8] = n;
+                    if (bounds[8] - bounds[7] > slice) {      // (cannot happen with these fractions; keep the invariant anyway)
+                        stream_of(ctx).active = false;
+                        set_error("msm: slice re-plan exceeded the reserved scratch");
+                        return OZK_ERR_ARG;
+                    }
+                }
+            } else {
+                cudaGetLastError();
+            }
         }
     }
     return msm_stream_end(ctx, out);
@@ -1062,7 +1104,7 @@ int ozk_sum_g2_dev(ozk_ctx* ctx, const void* d_points, size_t k, uint8_t out[192
 
 int ozk_msm_last_stats(ozk_ctx* ctx, double* out, int cap) {
     if (!ctx || !out) return 0;
-    int k = cap < 10 ? cap : 10;
+    int k = cap < 11 ? cap : 11;       // [10]: GB/s of the first slice's upload in the last host-pointer call that measured it
     for (int i = 0; i < k; i++) out[i] = ctx->msm_stats[i];
     return k;
 }

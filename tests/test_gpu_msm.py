@@ -442,3 +442,25 @@ def test_smem_accumulate_matches_oracle(ctx, gname, mask, monkeypatch):
     hb = d_b.cpu().numpy()
     out = ctx.msm_g1(raw, hb, n) if G is O.G1 else ctx.msm_g2(raw, hb, n)
     assert G.equals(util.unpack_point(G, out), exp)
+
+
+def test_host_schedule_replan_on_slow_link(ctx, monkeypatch):
+    """The whole-array host entry point measures the rate of its first slice's upload and, on a slow host link, re-plans the
+    remaining slices (small last slice).  Forced here by a threshold no link reaches: same result as the known answer, at a size
+    with eight slices, with a Z per base; the measured rate is reported in the stats."""
+    import torch
+    n = 1 << 22
+    d_b, ks = util.gpu_distinct_bases(ctx, O.G1, n, seed=31, keep_z=True, verify=2)
+    raw = util.force_edge_scalars(util.rand_scalars_full_range(n, seed=32))
+    exp = util.expected_from_dot(O.G1, raw, ks)
+    h_s = torch.from_numpy(raw).pin_memory()
+    h_b = d_b.cpu().pin_memory()
+    del d_b
+    out_plain = ctx.msm_g1(h_s, h_b, n)
+    assert O.G1.equals(O.unpack_g1(out_plain)[0], exp)
+    assert ctx.msm_last_stats()[10] > 1.0                      # GB/s of the first slice: measured
+    monkeypatch.setenv("OZK_HOST_ADAPT_GBPS", "100000")
+    out_replanned = ctx.msm_g1(h_s, h_b, n)
+    assert O.G1.equals(O.unpack_g1(out_replanned)[0], exp)
+    monkeypatch.setenv("OZK_HOST_NO_ADAPT", "1")
+    assert O.G1.equals(O.unpack_g1(ctx.msm_g1(h_s, h_b, n))[0], exp)
