@@ -270,6 +270,7 @@ def test_ntt_beyond_headline_direct_tables(ctx, log_n):
     against Horner evaluation of the whole input by the C oracle."""
     import torch
     n = 1 << log_n
+    torch.cuda.empty_cache()                          # blocks cached by earlier tests count as used otherwise
     free, _total = torch.cuda.mem_get_info()
     if free < 9 * n * 32:
         pytest.skip("not enough free device memory for five 2^%d-element vectors, the scratch and the tables" % log_n)
